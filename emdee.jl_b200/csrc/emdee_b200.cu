@@ -1,0 +1,1113 @@
+// emdee_b200.cu -- host side of libemdee_b200.so: contexts, systems, launch logic and the C ABI
+// declared in include/emdee_b200.h.  sm_100a only; there is no CPU path in this library.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+#include <cmath>
+
+#include "common.cuh"
+#include "binning.cuh"
+#include "force_cells.cuh"
+#include "force_tiles.cuh"
+#include "integrate.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+void emdee_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char *emdee_last_error(void) { return g_err; }
+extern "C" int emdee_version(void) { return 100; }
+
+// ------------------------------------------------------------------------------------------------
+// handles
+// ------------------------------------------------------------------------------------------------
+struct emdee_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t smem_optin = 0, mem_bytes = 0;
+    int64_t launches = 0;
+    int rank = 0, nranks = 1;
+};
+
+struct emdee_system {
+    emdee_ctx *ctx = nullptr;
+    int64_t N = 0;          // global atom count
+    double L = 0;
+    // parameters
+    bool has_model = false, has_atoms = false, has_pos = false, has_vel = false, has_mass = false, has_excl = false;
+    double cutoff = 0, sw = 0, skin = 0;
+    LJModel model{};
+    // per-atom state, ping-pong for the re-ordering gather
+    int64_t cap = 0;
+    AtomArrays A[2];
+    int cur = 0;
+    double *f[3] = {nullptr, nullptr, nullptr}, *en = nullptr, *vir = nullptr;
+    int32_t *gcell[2] = {nullptr, nullptr}, *lcell[2] = {nullptr, nullptr};
+    int32_t *slot_of_id = nullptr;
+    int64_t nlo = 0, nown = 0, nhi = 0;   // lower ghosts, owned, upper ghosts
+    // cell grid
+    bool binned = false, grid_ok = false;
+    int ndiv = 0;
+    GridDesc g{};
+    int64_t ncell = 0, ncell_cap = 0;
+    int32_t *count = nullptr, *cell_start = nullptr, *fill = nullptr, *order = nullptr, *src_of_new = nullptr;
+    int32_t *block_sum = nullptr, *maxpop = nullptr;
+    int64_t steps_since_bin = 0;
+    // force kernel configuration
+    int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
+    size_t fc_smem = 0;
+    double *partial = nullptr;
+    unsigned long long *partial_n = nullptr;
+    int64_t partial_cap = 0;
+    double *totals = nullptr;                 // device {E, W}
+    unsigned long long *digest = nullptr;     // device {count, sum, xor} + pair counter at [3]
+    int *err = nullptr;                       // device error flag
+    int *brick_max = nullptr;
+    // tiles for ALLPAIRS_REFERENCE
+    int32_t *tiles = nullptr;
+    int64_t ntiles = 0;
+    bool tiles_default = true;
+    // results
+    int last_mode = -1, last_bitmask = 0;
+    bool forces_valid = false, kick_pending = false;
+    // scratch for host transfers
+    double *tmp = nullptr;
+    size_t tmp_bytes = 0;
+};
+
+#define LAUNCH_1D(ctx, kernel, n, ...)                                                        \
+    do {                                                                                      \
+        if ((n) > 0) {                                                                        \
+            kernel<<<(unsigned)ceil_div64((n), 256), 256, 0, (ctx)->stream>>>(__VA_ARGS__);   \
+            (ctx)->launches++;                                                                \
+        }                                                                                     \
+    } while (0)
+
+static int check_launch(const char *what)
+{
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) EMDEE_FAIL(EMDEE_ERR_CUDA, "kernel launch %s failed: %s", what, cudaGetErrorString(e));
+    return EMDEE_OK;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    CUDA_TRY(cudaMalloc((void **)p, n * sizeof(T)));
+    return EMDEE_OK;
+}
+template <typename T>
+static void dev_free(T *&p)
+{
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+static int ensure_tmp(emdee_system *s, size_t bytes)
+{
+    if (bytes <= s->tmp_bytes) return EMDEE_OK;
+    dev_free(s->tmp);
+    CUDA_TRY(cudaMalloc((void **)&s->tmp, bytes));
+    s->tmp_bytes = bytes;
+    return EMDEE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+extern "C" int emdee_create(emdee_ctx **out, int device)
+{
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_create: null output pointer");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        EMDEE_FAIL(EMDEE_ERR_CUDA, "emdee_create: no CUDA device (%s); this library has no CPU fallback",
+                   e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_create: device %d out of range [0,%d)", device, ndev);
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        EMDEE_FAIL(EMDEE_ERR_CUDA, "emdee_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                   device, prop.major, prop.minor);
+    CUDA_TRY(cudaSetDevice(device));
+    emdee_ctx *c = new emdee_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc_major = prop.major;
+    c->cc_minor = prop.minor;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    c->mem_bytes = prop.totalGlobalMem;
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&c->ev0));
+    CUDA_TRY(cudaEventCreate(&c->ev1));
+    *out = c;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_destroy(emdee_ctx *c)
+{
+    if (!c) return EMDEE_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_comm_unique_id(char id[128])
+{
+    (void)id;
+    EMDEE_FAIL(EMDEE_ERR_NCCL, "emdee_comm_unique_id: slab decomposition is not built into this library yet");
+}
+extern "C" int emdee_comm_init(emdee_ctx *c, int rank, int nranks, const char id[128])
+{
+    (void)id;
+    if (!c) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_init: null context");
+    if (nranks == 1 && rank == 0) return EMDEE_OK;
+    EMDEE_FAIL(EMDEE_ERR_NCCL, "emdee_comm_init: slab decomposition is not built into this library yet");
+}
+
+extern "C" int emdee_device_info(emdee_ctx *c, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes)
+{
+    if (!c) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_device_info: null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (mem_bytes) *mem_bytes = (int64_t)c->mem_bytes;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_launch_count(emdee_ctx *c, int64_t *n)
+{
+    if (!c || !n) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_launch_count: null argument");
+    *n = c->launches;
+    return EMDEE_OK;
+}
+extern "C" int emdee_timer_start(emdee_ctx *c)
+{
+    if (!c) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_timer_start: null context");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+    return EMDEE_OK;
+}
+extern "C" int emdee_timer_stop(emdee_ctx *c, double *ms)
+{
+    if (!c || !ms) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_timer_stop: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaEventSynchronize(c->ev1));
+    float t = 0;
+    CUDA_TRY(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+    *ms = (double)t;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_measure_fp64_peak(emdee_ctx *c, double *flops_per_s, double *ms_out)
+{
+    if (!c || !flops_per_s) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_measure_fp64_peak: null argument");
+    CUDA_TRY(cudaSetDevice(c->device));
+    double *d = nullptr;
+    EMDEE_TRY(dev_alloc(&d, 1));
+    const int iters = 1 << 15, blocks = c->sm_count * 8, threads = 256;
+    double best = 1e30;
+    for (int rep = 0; rep < 5; rep++) {
+        CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+        k_dfma_peak<<<blocks, threads, 0, c->stream>>>(iters, 1.0 + rep, d);
+        c->launches++;
+        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        CUDA_TRY(cudaEventSynchronize(c->ev1));
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, c->ev0, c->ev1));
+        if (rep > 0) best = std::min(best, (double)t);
+    }
+    dev_free(d);
+    EMDEE_TRY(check_launch("k_dfma_peak"));
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+    *flops_per_s = flops / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return EMDEE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// system
+// ------------------------------------------------------------------------------------------------
+static int alloc_atoms(AtomArrays &A, int64_t cap)
+{
+    for (int c = 0; c < 3; c++) {
+        EMDEE_TRY(dev_alloc(&A.r[c], cap));
+        EMDEE_TRY(dev_alloc(&A.s[c], cap));
+        EMDEE_TRY(dev_alloc(&A.v[c], cap));
+        EMDEE_TRY(dev_alloc(&A.rb[c], cap));
+    }
+    EMDEE_TRY(dev_alloc(&A.hs, cap));
+    EMDEE_TRY(dev_alloc(&A.ts, cap));
+    EMDEE_TRY(dev_alloc(&A.mass, cap));
+    EMDEE_TRY(dev_alloc(&A.id, cap));
+    EMDEE_TRY(dev_alloc(&A.xbase, cap));
+    EMDEE_TRY(dev_alloc(&A.xmask, cap));
+    return EMDEE_OK;
+}
+static void free_atoms(AtomArrays &A)
+{
+    for (int c = 0; c < 3; c++) { dev_free(A.r[c]); dev_free(A.s[c]); dev_free(A.v[c]); dev_free(A.rb[c]); }
+    dev_free(A.hs); dev_free(A.ts); dev_free(A.mass); dev_free(A.id); dev_free(A.xbase); dev_free(A.xmask);
+}
+
+extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_system **out)
+{
+    if (!c || !out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_system_create: null argument");
+    *out = nullptr;
+    if (N <= 0 || N > 0x7fffffff) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_system_create: N=%lld must be in [1, 2^31)", (long long)N);
+    if (!(L > 0) || !std::isfinite(L)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_system_create: L=%g must be positive and finite", L);
+    CUDA_TRY(cudaSetDevice(c->device));
+    emdee_system *s = new emdee_system();
+    s->ctx = c;
+    s->N = N;
+    s->L = L;
+    s->cap = N;
+    s->nown = N;
+    int st = EMDEE_OK;
+    auto A = [&](int rc) { if (st == EMDEE_OK) st = rc; };
+    A(alloc_atoms(s->A[0], s->cap));
+    A(alloc_atoms(s->A[1], s->cap));
+    for (int k = 0; k < 3; k++) A(dev_alloc(&s->f[k], s->cap));
+    A(dev_alloc(&s->en, s->cap));
+    A(dev_alloc(&s->vir, s->cap));
+    for (int k = 0; k < 2; k++) { A(dev_alloc(&s->gcell[k], s->cap)); A(dev_alloc(&s->lcell[k], s->cap)); }
+    A(dev_alloc(&s->slot_of_id, N));
+    A(dev_alloc(&s->order, s->cap));
+    A(dev_alloc(&s->src_of_new, s->cap));
+    A(dev_alloc(&s->totals, 2));
+    A(dev_alloc(&s->digest, 4));
+    A(dev_alloc(&s->err, 1));
+    A(dev_alloc(&s->maxpop, 1));
+    A(dev_alloc(&s->brick_max, 1));
+    if (st != EMDEE_OK) { emdee_system_destroy(s); return st; }
+    // slot == id until the first binning; unit masses; zero velocities; no exclusions
+    LAUNCH_1D(c, k_iota, N, N, s->A[0].id);
+    LAUNCH_1D(c, k_iota, N, N, s->slot_of_id);
+    LAUNCH_1D(c, k_fill<double>, N, N, s->A[0].mass, 1.0);
+    for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(s->A[0].v[k], 0, sizeof(double) * N, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->A[0].xbase, 0, sizeof(int32_t) * N, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->A[0].xmask, 0, sizeof(uint64_t) * N, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+    EMDEE_TRY(check_launch("system init"));
+    *out = s;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_system_destroy(emdee_system *s)
+{
+    if (!s) return EMDEE_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    free_atoms(s->A[0]);
+    free_atoms(s->A[1]);
+    for (int k = 0; k < 3; k++) dev_free(s->f[k]);
+    dev_free(s->en); dev_free(s->vir);
+    for (int k = 0; k < 2; k++) { dev_free(s->gcell[k]); dev_free(s->lcell[k]); }
+    dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
+    dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
+    dev_free(s->partial); dev_free(s->partial_n); dev_free(s->totals); dev_free(s->digest);
+    dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
+    delete s;
+    return EMDEE_OK;
+}
+
+#define SYS_ENTER(s, name)                                                            \
+    if (!(s)) EMDEE_FAIL(EMDEE_ERR_INVALID, name ": null system");                    \
+    emdee_ctx *c = (s)->ctx;                                                          \
+    CUDA_TRY(cudaSetDevice(c->device));                                               \
+    AtomArrays &A = (s)->A[(s)->cur];                                                 \
+    (void)A;                                                                          \
+    const int64_t ntot = (s)->nlo + (s)->nown + (s)->nhi;                             \
+    (void)ntot;
+
+extern "C" int emdee_set_model(emdee_system *s, double cutoff, double sw)
+{
+    SYS_ENTER(s, "emdee_set_model");
+    if (!(sw > 0) || !(cutoff > sw) || !std::isfinite(cutoff))
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_model: need 0 < switch (%g) < cutoff (%g)", sw, cutoff);
+    if (cutoff > 0.5 * s->L)
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_model: cutoff %g exceeds L/2 = %g (minimum image invalid)", cutoff, 0.5 * s->L);
+    // LennardJonesModel(cutoff, switch) = new(cutoff^2, switch^2, 1/(cutoff^2 - switch^2)), src/lennard_jones.jl:10
+    s->cutoff = cutoff;
+    s->sw = sw;
+    s->model.rc2 = cutoff * cutoff;
+    s->model.rs2 = sw * sw;
+    s->model.id2 = 1.0 / (cutoff * cutoff - sw * sw);
+    s->has_model = true;
+    s->forces_valid = false;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_set_skin(emdee_system *s, double skin)
+{
+    SYS_ENTER(s, "emdee_set_skin");
+    if (!(skin >= 0) || !std::isfinite(skin)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_skin: skin=%g must be >= 0", skin);
+    s->skin = skin;
+    s->binned = false;
+    return EMDEE_OK;
+}
+
+static int upload(emdee_system *s, const void *host, size_t bytes)
+{
+    EMDEE_TRY(ensure_tmp(s, bytes));
+    CUDA_TRY(cudaMemcpyAsync(s->tmp, host, bytes, cudaMemcpyHostToDevice, s->ctx->stream));
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_set_lj_atoms(emdee_system *s, const double *atoms)
+{
+    SYS_ENTER(s, "emdee_set_lj_atoms");
+    if (!atoms) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_lj_atoms: null array");
+    EMDEE_TRY(upload(s, atoms, sizeof(double) * 2 * s->N));
+    LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 2, 0, A.hs);
+    LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 2, 1, A.ts);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->has_atoms = true;
+    s->forces_valid = false;
+    return check_launch("set_lj_atoms");
+}
+
+extern "C" int emdee_set_positions(emdee_system *s, const double *pos)
+{
+    SYS_ENTER(s, "emdee_set_positions");
+    if (!pos) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions: null array");
+    EMDEE_TRY(upload(s, pos, sizeof(double) * 3 * s->N));
+    LAUNCH_1D(c, k_set3, ntot, 0, ntot, A.id, s->tmp, A.r[0], A.r[1], A.r[2]);
+    LAUNCH_1D(c, k_scale_positions, ntot, ntot, A.r[0], A.r[1], A.r[2], s->L, A.s[0], A.s[1], A.s[2]);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->has_pos = true;
+    s->binned = false;        // cells must be rebuilt (update_cells!, src/cells.jl:196)
+    s->forces_valid = false;
+    s->kick_pending = false;
+    return check_launch("set_positions");
+}
+
+extern "C" int emdee_set_velocities(emdee_system *s, const double *vel)
+{
+    SYS_ENTER(s, "emdee_set_velocities");
+    if (!vel) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_velocities: null array");
+    EMDEE_TRY(upload(s, vel, sizeof(double) * 3 * s->N));
+    LAUNCH_1D(c, k_set3, ntot, 0, ntot, A.id, s->tmp, A.v[0], A.v[1], A.v[2]);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->has_vel = true;
+    s->kick_pending = false;
+    return check_launch("set_velocities");
+}
+
+extern "C" int emdee_set_masses(emdee_system *s, const double *mass)
+{
+    SYS_ENTER(s, "emdee_set_masses");
+    if (!mass) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_masses: null array");
+    for (int64_t i = 0; i < s->N; i++)
+        if (!(mass[i] > 0)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_masses: mass[%lld]=%g must be positive", (long long)i, mass[i]);
+    EMDEE_TRY(upload(s, mass, sizeof(double) * s->N));
+    LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 1, 0, A.mass);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->has_mass = true;
+    return check_launch("set_masses");
+}
+
+extern "C" int emdee_set_exclusions(emdee_system *s, const int32_t *base, const uint64_t *mask)
+{
+    SYS_ENTER(s, "emdee_set_exclusions");
+    if (!base || !mask) {
+        s->has_excl = false;
+        s->forces_valid = false;
+        return EMDEE_OK;
+    }
+    EMDEE_TRY(upload(s, base, sizeof(int32_t) * s->N));
+    LAUNCH_1D(c, k_set1<int32_t>, ntot, 0, ntot, A.id, (const int32_t *)s->tmp, 1, 0, A.xbase);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EMDEE_TRY(upload(s, mask, sizeof(uint64_t) * s->N));
+    LAUNCH_1D(c, k_set1<uint64_t>, ntot, 0, ntot, A.id, (const uint64_t *)s->tmp, 1, 0, A.xmask);
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->has_excl = true;
+    s->forces_valid = false;
+    return check_launch("set_exclusions");
+}
+
+extern "C" int emdee_set_tiles(emdee_system *s, const int32_t *tiles, int64_t ntiles)
+{
+    SYS_ENTER(s, "emdee_set_tiles");
+    dev_free(s->tiles);
+    s->ntiles = 0;
+    s->tiles_default = true;
+    if (!tiles) return EMDEE_OK;
+    if (ntiles < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_tiles: negative tile count");
+    const int64_t nb = (s->N + 31) / 32;
+    for (int64_t t = 0; t < ntiles; t++)
+        if (tiles[2 * t] < 1 || tiles[2 * t] > nb || tiles[2 * t + 1] < 1 || tiles[2 * t + 1] > nb)
+            EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_tiles: tile %lld = (%d,%d) outside [1,%lld]", (long long)t,
+                       tiles[2 * t], tiles[2 * t + 1], (long long)nb);
+    EMDEE_TRY(dev_alloc(&s->tiles, (size_t)2 * ntiles));
+    CUDA_TRY(cudaMemcpy(s->tiles, tiles, sizeof(int32_t) * 2 * ntiles, cudaMemcpyHostToDevice));
+    s->ntiles = ntiles;
+    s->tiles_default = false;
+    return EMDEE_OK;
+}
+
+// nonbonded_computation_tiles(N): n = cld(N,32); for i=0:n-1, j=1:n-i -> (j, j+i), src/nonbonded.jl:18-26
+static int default_tiles(emdee_system *s)
+{
+    const int64_t n = (s->N + 31) / 32, nt = n * (n + 1) / 2;
+    if (nt > (int64_t)1 << 28)
+        EMDEE_FAIL(EMDEE_ERR_CAPACITY, "ALLPAIRS_REFERENCE: N=%lld needs %lld tiles; the all-pairs mode is for small N", (long long)s->N, (long long)nt);
+    std::vector<int32_t> h((size_t)2 * nt);
+    int64_t k = 0;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = 1; j <= n - i; j++) { h[2 * k] = (int32_t)j; h[2 * k + 1] = (int32_t)(j + i); k++; }
+    dev_free(s->tiles);
+    EMDEE_TRY(dev_alloc(&s->tiles, (size_t)2 * nt));
+    CUDA_TRY(cudaMemcpy(s->tiles, h.data(), sizeof(int32_t) * 2 * nt, cudaMemcpyHostToDevice));
+    s->ntiles = nt;
+    return EMDEE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// binning
+// ------------------------------------------------------------------------------------------------
+// max over bricks of the number of atoms in the brick plus its halo (shared-memory sizing)
+__global__ void k_brick_max(GridDesc g, const int32_t *__restrict__ cell_start, int *__restrict__ out)
+{
+    const int b0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b0 >= g.nbx * g.nby * g.nbz) return;
+    int b = b0;
+    const int bxi = b % g.nbx; b /= g.nbx;
+    const int byi = b % g.nby;
+    const int bzi = b / g.nby;
+    const int M = g.M, R = g.R;
+    const int hx0 = bxi * g.bx, hy0 = byi * g.by, hz0 = g.zhome0 + bzi * g.bz;
+    const int nhx = min(g.bx, M - hx0), nhy = min(g.by, M - hy0), nhz = min(g.bz, g.zhome0 + g.nzhome - hz0);
+    int total = 0;
+    for (int cz = 0; cz < nhz + 2 * R; cz++)
+        for (int cy = 0; cy < nhy + 2 * R; cy++) {
+            int lz = hz0 - R + cz;
+            if (g.zwrap) lz = wrap_mod(lz, M);
+            const int gy = wrap_mod(hy0 - R + cy, M);
+            for (int cx = 0; cx < nhx + 2 * R; cx++) {
+                const int lc = wrap_mod(hx0 - R + cx, M) + M * (gy + M * lz);
+                total += cell_start[lc + 1] - cell_start[lc];
+            }
+        }
+    atomicMax(out, total);
+}
+
+static int exclusive_scan(emdee_system *s, int32_t *data, int64_t n, int32_t *maxval)
+{
+    emdee_ctx *c = s->ctx;
+    const int64_t per = SCAN_BLOCK * SCAN_ITEMS;
+    const int64_t nb = ceil_div64(n, per);
+    if (nb > per) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "exclusive_scan: %lld entries exceed the two-level scan", (long long)n);
+    k_scan_block<<<(unsigned)nb, SCAN_BLOCK, 0, c->stream>>>(data, data, n, s->block_sum, maxval);
+    c->launches++;
+    if (nb > 1) {
+        k_scan_block<<<1, SCAN_BLOCK, 0, c->stream>>>(s->block_sum, s->block_sum, nb, nullptr, nullptr);
+        c->launches++;
+        LAUNCH_1D(c, k_scan_add, n, data, n, s->block_sum);
+    }
+    return check_launch("exclusive_scan");
+}
+
+static int choose_bricks(emdee_system *s)
+{
+    emdee_ctx *c = s->ctx;
+    GridDesc &g = s->g;
+    const int R = g.R, M = g.M;
+    static const int shapes[][3] = {{4, 4, 2}, {4, 2, 2}, {2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+    int forced[3] = {0, 0, 0};
+    if (const char *e = getenv("EMDEE_BRICK")) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
+    int block = 256;
+    if (const char *e = getenv("EMDEE_BLOCK")) block = atoi(e) == 128 ? 128 : 256;
+    const size_t budget2 = (c->smem_optin + 1024) / 2 - 1024;   // two blocks per SM (1 KB reserved per block)
+    int best = -1;
+    int best_cap = 0;
+    size_t best_smem = 0;
+    const int nshape = forced[0] > 0 ? 1 : (int)(sizeof(shapes) / sizeof(shapes[0]));
+    for (int pass = 0; pass < 2 && best < 0; pass++) {
+        const size_t budget = pass == 0 ? budget2 : c->smem_optin;
+        for (int k = 0; k < nshape; k++) {
+            const int *sh = forced[0] > 0 ? forced : shapes[k];
+            g.bx = std::max(1, std::min(sh[0], M - 2 * R));
+            g.by = std::max(1, std::min(sh[1], M - 2 * R));
+            g.bz = std::max(1, std::min(sh[2], g.zwrap ? M - 2 * R : g.nzhome));
+            if (g.by * g.bz > FC_MAX_HOMEROWS) continue;
+            g.nbx = (M + g.bx - 1) / g.bx;
+            g.nby = (M + g.by - 1) / g.by;
+            g.nbz = (g.nzhome + g.bz - 1) / g.bz;
+            CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
+            const int nb = g.nbx * g.nby * g.nbz;
+            LAUNCH_1D(c, k_brick_max, (int64_t)nb, g, s->cell_start, s->brick_max);
+            int mx = 0;
+            CUDA_TRY(cudaMemcpyAsync(&mx, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const int cap = std::max(64, (mx + 1) & ~1);
+            const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
+            const size_t smem = fc_smem_bytes(cap, ncs, block);
+            if (cap <= 65535 && smem <= budget) {
+                best = k; best_cap = cap; best_smem = smem;
+                s->fc_ncs = ncs;
+                s->fc_nblocks = nb;
+                break;
+            }
+        }
+    }
+    if (best < 0) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: no brick shape fits shared memory (cells too populated); use a larger ndiv");
+    s->fc_cap = best_cap;
+    s->fc_smem = best_smem;
+    s->fc_block = block;
+    if ((int64_t)s->fc_nblocks > s->partial_cap) {
+        dev_free(s->partial); dev_free(s->partial_n);
+        s->partial_cap = s->fc_nblocks;
+        EMDEE_TRY(dev_alloc(&s->partial, (size_t)2 * s->partial_cap));
+        EMDEE_TRY(dev_alloc(&s->partial_n, (size_t)s->partial_cap));
+    }
+    return EMDEE_OK;
+}
+
+static int do_bin(emdee_system *s, int ndiv)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    // cells_per_dimension(L, cutoff, ndiv) = floor(Int32, ndiv*L/cutoff), src/cells.jl:36 (cutoff + skin here)
+    const double Mf = std::floor((double)ndiv * s->L / (s->cutoff + s->skin));
+    if (!(Mf >= 1) || Mf > 2000) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: M=%g cells per dimension out of range", Mf);
+    const int M = (int)Mf;
+    GridDesc &g = s->g;
+    g.M = M;
+    g.R = ndiv;
+    g.zwrap = 1;
+    g.nzt = M;
+    g.zhome0 = 0;
+    g.nzhome = M;
+    g.zglob0 = 0;
+    s->ndiv = ndiv;
+    s->grid_ok = (M >= 2 * g.R + 1);   // otherwise a neighbourhood would hold a cell twice
+    s->ncell = (int64_t)M * M * g.nzt;
+    if (s->ncell + 1 > s->ncell_cap) {
+        dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
+        s->ncell_cap = s->ncell + 1;
+        EMDEE_TRY(dev_alloc(&s->count, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->cell_start, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->fill, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->block_sum, (size_t)ceil_div64(s->ncell_cap, SCAN_BLOCK * SCAN_ITEMS) + 1));
+    }
+    const int64_t n = s->nown;
+    CUDA_TRY(cudaMemsetAsync(s->cell_start, 0, sizeof(int32_t) * (s->ncell + 1), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->fill, 0, sizeof(int32_t) * (s->ncell + 1), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->maxpop, 0, sizeof(int32_t), c->stream));
+    LAUNCH_1D(c, k_cell_index, n, s->nlo, n, A.s[0], A.s[1], A.s[2], M, g.zglob0, g.nzt, g.zwrap, s->gcell[s->cur],
+              s->lcell[s->cur], s->cell_start, s->err);
+    CUDA_TRY(cudaMemcpyAsync(s->count, s->cell_start, sizeof(int32_t) * (s->ncell + 1), cudaMemcpyDeviceToDevice, c->stream));
+    EMDEE_TRY(exclusive_scan(s, s->cell_start, s->ncell + 1, s->maxpop));
+    LAUNCH_1D(c, k_scatter, n, s->nlo, n, s->lcell[s->cur], s->cell_start, s->fill, s->order);
+    LAUNCH_1D(c, k_rank_in_cell, n, s->nlo, n, s->order, s->lcell[s->cur], s->cell_start, A.id, s->src_of_new);
+    GatherArgs ga;
+    ga.pfirst = s->nlo;
+    ga.n = n;
+    ga.src_of_new = s->src_of_new;
+    ga.gcell_old = s->gcell[s->cur];
+    ga.lcell_old = s->lcell[s->cur];
+    ga.in = A;
+    ga.out = s->A[1 - s->cur];
+    ga.gcell_new = s->gcell[1 - s->cur];
+    ga.lcell_new = s->lcell[1 - s->cur];
+    ga.slot_of_id = s->slot_of_id;
+    ga.has_vel = 1;
+    ga.has_excl = 1;
+    LAUNCH_1D(c, k_gather, n, ga);
+    EMDEE_TRY(check_launch("binning"));
+    s->cur = 1 - s->cur;
+    s->binned = true;
+    s->steps_since_bin = 0;
+    s->forces_valid = false;
+    if (s->grid_ok) EMDEE_TRY(choose_bricks(s));
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_bin(emdee_system *s, int ndiv)
+{
+    SYS_ENTER(s, "emdee_bin");
+    if (!s->has_model || !s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: set the model (cutoff) and positions first");
+    if (ndiv < 1 || ndiv > 4) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: ndiv=%d must be in [1,4]", ndiv);
+    if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: a velocity-Verlet step is half-finished");
+    return do_bin(s, ndiv);
+}
+
+extern "C" int emdee_get_cells_per_dimension(emdee_system *s, int32_t *M)
+{
+    SYS_ENTER(s, "emdee_get_cells_per_dimension");
+    if (!s->binned || !M) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_cells_per_dimension: call emdee_bin first");
+    *M = s->g.M;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_get_cell_index(emdee_system *s, int32_t *index)
+{
+    SYS_ENTER(s, "emdee_get_cell_index");
+    if (!s->binned || !index) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_cell_index: call emdee_bin first");
+    EMDEE_TRY(ensure_tmp(s, sizeof(int32_t) * s->N));
+    CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(int32_t) * s->N, c->stream));
+    // the reference's index is 1-based (src/cells.jl:85)
+    LAUNCH_1D(c, k_get1<int32_t>, s->nown, s->nlo, s->nown, A.id, s->gcell[s->cur], (int32_t *)s->tmp, (int32_t)1);
+    CUDA_TRY(cudaMemcpyAsync(index, s->tmp, sizeof(int32_t) * s->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_launch("get_cell_index");
+}
+
+extern "C" int emdee_get_cell_population(emdee_system *s, int32_t *pop)
+{
+    SYS_ENTER(s, "emdee_get_cell_population");
+    if (!s->binned || !pop) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_cell_population: call emdee_bin first");
+    const int64_t plane = (int64_t)s->g.M * s->g.M;
+    CUDA_TRY(cudaMemcpyAsync(pop, s->count + plane * s->g.zhome0, sizeof(int32_t) * plane * s->g.nzhome,
+                             cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_get_cell_order(emdee_system *s, int32_t *perm, int32_t *cell_start)
+{
+    SYS_ENTER(s, "emdee_get_cell_order");
+    if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_cell_order: call emdee_bin first");
+    if (perm) CUDA_TRY(cudaMemcpyAsync(perm, A.id + s->nlo, sizeof(int32_t) * s->nown, cudaMemcpyDeviceToHost, c->stream));
+    if (cell_start) {
+        const int64_t plane = (int64_t)s->g.M * s->g.M;
+        CUDA_TRY(cudaMemcpyAsync(cell_start, s->cell_start + plane * s->g.zhome0, sizeof(int32_t) * (plane * s->g.nzhome + 1),
+                                 cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_get_local_count(emdee_system *s, int64_t *nlocal, int64_t *nghost)
+{
+    SYS_ENTER(s, "emdee_get_local_count");
+    if (nlocal) *nlocal = s->nown;
+    if (nghost) *nghost = s->nlo + s->nhi;
+    return EMDEE_OK;
+}
+extern "C" int emdee_get_local_ids(emdee_system *s, int32_t *ids)
+{
+    SYS_ENTER(s, "emdee_get_local_ids");
+    if (!ids) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_local_ids: null array");
+    CUDA_TRY(cudaMemcpyAsync(ids, A.id + s->nlo, sizeof(int32_t) * s->nown, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return EMDEE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// force evaluation
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK, bool F, bool EW, bool EXCL, bool AUDIT>
+static int launch_cells_t(emdee_system *s, const CellArgs &a)
+{
+    auto kern = k_force_cells<BLOCK, F, EW, EXCL, AUDIT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fc_smem));
+    kern<<<s->fc_nblocks, BLOCK, s->fc_smem, s->ctx->stream>>>(a);
+    s->ctx->launches++;
+    return check_launch("k_force_cells");
+}
+template <int BLOCK>
+static int launch_cells_b(emdee_system *s, const CellArgs &a, bool F, bool EW, bool EXCL, bool AUDIT)
+{
+    if (AUDIT) return EXCL ? launch_cells_t<BLOCK, true, true, true, true>(s, a) : launch_cells_t<BLOCK, true, true, false, true>(s, a);
+    if (EXCL) {
+        if (F && EW) return launch_cells_t<BLOCK, true, true, true, false>(s, a);
+        if (F) return launch_cells_t<BLOCK, true, false, true, false>(s, a);
+        return launch_cells_t<BLOCK, false, true, true, false>(s, a);
+    }
+    if (F && EW) return launch_cells_t<BLOCK, true, true, false, false>(s, a);
+    if (F) return launch_cells_t<BLOCK, true, false, false, false>(s, a);
+    return launch_cells_t<BLOCK, false, true, false, false>(s, a);
+}
+
+static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    CellArgs a;
+    a.g = s->g;
+    a.cell_start = s->cell_start;
+    a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2];
+    a.hs = A.hs; a.ts = A.ts;
+    a.id = A.id; a.xbase = A.xbase; a.xmask = A.xmask;
+    a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2];
+    a.en = s->en; a.vir = s->vir;
+    a.partial = s->partial;
+    a.partial_n = s->partial_n;
+    a.digest = s->digest;
+    a.pairs = pairs;
+    a.pair_cap = pair_cap;
+    a.pair_n = s->digest + 3;
+    a.L = s->L;
+    a.cell_edge = s->L / s->g.M;
+    a.model = s->model;
+    a.rc2f = (float)(s->model.rc2 * (1.0 + 1e-3));
+    a.cap = s->fc_cap;
+    a.ncs_max = s->fc_ncs;
+    a.err = s->err;
+    const bool F = (bitmask & EMDEE_FORCES) != 0;
+    const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0 || !F;
+    if (audit) CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
+    if (s->fc_block == 128)
+        EMDEE_TRY(launch_cells_b<128>(s, a, F, EW, s->has_excl, audit));
+    else
+        EMDEE_TRY(launch_cells_b<256>(s, a, F, EW, s->has_excl, audit));
+    if (EW || audit) {
+        k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks, s->partial, s->totals);
+        c->launches++;
+    }
+    return check_launch("k_reduce_partials");
+}
+
+template <bool CULL, bool EXCL>
+static int launch_tiles_t(emdee_system *s, const TileArgs &a, int bitmask)
+{
+    const unsigned grid = (unsigned)ceil_div64(a.ntiles, 4);
+    const bool F = bitmask & EMDEE_FORCES, E = bitmask & EMDEE_ENERGIES, W = bitmask & EMDEE_VIRIALS;
+#define TILE_CASE(f, e, w) \
+    if (F == f && E == e && W == w) k_force_tiles<f, e, w, CULL, EXCL><<<grid, 128, 0, s->ctx->stream>>>(a);
+    TILE_CASE(true, true, true) TILE_CASE(true, true, false) TILE_CASE(true, false, true) TILE_CASE(true, false, false)
+    TILE_CASE(false, true, true) TILE_CASE(false, true, false) TILE_CASE(false, false, true)
+#undef TILE_CASE
+    s->ctx->launches++;
+    return check_launch("k_force_tiles");
+}
+
+static int run_tiles(emdee_system *s, int bitmask, bool cull)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    if (s->tiles_default && s->ntiles == 0) EMDEE_TRY(default_tiles(s));
+    const int64_t n = s->nown;
+    // compute_nonbonded! zeroes the selected outputs, then accumulates with atomics (src/nonbonded.jl:112-114)
+    if (bitmask & EMDEE_FORCES) for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(s->f[k], 0, sizeof(double) * n, c->stream));
+    if (bitmask & EMDEE_ENERGIES) CUDA_TRY(cudaMemsetAsync(s->en, 0, sizeof(double) * n, c->stream));
+    if (bitmask & EMDEE_VIRIALS) CUDA_TRY(cudaMemsetAsync(s->vir, 0, sizeof(double) * n, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
+    TileArgs a;
+    a.tiles = s->tiles; a.ntiles = s->ntiles; a.N = s->N;
+    a.slot_of_id = s->slot_of_id;
+    a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2]; a.hs = A.hs; a.ts = A.ts;
+    a.id = A.id; a.xbase = A.xbase; a.xmask = A.xmask;
+    a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2]; a.en = s->en; a.vir = s->vir;
+    a.pair_count = s->digest;
+    a.L = s->L;
+    a.model = s->model;
+    if (cull) return s->has_excl ? launch_tiles_t<true, true>(s, a, bitmask) : launch_tiles_t<true, false>(s, a, bitmask);
+    return s->has_excl ? launch_tiles_t<false, true>(s, a, bitmask) : launch_tiles_t<false, false>(s, a, bitmask);
+}
+
+static int check_device_flag(emdee_system *s, const char *where)
+{
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, s->ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->ctx->stream));
+    if (flag) {
+        CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), s->ctx->stream));
+        if (flag == 3) EMDEE_FAIL(EMDEE_ERR_SKIN, "%s: an atom moved more than skin/2 since the last binning; re-bin more often or raise the skin", where);
+        if (flag == 2) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: a brick overflowed its shared-memory staging area", where);
+        EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
+    }
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_compute_nonbonded(emdee_system *s, int mode, int bitmask)
+{
+    SYS_ENTER(s, "emdee_compute_nonbonded");
+    if (!s->has_model || !s->has_atoms || !s->has_pos)
+        EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: set model, LJ atoms and positions first");
+    if ((bitmask & 7) == 0 || (bitmask & ~7)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded: bitmask %d must combine FORCES|ENERGIES|VIRIALS", bitmask);
+    if (mode == EMDEE_ALLPAIRS_REFERENCE) {
+        EMDEE_TRY(run_tiles(s, bitmask, false));
+    } else if (mode == EMDEE_CUTOFF) {
+        if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: EMDEE_CUTOFF needs emdee_bin after the last emdee_set_positions");
+        if (s->grid_ok)
+            EMDEE_TRY(run_cells(s, bitmask, false, nullptr, 0));
+        else {
+            if (!s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: box too small for a cell grid and a custom tile list is set");
+            EMDEE_TRY(run_tiles(s, bitmask, true));
+        }
+    } else
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded: unknown mode %d", mode);
+    s->last_mode = mode;
+    s->last_bitmask = bitmask;
+    s->forces_valid = (bitmask & EMDEE_FORCES) != 0;
+    return EMDEE_OK;
+}
+
+static int get3(emdee_system *s, double *const src[3], double *out, const char *what)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: null array", what);
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * s->N));
+    if (s->nown != s->N) CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * 3 * s->N, c->stream));
+    LAUNCH_1D(c, k_get3, s->nown, s->nlo, s->nown, A.id, src[0], src[1], src[2], s->tmp);
+    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * 3 * s->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_launch(what);
+}
+static int get1(emdee_system *s, const double *src, double *out, const char *what)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: null array", what);
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * s->N));
+    if (s->nown != s->N) CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * s->N, c->stream));
+    LAUNCH_1D(c, k_get1<double>, s->nown, s->nlo, s->nown, A.id, src, s->tmp, 0.0);
+    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * s->N, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_launch(what);
+}
+
+extern "C" int emdee_get_positions(emdee_system *s, double *out)
+{
+    SYS_ENTER(s, "emdee_get_positions");
+    if (!s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_positions: positions were never set");
+    return get3(s, A.r, out, "emdee_get_positions");
+}
+extern "C" int emdee_get_velocities(emdee_system *s, double *out)
+{
+    SYS_ENTER(s, "emdee_get_velocities");
+    return get3(s, A.v, out, "emdee_get_velocities");
+}
+extern "C" int emdee_get_forces(emdee_system *s, double *out)
+{
+    SYS_ENTER(s, "emdee_get_forces");
+    if (!(s->last_bitmask & EMDEE_FORCES)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_forces: the last compute did not select FORCES");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_forces"));
+    return get3(s, s->f, out, "emdee_get_forces");
+}
+extern "C" int emdee_get_energies(emdee_system *s, double *out)
+{
+    SYS_ENTER(s, "emdee_get_energies");
+    if (!(s->last_bitmask & EMDEE_ENERGIES)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_energies: the last compute did not select ENERGIES");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_energies"));
+    return get1(s, s->en, out, "emdee_get_energies");
+}
+extern "C" int emdee_get_virials(emdee_system *s, double *out)
+{
+    SYS_ENTER(s, "emdee_get_virials");
+    if (!(s->last_bitmask & EMDEE_VIRIALS)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_virials: the last compute did not select VIRIALS");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_virials"));
+    return get1(s, s->vir, out, "emdee_get_virials");
+}
+
+__global__ void k_sum_ew(int64_t first, int64_t n, const double *__restrict__ en, const double *__restrict__ vir,
+                         int do_e, int do_w, double *__restrict__ partial)
+{
+    __shared__ double sE[256], sW[256];
+    double E = 0, W = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        if (do_e) E += en[first + k];
+        if (do_w) W += vir[first + k];
+    }
+    sE[threadIdx.x] = E; sW[threadIdx.x] = W;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sE[threadIdx.x] += sE[threadIdx.x + o]; sW[threadIdx.x] += sW[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sE[0]; partial[2 * blockIdx.x + 1] = sW[0]; }
+}
+
+extern "C" int emdee_get_totals(emdee_system *s, double *E, double *W, int64_t *npairs)
+{
+    SYS_ENTER(s, "emdee_get_totals");
+    if (s->last_mode < 0) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_totals: nothing has been computed");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_totals"));
+    // per-atom arrays summed in slot order with a fixed tree: deterministic
+    const int nb = 64;
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 2 * nb));
+    k_sum_ew<<<nb, 256, 0, c->stream>>>(s->nlo, s->nown, s->en, s->vir, (s->last_bitmask & EMDEE_ENERGIES) != 0,
+                                        (s->last_bitmask & EMDEE_VIRIALS) != 0, s->tmp);
+    c->launches++;
+    double h[2 * 64];
+    CUDA_TRY(cudaMemcpyAsync(h, s->tmp, sizeof(double) * 2 * nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double e = 0, w = 0;
+    for (int k = 0; k < nb; k++) { e += h[2 * k]; w += h[2 * k + 1]; }
+    if (E) *E = e;
+    if (W) *W = w;
+    if (npairs) {
+        *npairs = -1;
+        if (s->last_mode == EMDEE_CUTOFF) {
+            uint64_t d[3];
+            EMDEE_TRY(emdee_pair_set_digest(s, d));
+            *npairs = (int64_t)d[0];
+        } else
+            *npairs = s->N * (s->N - 1) / 2;
+    }
+    return check_launch("emdee_get_totals");
+}
+
+extern "C" int emdee_pair_set_digest(emdee_system *s, uint64_t out[3])
+{
+    SYS_ENTER(s, "emdee_pair_set_digest");
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_pair_set_digest: null output");
+    if (!s->binned || !s->has_atoms) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: needs LJ atoms, positions and emdee_bin");
+    if (!s->grid_ok) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: box too small for a cell grid (M < 2*ndiv+1)");
+    // the audit pass recomputes forces/energies into the same arrays with the same values
+    EMDEE_TRY(run_cells(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true, nullptr, 0));
+    unsigned long long h[4];
+    CUDA_TRY(cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EMDEE_TRY(check_device_flag(s, "emdee_pair_set_digest"));
+    out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
+    s->last_mode = EMDEE_CUTOFF;
+    s->last_bitmask = 7;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_pair_set(emdee_system *s, int32_t *ij, int64_t cap, int64_t *n)
+{
+    SYS_ENTER(s, "emdee_pair_set");
+    if (!ij || !n || cap < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_pair_set: bad arguments");
+    if (!s->binned || !s->has_atoms) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: needs LJ atoms, positions and emdee_bin");
+    if (!s->grid_ok) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: box too small for a cell grid (M < 2*ndiv+1)");
+    int32_t *d = nullptr;
+    EMDEE_TRY(dev_alloc(&d, (size_t)2 * std::max<int64_t>(cap, 1)));
+    int st = run_cells(s, 7, true, d, cap);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    if (st == EMDEE_OK && cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
+    if (st == EMDEE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
+    if (st == EMDEE_OK) {
+        *n = (int64_t)h[3];
+        const int64_t m = std::min<int64_t>(*n, cap);
+        if (cudaMemcpy(ij, d, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost) != cudaSuccess) st = EMDEE_ERR_CUDA;
+        // lexicographic order (i, j): the device emits pairs in arrival order
+        struct P { int32_t i, j; };
+        P *p = reinterpret_cast<P *>(ij);
+        std::sort(p, p + m, [](const P &x, const P &y) { return x.i != y.i ? x.i < y.i : x.j < y.j; });
+    }
+    dev_free(d);
+    if (st != EMDEE_OK) EMDEE_FAIL(st, "emdee_pair_set: device failure (%s)", cudaGetErrorString(cudaGetLastError()));
+    EMDEE_TRY(check_device_flag(s, "emdee_pair_set"));
+    s->last_mode = EMDEE_CUTOFF;
+    s->last_bitmask = 7;
+    if (*n > cap) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_pair_set: %lld pairs exceed the buffer capacity %lld", (long long)*n, (long long)cap);
+    return EMDEE_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// velocity-Verlet
+// ------------------------------------------------------------------------------------------------
+static int launch_vv(emdee_system *s, double dt, int drift, int check_skin)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    VVArgs a;
+    a.first = s->nlo;
+    a.n = s->nown;
+    for (int k = 0; k < 3; k++) { a.r[k] = A.r[k]; a.s[k] = A.s[k]; a.v[k] = A.v[k]; a.rb[k] = A.rb[k]; a.f[k] = s->f[k]; }
+    a.mass = A.mass;
+    a.dt = dt;
+    a.L = s->L;
+    a.half_skin2 = 0.25 * s->skin * s->skin;
+    a.pending_kick = s->kick_pending ? 1 : 0;
+    a.drift = drift;
+    a.check_skin = check_skin;
+    a.err = s->err;
+    LAUNCH_1D(c, k_vv, a.n, a);
+    return check_launch("k_vv");
+}
+
+extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int rebin_every)
+{
+    SYS_ENTER(s, "emdee_vv_step");
+    if (!s->has_model || !s->has_atoms || !s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: set model, LJ atoms and positions first");
+    if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: call emdee_bin first");
+    if (!s->forces_valid) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: call emdee_compute_nonbonded(EMDEE_CUTOFF, FORCES|...) first");
+    if (s->last_mode != EMDEE_CUTOFF) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: forces must come from EMDEE_CUTOFF mode");
+    if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
+    for (int64_t st = 0; st < nsteps; st++) {
+        const bool rebin = rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every;
+        EMDEE_TRY(launch_vv(s, dt, 1, rebin ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
+        s->kick_pending = false;
+        s->steps_since_bin++;
+        if (rebin) EMDEE_TRY(do_bin(s, s->ndiv));
+        if (s->grid_ok)
+            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0));
+        else
+            EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));
+        s->kick_pending = true;
+    }
+    if (s->kick_pending) {
+        EMDEE_TRY(launch_vv(s, dt, 0, 0));                  // final second half-kick
+        s->kick_pending = false;
+    }
+    s->last_bitmask = EMDEE_FORCES;
+    s->forces_valid = true;
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_kinetic_energy(emdee_system *s, double *K)
+{
+    SYS_ENTER(s, "emdee_kinetic_energy");
+    if (!K) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_kinetic_energy: null output");
+    const int nb = 128;
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * nb));
+    k_kinetic<<<nb, 256, 0, c->stream>>>(s->nlo, s->nown, A.v[0], A.v[1], A.v[2], A.mass, s->tmp);
+    c->launches++;
+    double h[128];
+    CUDA_TRY(cudaMemcpyAsync(h, s->tmp, sizeof(double) * nb, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double k = 0;
+    for (int i = 0; i < nb; i++) k += h[i];
+    *K = k;
+    return check_launch("k_kinetic");
+}
+
+extern "C" int emdee_synchronize(emdee_system *s)
+{
+    SYS_ENTER(s, "emdee_synchronize");
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_device_flag(s, "emdee_synchronize");
+}
+
+// ------------------------------------------------------------------------------------------------
+// one-shot mirror of compute_nonbonded! on host arrays (src/nonbonded.jl:109-120)
+// ------------------------------------------------------------------------------------------------
+extern "C" int emdee_compute_nonbonded_host(int64_t N, const double *pos, double L, double cutoff, double sw,
+                                            const double *atoms, const int32_t *tiles, int64_t ntiles, int mode, int ndiv,
+                                            int bitmask, double *forces, double *energies, double *virials)
+{
+    emdee_ctx *c = nullptr;
+    emdee_system *s = nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    int st = emdee_create(&c, dev);
+    if (st == EMDEE_OK) st = emdee_system_create(c, N, L, &s);
+    if (st == EMDEE_OK) st = emdee_set_model(s, cutoff, sw);
+    if (st == EMDEE_OK) st = emdee_set_lj_atoms(s, atoms);
+    if (st == EMDEE_OK) st = emdee_set_positions(s, pos);
+    if (st == EMDEE_OK && tiles) st = emdee_set_tiles(s, tiles, ntiles);
+    if (st == EMDEE_OK && mode == EMDEE_CUTOFF) st = emdee_bin(s, ndiv);
+    if (st == EMDEE_OK) st = emdee_compute_nonbonded(s, mode, bitmask);
+    if (st == EMDEE_OK && (bitmask & EMDEE_FORCES)) st = emdee_get_forces(s, forces);
+    if (st == EMDEE_OK && (bitmask & EMDEE_ENERGIES)) st = emdee_get_energies(s, energies);
+    if (st == EMDEE_OK && (bitmask & EMDEE_VIRIALS)) st = emdee_get_virials(s, virials);
+    emdee_system_destroy(s);
+    emdee_destroy(c);
+    return st;
+}

@@ -1,0 +1,128 @@
+// integrate.cuh -- velocity-Verlet update and host<->slot-order transfer kernels.
+//
+// The reference has no integrator; the update below is the oracle's definition
+// (oracle_vv_steps):  v += (dt/2m) f ; r += dt v ; f = F(r) ; v += (dt/2m) f,
+// each line one fma so that CPU and GPU round identically per step.
+#pragma once
+#include "common.cuh"
+
+struct VVArgs {
+    int64_t first, n;          // owned slots
+    double *r[3], *s[3], *v[3];
+    const double *rb[3];
+    const double *f[3];
+    const double *mass;
+    double dt, L, half_skin2;  // (skin/2)^2
+    int pending_kick;          // complete the previous step's second half-kick first
+    int drift;                 // 1: kick + drift (+ rescale s), 0: kick only
+    int check_skin;
+    int *err;
+};
+
+// One kernel per step: [second half-kick of step n-1] + first half-kick + drift of step n.
+// Reads r, v, f (+ r_bin for the skin check), writes r, v, s: 120 B/atom-step + 48 B for s and r_bin.
+__global__ void k_vv(VVArgs a)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= a.n) return;
+    const int64_t i = a.first + k;
+    const double h = __ddiv_rn(0.5 * a.dt, a.mass[i]);
+    double d2 = 0;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double f = a.f[c][i];
+        double v = a.v[c][i];
+        if (a.pending_kick) v = __fma_rn(h, f, v);
+        if (a.drift) {
+            v = __fma_rn(h, f, v);
+            const double r = __fma_rn(a.dt, v, a.r[c][i]);
+            a.r[c][i] = r;
+            a.s[c][i] = __ddiv_rn(r, a.L);     // scaled position for the next force evaluation
+            const double d = r - a.rb[c][i];
+            d2 = fma(d, d, d2);
+        }
+        a.v[c][i] = v;
+    }
+    if (a.drift && a.check_skin && d2 > a.half_skin2) atomicExch(a.err, 3);
+}
+
+// K = sum 1/2 m v^2 over owned slots; per-block partials, summed on the host in block order.
+__global__ void k_kinetic(int64_t first, int64_t n, const double *__restrict__ vx, const double *__restrict__ vy,
+                          const double *__restrict__ vz, const double *__restrict__ mass, double *__restrict__ partial)
+{
+    __shared__ double sh[256];
+    double acc = 0;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + k;
+        acc += 0.5 * mass[i] * (vx[i] * vx[i] + vy[i] * vy[i] + vz[i] * vz[i]);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+// host layout (3xN column-major, id order) <-> slot order
+__global__ void k_set3(int64_t first, int64_t n, const int32_t *__restrict__ id, const double *__restrict__ in,
+                       double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    const int64_t g = id[i];
+    d0[i] = in[3 * g]; d1[i] = in[3 * g + 1]; d2[i] = in[3 * g + 2];
+}
+__global__ void k_get3(int64_t first, int64_t n, const int32_t *__restrict__ id, const double *__restrict__ d0,
+                       const double *__restrict__ d1, const double *__restrict__ d2, double *__restrict__ out)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    const int64_t g = id[i];
+    out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
+}
+template <typename T>
+__global__ void k_set1(int64_t first, int64_t n, const int32_t *__restrict__ id, const T *__restrict__ in,
+                       int stride, int off, T *__restrict__ d)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    d[i] = in[(int64_t)stride * id[i] + off];
+}
+template <typename T>
+__global__ void k_get1(int64_t first, int64_t n, const int32_t *__restrict__ id, const T *__restrict__ d,
+                       T *__restrict__ out, T add)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    out[id[i]] = d[i] + add;
+}
+__global__ void k_iota(int64_t n, int32_t *__restrict__ d)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = (int32_t)i;
+}
+template <typename T>
+__global__ void k_fill(int64_t n, T *__restrict__ d, T v)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) d[i] = v;
+}
+
+// FP64 FMA throughput probe: 8 independent dependent-chains per thread, 2 flops per DFMA.
+__global__ void __launch_bounds__(256) k_dfma_peak(int iters, double seed, double *__restrict__ out)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;   // never true; keeps the chains alive
+}

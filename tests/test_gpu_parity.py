@@ -1,0 +1,337 @@
+"""GPU parity tests (-m gpu): the CUDA path through the C ABI against the CPU oracle and the golden
+fixtures.  Bars (BASELINE.json north_star): integer work bit-exact (cell index, population, order,
+pair set), E and W within 1e-10 relative, per-atom forces within 1e-9 of the RMS force."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-10
+F_TOL = 1e-9
+
+
+def frms(f):
+    return np.sqrt((f ** 2).sum(axis=1).mean())
+
+
+def check_efw(got, ref, what=""):
+    f, e, w = got
+    fr, er, wr = ref
+    assert np.abs(f - fr).max() <= F_TOL * frms(fr), what
+    assert abs(e.sum() - er.sum()) <= E_TOL * abs(er.sum()), what
+    assert abs(w.sum() - wr.sum()) <= E_TOL * abs(wr.sum()), what
+    # per-atom energies and virials at the same relative level against their RMS
+    assert np.abs(e - er).max() <= F_TOL * np.sqrt((er ** 2).mean()), what
+    assert np.abs(w - wr).max() <= F_TOL * np.sqrt((wr ** 2).mean()), what
+
+
+def make_system(em, pos, L, rc, rs, atoms):
+    s = em.NonbondedSystem(pos.shape[0], L)
+    s.set_model(em.LennardJonesModel(rc, rs))
+    s.set_atoms(atoms)
+    s.set_positions(pos)
+    return s
+
+
+def test_reference_test_case_allpairs(em, oracle, lj_sample):
+    """Mirror of test_compute_nonbonded (test/runtests.jl:19-42,58) in FP64: tile kernel vs naive loop."""
+    g = lj_sample
+    pos, L = g["positions"], float(g["L"])
+    N = pos.shape[0]
+    model = em.LennardJonesModel(3, 2.5)
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (N, 1))
+    forces_ref = np.zeros((N, 3)); energies_ref = np.zeros(N); virials_ref = np.zeros(N)
+    em.naively_compute_nonbonded_(forces_ref, energies_ref, virials_ref, pos, L, model, atoms)
+    tiles = em.nonbonded_computation_tiles(N)
+    forces = np.zeros((N, 3)); energies = np.zeros(N); virials = np.zeros(N)
+    em.compute_nonbonded_(forces, energies, virials, pos, L, tiles, model, atoms, em.FORCES | em.ENERGIES | em.VIRIALS)
+    # the reference's own criterion ...
+    assert (forces - forces_ref).max() < 1e-4 and (energies - energies_ref).max() < 1e-4 and (virials - virials_ref).max() < 1e-4
+    # ... and the FP64 bar against the oracle / golden vectors
+    ref = (g["allpairs_forces"], g["allpairs_energies"], g["allpairs_virials"])
+    check_efw((forces, energies, virials), ref, "allpairs vs golden")
+    check_efw((forces, energies, virials), oracle.naive_allpairs(pos, L, oracle.lj_model(3.0, 2.5), atoms), "allpairs vs oracle")
+    # Fortran-ordered 3xN outputs, as a Julia caller would hold them
+    fF = np.zeros((3, N), order="F")
+    em.compute_nonbonded_(fF, energies, virials, np.asfortranarray(pos.T), L, tiles, model, atoms, em.FORCES)
+    assert np.abs(fF.T - forces).max() <= F_TOL * frms(forces)
+
+
+@pytest.mark.parametrize("bitmask", [1, 2, 4, 3, 5, 6, 7])
+def test_bitmask_selects_outputs(em, lj_sample, bitmask):
+    g = lj_sample
+    pos = g["positions"][:256]
+    N = pos.shape[0]
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (N, 1))
+    model = em.LennardJonesModel(3, 2.5)
+    full = [np.zeros((N, 3)), np.zeros(N), np.zeros(N)]
+    em.compute_nonbonded_(*full, pos, 10.0, em.nonbonded_computation_tiles(N), model, atoms, 7)
+    out = [np.full((N, 3), 77.0), np.full(N, 77.0), np.full(N, 77.0)]
+    em.compute_nonbonded_(*out, pos, 10.0, em.nonbonded_computation_tiles(N), model, atoms, bitmask)
+    for k, bit in enumerate((1, 2, 4)):
+        if bitmask & bit:
+            assert np.abs(out[k] - full[k]).max() <= 1e-9 * np.abs(full[k]).max()
+        else:
+            assert np.all(out[k] == 77.0)       # unselected outputs untouched (src/nonbonded.jl:112-114)
+
+
+@pytest.mark.parametrize("N", [1, 31, 32, 33, 95, 257])
+def test_allpairs_ragged_sizes(em, oracle, lj_sample, N):
+    """Tail masking: the reference kernel assumes N % 32 == 0."""
+    pos = lj_sample["positions"][:N]
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (N, 1))
+    out = [np.zeros((N, 3)), np.zeros(N), np.zeros(N)]
+    em.compute_nonbonded_(*out, pos, 10.0, em.nonbonded_computation_tiles(N), em.LennardJonesModel(3, 2.5), atoms, 7)
+    ref = oracle.naive_allpairs(pos, 10.0, oracle.lj_model(3.0, 2.5), atoms)
+    if N == 1:
+        assert all(np.all(o == 0) for o in out)
+    else:
+        assert np.abs(out[0] - ref[0]).max() <= F_TOL * max(frms(ref[0]), 1e-300)
+        assert np.abs(out[1] - ref[1]).max() <= 1e-9 * np.abs(ref[1]).max()
+
+
+def test_custom_tile_list(em, oracle, lj_sample):
+    """A caller-supplied tile subset evaluates exactly those tiles (src/nonbonded.jl:50-53)."""
+    pos = lj_sample["positions"][:128]
+    N = 128
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (N, 1))
+    tiles = np.array([[1, 1], [2, 4], [3, 3]], dtype=np.int32)
+    out = [np.zeros((N, 3)), np.zeros(N), np.zeros(N)]
+    em.compute_nonbonded_(*out, pos, 10.0, tiles, em.LennardJonesModel(3, 2.5), atoms, 7)
+    ref = oracle.tiles_allpairs(pos, 10.0, tiles, oracle.lj_model(3.0, 2.5), atoms)
+    check_efw(out, ref)
+    assert np.all(out[0][96:128][:, 0] != 0) and np.all(out[1][64:96] != 0)
+
+
+@pytest.mark.parametrize("ndiv", [1, 2])
+def test_cells_bit_exact(em, oracle, lj_sample, ndiv):
+    """Cells(r, L, cutoff; ndiv): M, index, population, sorted order, linked lists -- all integer, all exact."""
+    g = lj_sample
+    pos = g["positions"]
+    cells = em.Cells(pos, 10.0, 3.0, ndiv=ndiv)
+    M = oracle.cells_per_dimension(10.0, 3.0, ndiv)
+    idx = oracle.cell_index(pos, 10.0, M)
+    assert cells.M == M
+    assert np.array_equal(cells.index, idx) and np.array_equal(cells.index, g["cell_index_ndiv%d" % ndiv])
+    assert np.array_equal(cells.population, np.bincount(idx - 1, minlength=M ** 3))
+    order = np.lexsort((np.arange(800), idx))
+    assert np.array_equal(cells.perm, order)
+    assert np.array_equal(cells.cell_start, np.concatenate(([0], np.cumsum(cells.population))))
+    # distribute! builds lists in descending atom order (src/cells.jl:52-56)
+    head, nxt = cells.head, cells.next
+    for c in (0, 5, M ** 3 - 1):
+        members = []
+        i = head[c]
+        while i != 0:
+            members.append(i)
+            i = nxt[i - 1]
+        assert members == sorted((np.nonzero(idx == c + 1)[0] + 1).tolist(), reverse=True)
+    # update_cells!(cells, y, L) == Cells(y, L, cutoff)   (the reference's disabled test_cells, test/runtests.jl:6-17)
+    y = pos + 0.01
+    em.update_cells_(cells, y, 10.0)
+    fresh = em.Cells(y, 10.0, 3.0, ndiv=ndiv)
+    assert np.array_equal(cells.index, fresh.index) and np.array_equal(cells.population, fresh.population)
+    assert np.array_equal(cells.index, oracle.cell_index(y, 10.0, M))
+
+
+def test_cell_index_edge_cases(em, oracle):
+    """Unwrapped coordinates, exact cell boundaries, and the frac==1.0 overflow."""
+    L, rc = 12.0, 2.0
+    rng = np.random.default_rng(5)
+    pos = rng.uniform(-3 * L, 3 * L, size=(4096, 3))
+    pos[:64] = np.round(pos[:64] / 2.0) * 2.0                  # on cell faces
+    pos[64:70] = [[-1e-18, 0, 0], [0, -1e-300, 5], [L, L, L], [-L, 2 * L, 0.0], [11.999999999999998, 0, 0], [-0.0, 0.0, 0.0]]
+    for ndiv in (1, 2):
+        cells = em.Cells(pos, L, rc, ndiv=ndiv)
+        assert np.array_equal(cells.index, oracle.cell_index(pos, L, cells.M))
+        assert cells.index.min() >= 1 and cells.index.max() <= cells.M ** 3
+
+
+@pytest.mark.parametrize("ndiv", [1, 2])
+def test_cutoff_fixture(em, oracle, lj_sample, ndiv):
+    g = lj_sample
+    pos = g["positions"]
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (800, 1))
+    s = make_system(em, pos, 10.0, 3.0, 2.5, atoms)
+    s.bin(ndiv)
+    s.compute(em.CUTOFF, 7)
+    got = (s.forces(), s.energies(), s.virials())
+    check_efw(got, (g["cutoff_forces"], g["cutoff_energies"], g["cutoff_virials"]), "cutoff vs golden")
+    E, W, npairs = s.totals()
+    assert npairs == 35677
+    assert np.array_equal(s.pair_set_digest(), g["cutoff_digest"])
+    assert np.array_equal(s.pair_set(), g["cutoff_pairs"])          # sorted pair set, bit-exact
+    ref = oracle.cutoff_cells(pos, 10.0, 3.0, 2.5, atoms, ndiv=ndiv)
+    assert abs(E - ref["E"]) <= E_TOL * abs(ref["E"]) and abs(W - ref["W"]) <= E_TOL * abs(ref["W"])
+    # compute_nonbonded! mirror in CUTOFF mode
+    out = [np.zeros((800, 3)), np.zeros(800), np.zeros(800)]
+    em.compute_nonbonded_(*out, pos, 10.0, None, em.LennardJonesModel(3, 2.5), atoms, 7, mode=em.CUTOFF, ndiv=ndiv)
+    check_efw(out, (g["cutoff_forces"], g["cutoff_energies"], g["cutoff_virials"]))
+    s.close()
+
+
+@pytest.mark.parametrize("n,ndiv", [(10, 1), (10, 2), (7, 1), (16, 1), (16, 2)])
+def test_cutoff_fcc(em, oracle, n, ndiv):
+    """BASELINE config 1 (n=10: N=4000, rc=2.5, rho*=0.8442) and neighbours, both cell geometries."""
+    pos, L = em.workloads.fcc_lattice(n)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(ndiv)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=ndiv)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    M = oracle.cells_per_dimension(L, 2.5, ndiv)
+    assert s.cells_per_dimension() == M
+    assert np.array_equal(s.cell_index(), oracle.cell_index(pos, L, M))
+    if N <= 4000:
+        assert np.array_equal(s.pair_set(), oracle.pair_set_cells(pos, L, 2.5, ndiv))
+    s.close()
+
+
+def test_config1_both_modes(em, oracle):
+    """Config 1 checked in ALLPAIRS_REFERENCE mode as well."""
+    pos, L = em.workloads.fcc_lattice(10)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    out = [np.zeros((N, 3)), np.zeros(N), np.zeros(N)]
+    em.compute_nonbonded_(*out, pos, L, em.nonbonded_computation_tiles(N), em.LennardJonesModel(2.5, 2.0), atoms, 7)
+    check_efw(out, oracle.naive_allpairs(pos, L, oracle.lj_model(2.5, 2.0), atoms))
+
+
+def test_mixed_lj_parameters(em, oracle):
+    """Lorentz-Berthelot mixing through (half_sigma, twice_sqrt_eps), src/lennard_jones.jl:29,33."""
+    pos, L = em.workloads.fcc_lattice(8)
+    N = pos.shape[0]
+    rng = np.random.default_rng(11)
+    atoms = np.stack([0.5 * rng.uniform(0.8, 1.1, N), 2.0 * np.sqrt(rng.uniform(0.2, 1.5, N))], axis=1)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    s.close()
+
+
+def test_tiny_box_falls_back_to_tiles(em, oracle, lj_sample):
+    """L/rc < 3: no cell grid without double counting -> culled tile kernel."""
+    pos = lj_sample["positions"][:300] * 0.6
+    L = 6.0
+    atoms = np.tile(em.LennardJonesAtom(1, 1), (300, 1))
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(1)
+    assert s.cells_per_dimension() == 2
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    s.close()
+
+
+def test_exclusions_molecular(em, oracle, dioxin_water):
+    """Config 4 input (1519 atoms): per-type LJ parameters, nm->A, 1-2/1-3 exclusions as a bitmask."""
+    g = dioxin_water
+    pos, L = g["positions"], float(g["box"])
+    N = pos.shape[0]
+    sig = g["type_sigma_nm"][g["type_index"]] * 10.0
+    eps = g["type_epsilon"][g["type_index"]]
+    atoms = np.stack([0.5 * sig, 2.0 * np.sqrt(eps)], axis=1)
+    base, mask = em.workloads.exclusion_masks(N, g["bonds"])
+    s = make_system(em, pos, L, 10.0, 9.0, atoms)
+    s.set_exclusions(base, mask)
+    for ndiv in (1, 2):
+        s.bin(ndiv)
+        s.compute(em.CUTOFF, 7)
+        ref = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=ndiv, excl=(base, mask))
+        check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+        assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    noex = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1)
+    assert noex["npairs"] - ref["npairs"] == sum(bin(int(m)).count("1") for m in mask) // 2
+    s.close()
+
+
+def test_velocity_verlet(em, oracle):
+    pos, L = em.workloads.fcc_lattice(8)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    vel = em.workloads.maxwell_velocities(N, 1.44)
+    mass = np.ones(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.set_velocities(vel)
+    s.set_masses(mass)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES | em.ENERGIES)
+    E0 = s.totals(pairs=False)[0]
+    K0 = s.kinetic_energy()
+    assert K0 == pytest.approx(0.5 * (vel ** 2).sum(), rel=1e-13)
+    f0 = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1)["forces"]
+    nsteps, dt = 20, 0.005
+    s.vv_step(dt, nsteps, rebin_every=1)
+    p, v, f = oracle.vv_steps(pos, vel, f0, mass, L, 2.5, 2.0, atoms, dt, nsteps)
+    # 20 steps: chaotic growth of the 1e-16 summation-order differences stays far below the bars
+    assert np.abs(s.positions() - p).max() <= 1e-10
+    assert np.abs(s.velocities() - v).max() <= 1e-9
+    assert np.abs(s.forces() - f).max() <= 1e-8 * frms(f)
+    # energy conservation over a longer run, with a skin and sparse re-binning
+    s.set_skin(0.4)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(dt, 200, rebin_every=10)
+    s.compute(em.CUTOFF, em.FORCES | em.ENERGIES)
+    E1 = s.totals(pairs=False)[0]
+    K1 = s.kinetic_energy()
+    assert abs((E1 + K1) - (E0 + K0)) / N < 2e-3
+    assert np.abs(s.velocities().sum(axis=0)).max() < 1e-8
+    s.close()
+
+
+def test_skin_violation_is_reported(em):
+    pos, L = em.workloads.fcc_lattice(8)
+    N = pos.shape[0]
+    s = make_system(em, pos, L, 2.5, 2.0, em.workloads.lj_fluid_atoms(N))
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_skin(0.05)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.005, 60, rebin_every=0)         # never re-bins: atoms travel > skin/2
+    with pytest.raises(em.EmDeeError) as ei:
+        s.synchronize()
+    assert ei.value.status == 6
+    s.close()
+
+
+def test_error_conventions(em):
+    with pytest.raises(em.EmDeeError) as ei:
+        em.NonbondedSystem(0, 10.0)
+    assert ei.value.status == 1
+    s = em.NonbondedSystem(64, 10.0)
+    with pytest.raises(em.EmDeeError) as ei:
+        s.set_model(em.LennardJonesModel(6.0, 5.0))          # rc > L/2
+    assert ei.value.status == 1
+    with pytest.raises(em.EmDeeError) as ei:
+        s.compute(em.CUTOFF, 7)                               # nothing set
+    assert ei.value.status == 4
+    s.close()
+
+
+def test_large_system_properties(em, oracle):
+    """BASELINE config 2 size (N=256k): digest and totals against the OpenMP oracle, momentum = 0,
+    ndiv=1 and ndiv=2 agree with each other."""
+    pos, L = em.workloads.fcc_lattice(40)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+    res = {}
+    for ndiv in (1, 2):
+        s = make_system(em, pos, L, 2.5, 2.0, atoms)
+        s.bin(ndiv)
+        s.compute(em.CUTOFF, 7)
+        f = s.forces()
+        E, W, npairs = s.totals()
+        assert np.array_equal(s.pair_set_digest(), ref["digest"]) and npairs == ref["npairs"]
+        assert abs(E - ref["E"]) <= E_TOL * abs(ref["E"]) and abs(W - ref["W"]) <= E_TOL * abs(ref["W"])
+        assert np.abs(f - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+        assert np.abs(f.sum(axis=0)).max() < 1e-8            # Newton's third law over the whole system
+        res[ndiv] = f
+        s.close()
+    assert np.abs(res[1] - res[2]).max() <= F_TOL * frms(res[1])
