@@ -243,6 +243,15 @@ class NonbondedSystem:
     def synchronize(self):
         call("emdee_synchronize", self._h)
 
+    def profile_begin(self):
+        call("emdee_profile_begin", self._h)
+
+    def profile_end(self):
+        """(summed force-kernel milliseconds, number of force-kernel launches) since profile_begin."""
+        ms, n = C.c_double(), C.c_int64()
+        call("emdee_profile_end", self._h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
     # -- getters ---------------------------------------------------------------------------------
     def _get3(self, fn, out=None):
         out = np.empty((self.N, 3)) if out is None else out

@@ -81,6 +81,10 @@ struct emdee_system {
     // results
     int last_mode = -1, last_bitmask = 0;
     bool forces_valid = false, kick_pending = false;
+    // per-launch events of the force kernel (emdee_profile_begin/end)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;
+    size_t prof_used = 0;
     // scratch for host transfers
     double *tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -326,6 +330,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
     dev_free(s->partial); dev_free(s->partial_n); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
+    for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     delete s;
     return EMDEE_OK;
 }
@@ -768,10 +773,23 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     const bool F = (bitmask & EMDEE_FORCES) != 0;
     const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0 || !F;
     if (audit) CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (s->profiling && s->prof_used + 2 <= 16384) {
+        if (s->prof_events.size() < s->prof_used + 2) {
+            s->prof_events.resize(s->prof_used + 2);
+            CUDA_TRY(cudaEventCreate(&s->prof_events[s->prof_used]));
+            CUDA_TRY(cudaEventCreate(&s->prof_events[s->prof_used + 1]));
+        }
+        pe0 = s->prof_events[s->prof_used];
+        pe1 = s->prof_events[s->prof_used + 1];
+        s->prof_used += 2;
+        CUDA_TRY(cudaEventRecord(pe0, c->stream));
+    }
     if (s->fc_block == 128)
         EMDEE_TRY(launch_cells_b<128>(s, a, F, EW, s->has_excl, audit));
     else
         EMDEE_TRY(launch_cells_b<256>(s, a, F, EW, s->has_excl, audit));
+    if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
     if (EW || audit) {
         k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks, s->partial, s->totals);
         c->launches++;
@@ -793,7 +811,7 @@ static int launch_tiles_t(emdee_system *s, const TileArgs &a, int bitmask)
     return check_launch("k_force_tiles");
 }
 
-static int run_tiles(emdee_system *s, int bitmask, bool cull)
+static int run_tiles(emdee_system *s, int bitmask, bool cull, int32_t *pairs = nullptr, int64_t pair_cap = 0)
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
@@ -810,7 +828,9 @@ static int run_tiles(emdee_system *s, int bitmask, bool cull)
     a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2]; a.hs = A.hs; a.ts = A.ts;
     a.id = A.id; a.xbase = A.xbase; a.xmask = A.xmask;
     a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2]; a.en = s->en; a.vir = s->vir;
-    a.pair_count = s->digest;
+    a.digest = s->digest;
+    a.pairs = pairs;
+    a.pair_cap = pair_cap;
     a.L = s->L;
     a.model = s->model;
     if (cull) return s->has_excl ? launch_tiles_t<true, true>(s, a, bitmask) : launch_tiles_t<true, false>(s, a, bitmask);
@@ -966,9 +986,13 @@ extern "C" int emdee_pair_set_digest(emdee_system *s, uint64_t out[3])
     SYS_ENTER(s, "emdee_pair_set_digest");
     if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_pair_set_digest: null output");
     if (!s->binned || !s->has_atoms) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: needs LJ atoms, positions and emdee_bin");
-    if (!s->grid_ok) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: box too small for a cell grid (M < 2*ndiv+1)");
     // the audit pass recomputes forces/energies into the same arrays with the same values
-    EMDEE_TRY(run_cells(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true, nullptr, 0));
+    if (s->grid_ok)
+        EMDEE_TRY(run_cells(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true, nullptr, 0));
+    else {
+        if (!s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: box too small for a cell grid and a custom tile list is set");
+        EMDEE_TRY(run_tiles(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true));
+    }
     unsigned long long h[4];
     CUDA_TRY(cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -984,10 +1008,10 @@ extern "C" int emdee_pair_set(emdee_system *s, int32_t *ij, int64_t cap, int64_t
     SYS_ENTER(s, "emdee_pair_set");
     if (!ij || !n || cap < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_pair_set: bad arguments");
     if (!s->binned || !s->has_atoms) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: needs LJ atoms, positions and emdee_bin");
-    if (!s->grid_ok) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: box too small for a cell grid (M < 2*ndiv+1)");
+    if (!s->grid_ok && !s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: box too small for a cell grid and a custom tile list is set");
     int32_t *d = nullptr;
     EMDEE_TRY(dev_alloc(&d, (size_t)2 * std::max<int64_t>(cap, 1)));
-    int st = run_cells(s, 7, true, d, cap);
+    int st = s->grid_ok ? run_cells(s, 7, true, d, cap) : run_tiles(s, 7, true, d, cap);
     unsigned long long h[4] = {0, 0, 0, 0};
     if (st == EMDEE_OK && cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
     if (st == EMDEE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
@@ -1076,6 +1100,29 @@ extern "C" int emdee_kinetic_energy(emdee_system *s, double *K)
     for (int i = 0; i < nb; i++) k += h[i];
     *K = k;
     return check_launch("k_kinetic");
+}
+
+extern "C" int emdee_profile_begin(emdee_system *s)
+{
+    SYS_ENTER(s, "emdee_profile_begin");
+    s->profiling = true;
+    s->prof_used = 0;
+    return EMDEE_OK;
+}
+extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
+{
+    SYS_ENTER(s, "emdee_profile_end");
+    s->profiling = false;
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double total = 0;
+    for (size_t k = 0; k + 1 < s->prof_used; k += 2) {
+        float t = 0;
+        CUDA_TRY(cudaEventElapsedTime(&t, s->prof_events[k], s->prof_events[k + 1]));
+        total += t;
+    }
+    if (ms) *ms = total;
+    if (launches) *launches = (int64_t)(s->prof_used / 2);
+    return EMDEE_OK;
 }
 
 extern "C" int emdee_synchronize(emdee_system *s)

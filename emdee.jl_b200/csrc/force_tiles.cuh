@@ -20,7 +20,9 @@ struct TileArgs {
     const int32_t *id, *xbase;
     const uint64_t *xmask;
     double *fx, *fy, *fz, *en, *vir;   // outputs by slot (zeroed by the launcher, :112-114)
-    unsigned long long *pair_count;    // CULL only: accepted pairs
+    unsigned long long *digest;        // CULL only: {accepted pairs, sum hash, xor hash, pair-list cursor}
+    int32_t *pairs;                    // CULL only: optional pair list (2 x pair_cap)
+    long long pair_cap;
     double L;
     LJModel model;
 };
@@ -47,7 +49,7 @@ __global__ void __launch_bounds__(128) k_force_tiles(TileArgs a)
 
     double fix = 0, fiy = 0, fiz = 0, ei = 0, wi = 0;
     double fjx = 0, fjy = 0, fjz = 0, ej = 0, wj = 0;
-    unsigned long long npairs = 0;
+    unsigned long long npairs = 0, hsum = 0, hxor = 0;
 
     const int niter = 32 - (diag ? 1 : 0);
     for (int m = 1; m <= niter; m++) {
@@ -68,7 +70,15 @@ __global__ void __launch_bounds__(128) k_force_tiles(TileArgs a)
                 lj_interaction(r2, inv, hsi + phs, tsi * pts, a.model, c60id2, Eg, Wg);   // :72
                 const double q = Wg * inv;                                                // :74
                 qx = q * vx; qy = q * vy; qz = q * vz;
-                if (CULL && (!diag || (int32_t)I < pid)) npairs++;
+                if (CULL && (!diag || (int32_t)I < pid)) {
+                    const int32_t lo = min((int32_t)I, pid), hi = max((int32_t)I, pid);
+                    const uint64_t hh = pair_hash(lo, hi);
+                    npairs++; hsum += hh; hxor ^= hh;
+                    if (a.pairs) {
+                        const unsigned long long k = atomicAdd(a.digest + 3, 1ull);
+                        if ((long long)k < a.pair_cap) { a.pairs[2 * k] = lo; a.pairs[2 * k + 1] = hi; }
+                    }
+                }
             }
         }
         if (F) {
@@ -89,7 +99,11 @@ __global__ void __launch_bounds__(128) k_force_tiles(TileArgs a)
         if (W) atomicAdd(a.vir + sj, 0.5 * wj);
     }
     if (CULL) {
-        for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
-        if (lane == 0 && npairs) atomicAdd(a.pair_count, npairs);
+        for (int o = 16; o > 0; o >>= 1) {
+            npairs += __shfl_xor_sync(0xffffffffu, npairs, o);
+            hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+            hxor ^= __shfl_xor_sync(0xffffffffu, hxor, o);
+        }
+        if (lane == 0 && npairs) { atomicAdd(a.digest, npairs); atomicAdd(a.digest + 1, hsum); atomicXor(a.digest + 2, hxor); }
     }
 }

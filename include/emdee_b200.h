@@ -122,6 +122,12 @@ int emdee_launch_count(emdee_ctx *ctx, int64_t *n);
 int emdee_timer_start(emdee_ctx *ctx);
 int emdee_timer_stop(emdee_ctx *ctx, double *ms);
 
+/* Per-kernel timing of the dominant kernel (the cell-list force kernel) with CUDA events recorded on the
+ * library's stream around every launch between begin and end; end synchronises and returns the summed
+ * duration and the number of launches (roofline.achieved in bench.py). */
+int emdee_profile_begin(emdee_system *sys);
+int emdee_profile_end(emdee_system *sys, double *force_kernel_ms, int64_t *force_kernel_launches);
+
 /* Slab decomposition info (valid after emdee_bin): atoms owned by this rank and their ids */
 int emdee_get_local_count(emdee_system *sys, int64_t *nlocal, int64_t *nghost);
 int emdee_get_local_ids(emdee_system *sys, int32_t *ids_nlocal);
