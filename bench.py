@@ -55,8 +55,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--ndiv", type=int, default=1)
-    ap.add_argument("--skin", type=float, default=0.3)
-    ap.add_argument("--rebin-every", type=int, default=10)
+    ap.add_argument("--skin", type=float, default=0.4)
+    ap.add_argument("--rebin-every", type=int, default=5)
     ap.add_argument("--dt", type=float, default=0.005)
     ap.add_argument("--temperature", type=float, default=1.44)
     ap.add_argument("--e2e-iters", type=int, default=3)

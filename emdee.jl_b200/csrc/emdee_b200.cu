@@ -12,6 +12,17 @@
 #include "force_cells.cuh"
 #include "force_tiles.cuh"
 #include "integrate.cuh"
+#include "slab.cuh"
+
+#include <nccl.h>
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t _r = (expr);                                                                   \
+        if (_r != ncclSuccess) {                                                                    \
+            emdee_set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, ncclGetErrorString(_r)); \
+            return EMDEE_ERR_NCCL;                                                                  \
+        }                                                                                           \
+    } while (0)
 
 // ------------------------------------------------------------------------------------------------
 // errors
@@ -38,6 +49,9 @@ struct emdee_ctx {
     size_t smem_optin = 0, mem_bytes = 0;
     int64_t launches = 0;
     int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
 };
 
 struct emdee_system {
@@ -64,6 +78,14 @@ struct emdee_system {
     int32_t *count = nullptr, *cell_start = nullptr, *fill = nullptr, *order = nullptr, *src_of_new = nullptr;
     int32_t *block_sum = nullptr, *maxpop = nullptr;
     int64_t steps_since_bin = 0;
+    // slab decomposition (nranks > 1)
+    bool decomposed = false;
+    int z0 = 0, nz = 0;                               // my global planes [z0, z0+nz)
+    int64_t lo_send_a = 0, lo_send_n = 0, hi_send_a = 0, hi_send_n = 0;   // slot ranges my neighbours need as ghosts
+    int brick_lo_end = 0, brick_hi_begin = 0;         // brick z layers [0,lo_end) and [hi_begin,nbz) read ghost planes
+    int32_t *sendcount = nullptr, *recvcount = nullptr, *list_lo = nullptr, *list_hi = nullptr;
+    double *migbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // send lo, send hi, recv lo, recv hi
+    int64_t migcap = 0;
     // force kernel configuration
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
     size_t fc_smem = 0;
@@ -167,8 +189,13 @@ extern "C" int emdee_destroy(emdee_ctx *c)
     if (!c) return EMDEE_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm_stream) cudaStreamSynchronize(c->comm_stream);
+    if (c->comm) ncclCommDestroy(c->comm);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->ev_compute) cudaEventDestroy(c->ev_compute);
+    if (c->ev_comm) cudaEventDestroy(c->ev_comm);
+    if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return EMDEE_OK;
@@ -176,15 +203,30 @@ extern "C" int emdee_destroy(emdee_ctx *c)
 
 extern "C" int emdee_comm_unique_id(char id[128])
 {
-    (void)id;
-    EMDEE_FAIL(EMDEE_ERR_NCCL, "emdee_comm_unique_id: slab decomposition is not built into this library yet");
+    if (!id) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_unique_id: null buffer");
+    static_assert(NCCL_UNIQUE_ID_BYTES == 128, "ncclUniqueId is expected to be 128 bytes");
+    ncclUniqueId u;
+    NCCL_TRY(ncclGetUniqueId(&u));
+    memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
+    return EMDEE_OK;
 }
 extern "C" int emdee_comm_init(emdee_ctx *c, int rank, int nranks, const char id[128])
 {
-    (void)id;
     if (!c) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_init: null context");
-    if (nranks == 1 && rank == 0) return EMDEE_OK;
-    EMDEE_FAIL(EMDEE_ERR_NCCL, "emdee_comm_init: slab decomposition is not built into this library yet");
+    if (nranks < 1 || rank < 0 || rank >= nranks) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_init: rank %d of %d", rank, nranks);
+    if (c->comm) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_comm_init: communicator already initialised");
+    if (nranks == 1) return EMDEE_OK;
+    if (!id) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_init: null id");
+    CUDA_TRY(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
+    NCCL_TRY(ncclCommInitRank(&c->comm, nranks, u, rank));
+    CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
+    c->rank = rank;
+    c->nranks = nranks;
+    return EMDEE_OK;
 }
 
 extern "C" int emdee_device_info(emdee_ctx *c, int *sm_count, int *cc_major, int *cc_minor, int64_t *mem_bytes)
@@ -284,7 +326,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     s->ctx = c;
     s->N = N;
     s->L = L;
-    s->cap = N;
+    s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
     auto A = [&](int rc) { if (st == EMDEE_OK) st = rc; };
@@ -302,6 +344,12 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
     A(dev_alloc(&s->brick_max, 1));
+    if (c->nranks > 1) {
+        A(dev_alloc(&s->sendcount, 2));
+        A(dev_alloc(&s->recvcount, 2));
+        A(dev_alloc(&s->list_lo, s->cap));
+        A(dev_alloc(&s->list_hi, s->cap));
+    }
     if (st != EMDEE_OK) { emdee_system_destroy(s); return st; }
     // slot == id until the first binning; unit masses; zero velocities; no exclusions
     LAUNCH_1D(c, k_iota, N, N, s->A[0].id);
@@ -331,6 +379,8 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->partial); dev_free(s->partial_n); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
+    for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     delete s;
     return EMDEE_OK;
 }
@@ -648,13 +698,161 @@ static int do_bin(emdee_system *s, int ndiv)
     return EMDEE_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// slab decomposition: re-binning with migration and ghost exchange, per-step halo
+// ------------------------------------------------------------------------------------------------
+// Message order inside every NCCL group: sends [to lower, to upper], receives [from upper, from lower].
+// With two ranks both neighbours are the same peer and NCCL pairs the k-th send with the k-th receive,
+// so the peer's "to lower" slice (its bottom planes) lands in my upper ghost range, as it must.
+static int slab_exchange(emdee_ctx *c, cudaStream_t st, const void *send_lo, size_t n_send_lo, const void *send_hi,
+                         size_t n_send_hi, void *recv_lo, size_t n_recv_lo, void *recv_hi, size_t n_recv_hi, size_t elem)
+{
+    const int lower = (c->rank + c->nranks - 1) % c->nranks, upper = (c->rank + 1) % c->nranks;
+    NCCL_TRY(ncclSend(send_lo, n_send_lo * elem, ncclInt8, lower, c->comm, st));
+    NCCL_TRY(ncclSend(send_hi, n_send_hi * elem, ncclInt8, upper, c->comm, st));
+    NCCL_TRY(ncclRecv(recv_hi, n_recv_hi * elem, ncclInt8, upper, c->comm, st));
+    NCCL_TRY(ncclRecv(recv_lo, n_recv_lo * elem, ncclInt8, lower, c->comm, st));
+    return EMDEE_OK;
+}
+
+// Scaled positions of the boundary planes -> neighbours' ghost ranges (three contiguous array slices
+// per side, no packing).  Runs on `st`; callers order it against the compute stream with events.
+static int slab_halo_positions(emdee_system *s, cudaStream_t st)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    const int64_t own_end = s->nlo + s->nown;
+    NCCL_TRY(ncclGroupStart());
+    for (int k = 0; k < 3; k++)
+        EMDEE_TRY(slab_exchange(c, st, A.s[k] + s->lo_send_a, s->lo_send_n, A.s[k] + s->hi_send_a, s->hi_send_n,
+                                A.s[k], s->nlo, A.s[k] + own_end, s->nhi, sizeof(double)));
+    NCCL_TRY(ncclGroupEnd());
+    return EMDEE_OK;
+}
+
+static int do_bin_slab(emdee_system *s, int ndiv)
+{
+    emdee_ctx *c = s->ctx;
+    const int G = c->nranks;
+    const double Mf = std::floor((double)ndiv * s->L / (s->cutoff + s->skin));
+    if (!(Mf >= 1) || Mf > 2000) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: M=%g cells per dimension out of range", Mf);
+    const int M = (int)Mf, R = ndiv;
+    if (M < 2 * R + 1) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: M=%d is too small for a cell grid; slab decomposition needs M >= %d", M, 2 * R + 1);
+    if (M / G < std::max(R, 1)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: %d z planes over %d ranks leaves fewer than %d planes per slab", M, G, R);
+    const int z0 = (int)((int64_t)c->rank * M / G), z1 = (int)((int64_t)(c->rank + 1) * M / G), nz = z1 - z0;
+    GridDesc &g = s->g;
+    g.M = M; g.R = R; g.zwrap = 0; g.nzt = nz + 2 * R; g.zhome0 = R; g.nzhome = nz; g.zglob0 = z0 - R;
+    s->ndiv = ndiv; s->grid_ok = true; s->z0 = z0; s->nz = nz;
+    const int64_t plane = (int64_t)M * M;
+    s->ncell = plane * g.nzt;
+    if (s->ncell + 2 > s->ncell_cap) {
+        dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
+        s->ncell_cap = s->ncell + 2;
+        EMDEE_TRY(dev_alloc(&s->count, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->cell_start, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->fill, (size_t)s->ncell_cap));
+        EMDEE_TRY(dev_alloc(&s->block_sum, (size_t)ceil_div64(s->ncell_cap, SCAN_BLOCK * SCAN_ITEMS) + 1));
+    }
+    AtomArrays &A = s->A[s->cur];
+    const bool first_time = !s->decomposed;
+    int64_t n_in = s->nown;
+    const int64_t first = s->nlo;
+    CUDA_TRY(cudaMemsetAsync(s->cell_start, 0, sizeof(int32_t) * (s->ncell + 2), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->fill, 0, sizeof(int32_t) * (s->ncell + 2), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->sendcount, 0, sizeof(int32_t) * 2, c->stream));
+    LAUNCH_1D(c, k_cell_index_slab, n_in, first, n_in, A.s[0], A.s[1], A.s[2], M, z0, nz, R, first_time ? 1 : 0,
+              (int)s->ncell, s->gcell[s->cur], s->lcell[s->cur], s->cell_start, s->sendcount, s->list_lo, s->list_hi,
+              (int)s->cap, s->err);
+    if (!first_time) {
+        // ---- migration: counts, then payload --------------------------------------------------
+        int32_t nsend[2] = {0, 0}, nrecv[2] = {0, 0};
+        NCCL_TRY(ncclGroupStart());
+        EMDEE_TRY(slab_exchange(c, c->stream, s->sendcount, 1, s->sendcount + 1, 1, s->recvcount, 1, s->recvcount + 1, 1, sizeof(int32_t)));
+        NCCL_TRY(ncclGroupEnd());
+        CUDA_TRY(cudaMemcpyAsync(nsend, s->sendcount, sizeof(nsend), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(nrecv, s->recvcount, sizeof(nrecv), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        const int64_t need = std::max<int64_t>(std::max(nsend[0], nsend[1]), std::max(nrecv[0], nrecv[1]));
+        if (need > s->migcap) {
+            for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
+            s->migcap = need + need / 2 + 1024;
+            for (int k = 0; k < 4; k++) EMDEE_TRY(dev_alloc(&s->migbuf[k], (size_t)MIG_FIELDS * s->migcap));
+        }
+        if (first + n_in + nrecv[0] + nrecv[1] > s->cap) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: slab capacity exceeded by migrating atoms");
+        LAUNCH_1D(c, k_pack_migrants, (int64_t)nsend[0], nsend[0], s->list_lo, A, s->migbuf[0]);
+        LAUNCH_1D(c, k_pack_migrants, (int64_t)nsend[1], nsend[1], s->list_hi, A, s->migbuf[1]);
+        NCCL_TRY(ncclGroupStart());
+        EMDEE_TRY(slab_exchange(c, c->stream, s->migbuf[0], (size_t)MIG_FIELDS * nsend[0], s->migbuf[1], (size_t)MIG_FIELDS * nsend[1],
+                                s->migbuf[2], (size_t)MIG_FIELDS * nrecv[0], s->migbuf[3], (size_t)MIG_FIELDS * nrecv[1], sizeof(double)));
+        NCCL_TRY(ncclGroupEnd());
+        LAUNCH_1D(c, k_unpack_migrants, (int64_t)nrecv[0], nrecv[0], s->migbuf[2], first + n_in, A, s->L, M, z0, nz, R,
+                  s->gcell[s->cur], s->lcell[s->cur], s->cell_start, s->err);
+        LAUNCH_1D(c, k_unpack_migrants, (int64_t)nrecv[1], nrecv[1], s->migbuf[3], first + n_in + nrecv[0], A, s->L, M, z0, nz, R,
+                  s->gcell[s->cur], s->lcell[s->cur], s->cell_start, s->err);
+        n_in += nrecv[0] + nrecv[1];
+    }
+    // ---- populations of the ghost planes come from the neighbours' boundary planes ----------------
+    int32_t *cnt = s->cell_start;
+    NCCL_TRY(ncclGroupStart());
+    EMDEE_TRY(slab_exchange(c, c->stream, cnt + plane * R, (size_t)plane * R, cnt + plane * nz, (size_t)plane * R,
+                            cnt, (size_t)plane * R, cnt + plane * (R + nz), (size_t)plane * R, sizeof(int32_t)));
+    NCCL_TRY(ncclGroupEnd());
+    CUDA_TRY(cudaMemcpyAsync(s->count, s->cell_start, sizeof(int32_t) * (s->ncell + 1), cudaMemcpyDeviceToDevice, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->maxpop, 0, sizeof(int32_t), c->stream));
+    EMDEE_TRY(exclusive_scan(s, s->cell_start, s->ncell + 1, s->maxpop));
+    int32_t marks[5];
+    const int64_t mark_idx[5] = {plane * R, plane * 2 * R, plane * nz, plane * (R + nz), s->ncell};
+    for (int k = 0; k < 5; k++)
+        CUDA_TRY(cudaMemcpyAsync(&marks[k], s->cell_start + mark_idx[k], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int64_t nlo = marks[0], own_end = marks[3], ntot = marks[4];
+    if (ntot > s->cap) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: slab holds %lld atoms incl. ghosts, capacity %lld", (long long)ntot, (long long)s->cap);
+    const int64_t nown = own_end - nlo;
+    LAUNCH_1D(c, k_scatter_slab, n_in, first, n_in, s->lcell[s->cur], (int)s->ncell, s->cell_start, s->fill, s->order);
+    LAUNCH_1D(c, k_rank_in_cell, nown, nlo, nown, s->order, s->lcell[s->cur], s->cell_start, A.id, s->src_of_new);
+    GatherArgs ga;
+    ga.pfirst = nlo; ga.n = nown; ga.src_of_new = s->src_of_new;
+    ga.gcell_old = s->gcell[s->cur]; ga.lcell_old = s->lcell[s->cur];
+    ga.in = A; ga.out = s->A[1 - s->cur];
+    ga.gcell_new = s->gcell[1 - s->cur]; ga.lcell_new = s->lcell[1 - s->cur];
+    ga.slot_of_id = nullptr; ga.has_vel = 1; ga.has_excl = 1;
+    LAUNCH_1D(c, k_gather, nown, ga);
+    EMDEE_TRY(check_launch("slab binning"));
+    s->cur = 1 - s->cur;
+    s->nlo = nlo; s->nown = nown; s->nhi = ntot - own_end;
+    s->lo_send_a = marks[0]; s->lo_send_n = marks[1] - marks[0];
+    s->hi_send_a = marks[2]; s->hi_send_n = marks[3] - marks[2];
+    s->decomposed = true;
+    // ---- ghost atoms: static per-atom data and current scaled positions ----------------------------
+    AtomArrays &B = s->A[s->cur];
+    NCCL_TRY(ncclGroupStart());
+#define GHOST_X(arr, T)                                                                                          \
+    EMDEE_TRY(slab_exchange(c, c->stream, (arr) + s->lo_send_a, s->lo_send_n, (arr) + s->hi_send_a, s->hi_send_n, \
+                            (arr), s->nlo, (arr) + own_end, s->nhi, sizeof(T)))
+    GHOST_X(B.s[0], double); GHOST_X(B.s[1], double); GHOST_X(B.s[2], double);
+    GHOST_X(B.hs, double); GHOST_X(B.ts, double);
+    GHOST_X(B.id, int32_t); GHOST_X(B.xbase, int32_t); GHOST_X(B.xmask, uint64_t);
+#undef GHOST_X
+    NCCL_TRY(ncclGroupEnd());
+    s->binned = true;
+    s->steps_since_bin = 0;
+    s->forces_valid = false;
+    EMDEE_TRY(choose_bricks(s));
+    // brick layers whose halo reaches ghost planes (they must wait for the halo exchange)
+    const int bz = s->g.bz, nbz = s->g.nbz;
+    s->brick_lo_end = std::min(nbz, (R + bz - 1) / bz);
+    s->brick_hi_begin = std::max(s->brick_lo_end, (nz - R) / bz);
+    return EMDEE_OK;
+}
+
 extern "C" int emdee_bin(emdee_system *s, int ndiv)
 {
     SYS_ENTER(s, "emdee_bin");
     if (!s->has_model || !s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: set the model (cutoff) and positions first");
     if (ndiv < 1 || ndiv > 4) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: ndiv=%d must be in [1,4]", ndiv);
     if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: a velocity-Verlet step is half-finished");
-    return do_bin(s, ndiv);
+    return c->nranks > 1 ? do_bin_slab(s, ndiv) : do_bin(s, ndiv);
 }
 
 extern "C" int emdee_get_cells_per_dimension(emdee_system *s, int32_t *M)
@@ -723,29 +921,32 @@ extern "C" int emdee_get_local_ids(emdee_system *s, int32_t *ids)
 // force evaluation
 // ------------------------------------------------------------------------------------------------
 template <int BLOCK, bool F, bool EW, bool EXCL, bool AUDIT>
-static int launch_cells_t(emdee_system *s, const CellArgs &a)
+static int launch_cells_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
+    if (nblocks <= 0) return EMDEE_OK;
     auto kern = k_force_cells<BLOCK, F, EW, EXCL, AUDIT>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fc_smem));
-    kern<<<s->fc_nblocks, BLOCK, s->fc_smem, s->ctx->stream>>>(a);
+    kern<<<nblocks, BLOCK, s->fc_smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_force_cells");
 }
 template <int BLOCK>
-static int launch_cells_b(emdee_system *s, const CellArgs &a, bool F, bool EW, bool EXCL, bool AUDIT)
+static int launch_cells_b(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
 {
-    if (AUDIT) return EXCL ? launch_cells_t<BLOCK, true, true, true, true>(s, a) : launch_cells_t<BLOCK, true, true, false, true>(s, a);
+    if (AUDIT) return EXCL ? launch_cells_t<BLOCK, true, true, true, true>(s, a, nb) : launch_cells_t<BLOCK, true, true, false, true>(s, a, nb);
     if (EXCL) {
-        if (F && EW) return launch_cells_t<BLOCK, true, true, true, false>(s, a);
-        if (F) return launch_cells_t<BLOCK, true, false, true, false>(s, a);
-        return launch_cells_t<BLOCK, false, true, true, false>(s, a);
+        if (F && EW) return launch_cells_t<BLOCK, true, true, true, false>(s, a, nb);
+        if (F) return launch_cells_t<BLOCK, true, false, true, false>(s, a, nb);
+        return launch_cells_t<BLOCK, false, true, true, false>(s, a, nb);
     }
-    if (F && EW) return launch_cells_t<BLOCK, true, true, false, false>(s, a);
-    if (F) return launch_cells_t<BLOCK, true, false, false, false>(s, a);
-    return launch_cells_t<BLOCK, false, true, false, false>(s, a);
+    if (F && EW) return launch_cells_t<BLOCK, true, true, false, false>(s, a, nb);
+    if (F) return launch_cells_t<BLOCK, true, false, false, false>(s, a, nb);
+    return launch_cells_t<BLOCK, false, true, false, false>(s, a, nb);
 }
 
-static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap)
+// halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
+// communication stream while the interior brick layers compute; the boundary layers wait for them.
+static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false)
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
@@ -785,10 +986,26 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         s->prof_used += 2;
         CUDA_TRY(cudaEventRecord(pe0, c->stream));
     }
-    if (s->fc_block == 128)
-        EMDEE_TRY(launch_cells_b<128>(s, a, F, EW, s->has_excl, audit));
-    else
-        EMDEE_TRY(launch_cells_b<256>(s, a, F, EW, s->has_excl, audit));
+    const int layer = s->g.nbx * s->g.nby;
+    // launch order: interior layers first, then the layers that read ghost planes
+    int ranges[3][2] = {{0, s->fc_nblocks}, {0, 0}, {0, 0}};
+    if (halo && c->nranks > 1) {
+        CUDA_TRY(cudaEventRecord(c->ev_compute, c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_compute, 0));
+        EMDEE_TRY(slab_halo_positions(s, c->comm_stream));
+        CUDA_TRY(cudaEventRecord(c->ev_comm, c->comm_stream));
+        ranges[0][0] = s->brick_lo_end * layer; ranges[0][1] = (s->brick_hi_begin - s->brick_lo_end) * layer;
+        ranges[1][0] = 0; ranges[1][1] = s->brick_lo_end * layer;
+        ranges[2][0] = s->brick_hi_begin * layer; ranges[2][1] = s->fc_nblocks - s->brick_hi_begin * layer;
+    }
+    for (int k = 0; k < 3; k++) {
+        if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        a.block_first = ranges[k][0];
+        if (s->fc_block == 128)
+            EMDEE_TRY(launch_cells_b<128>(s, a, ranges[k][1], F, EW, s->has_excl, audit));
+        else
+            EMDEE_TRY(launch_cells_b<256>(s, a, ranges[k][1], F, EW, s->has_excl, audit));
+    }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
     if (EW || audit) {
         k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks, s->partial, s->totals);
@@ -858,6 +1075,7 @@ extern "C" int emdee_compute_nonbonded(emdee_system *s, int mode, int bitmask)
         EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: set model, LJ atoms and positions first");
     if ((bitmask & 7) == 0 || (bitmask & ~7)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded: bitmask %d must combine FORCES|ENERGIES|VIRIALS", bitmask);
     if (mode == EMDEE_ALLPAIRS_REFERENCE) {
+        if (c->nranks > 1) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: ALLPAIRS_REFERENCE is single-GPU (the reference's O(N^2) mode is for small N)");
         EMDEE_TRY(run_tiles(s, bitmask, false));
     } else if (mode == EMDEE_CUTOFF) {
         if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: EMDEE_CUTOFF needs emdee_bin after the last emdee_set_positions");
@@ -1069,9 +1287,9 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         EMDEE_TRY(launch_vv(s, dt, 1, rebin ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
         s->kick_pending = false;
         s->steps_since_bin++;
-        if (rebin) EMDEE_TRY(do_bin(s, s->ndiv));
+        if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));
         if (s->grid_ok)
-            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0));
+            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin));   // a re-bin already refreshed the ghosts
         else
             EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));
         s->kick_pending = true;

@@ -43,6 +43,7 @@ struct CellArgs {
     int cap;                          // staged-atom capacity of the shared-memory arrays
     int ncs_max;                      // staged-cell capacity
     int *err;                         // device error flag (capacity overflow)
+    int block_first;                  // first brick of this launch (launches may cover a z-layer range)
 };
 
 __host__ __device__ inline size_t fc_smem_bytes(int cap, int ncs_max, int block)
@@ -83,7 +84,8 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
     const int R = g.R, M = g.M;
 
     // ---- brick geometry ---------------------------------------------------------------------
-    int b = blockIdx.x;
+    const int bid = blockIdx.x + a.block_first;
+    int b = bid;
     const int bxi = b % g.nbx; b /= g.nbx;
     const int byi = b % g.nby;
     const int bzi = b / g.nby;
@@ -288,9 +290,9 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
         if (tid == 0) {
             double E = 0, W = 0; unsigned long long n = 0, hs_ = 0, hx_ = 0;
             for (int k = 0; k < NW; k++) { E += red[k]; W += red[NW + k]; n += redn[k]; hs_ += redn[NW + k]; hx_ ^= redn[2 * NW + k]; }
-            if (EW) { a.partial[2 * blockIdx.x] = E; a.partial[2 * blockIdx.x + 1] = W; }
+            if (EW) { a.partial[2 * bid] = E; a.partial[2 * bid + 1] = W; }
             if (AUDIT) {
-                a.partial_n[blockIdx.x] = n;
+                a.partial_n[bid] = n;
                 atomicAdd(a.digest, n); atomicAdd(a.digest + 1, hs_); atomicXor(a.digest + 2, hx_);
             }
         }
