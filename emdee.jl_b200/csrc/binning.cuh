@@ -168,6 +168,7 @@ __global__ void k_gather(GatherArgs a)
     a.out.mass[p] = a.in.mass[o];
     const int id = a.in.id[o];
     a.out.id[p] = id;
+    a.out.type[p] = a.in.type[o];
     if (a.has_excl) { a.out.xbase[p] = a.in.xbase[o]; a.out.xmask[p] = a.in.xmask[o]; }
     a.gcell_new[p] = a.gcell_old[o];
     a.lcell_new[p] = a.lcell_old[o];

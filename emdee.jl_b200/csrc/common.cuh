@@ -46,6 +46,7 @@ struct AtomArrays {
     double *hs = nullptr, *ts = nullptr;          // LJAtom.half_sigma, LJAtom.twice_sqrt_eps
     double *mass = nullptr;
     int32_t *id = nullptr;                        // global atom id of the slot
+    int32_t *type = nullptr;                      // LJ parameter class (index into the pair table)
     int32_t *xbase = nullptr;                     // exclusion window base (global id)
     uint64_t *xmask = nullptr;                    // exclusion bits
 };

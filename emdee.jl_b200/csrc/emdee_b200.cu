@@ -14,6 +14,8 @@
 #include "integrate.cuh"
 #include "slab.cuh"
 
+#define FC_REGS_ESTIMATE 128   // registers per thread of k_force_cells assumed by the residency model
+
 #include <nccl.h>
 #define NCCL_TRY(expr)                                                                              \
     do {                                                                                            \
@@ -88,10 +90,14 @@ struct emdee_system {
     int64_t migcap = 0;
     // force kernel configuration
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
+    bool fc_typed = false;
+    int fc_shape[3] = {0, 0, 0};
+    size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
     double *partial = nullptr;
-    unsigned long long *partial_n = nullptr;
     int64_t partial_cap = 0;
+    double2 *ljtab = nullptr;                 // pair table of the LJ parameter classes
+    int ntypes = 0;                           // 0: too many classes, kernels gather per-atom parameters
     double *totals = nullptr;                 // device {E, W}
     unsigned long long *digest = nullptr;     // device {count, sum, xor} + pair counter at [3]
     int *err = nullptr;                       // device error flag
@@ -305,6 +311,7 @@ static int alloc_atoms(AtomArrays &A, int64_t cap)
     EMDEE_TRY(dev_alloc(&A.ts, cap));
     EMDEE_TRY(dev_alloc(&A.mass, cap));
     EMDEE_TRY(dev_alloc(&A.id, cap));
+    EMDEE_TRY(dev_alloc(&A.type, cap));
     EMDEE_TRY(dev_alloc(&A.xbase, cap));
     EMDEE_TRY(dev_alloc(&A.xmask, cap));
     return EMDEE_OK;
@@ -312,7 +319,7 @@ static int alloc_atoms(AtomArrays &A, int64_t cap)
 static void free_atoms(AtomArrays &A)
 {
     for (int c = 0; c < 3; c++) { dev_free(A.r[c]); dev_free(A.s[c]); dev_free(A.v[c]); dev_free(A.rb[c]); }
-    dev_free(A.hs); dev_free(A.ts); dev_free(A.mass); dev_free(A.id); dev_free(A.xbase); dev_free(A.xmask);
+    dev_free(A.hs); dev_free(A.ts); dev_free(A.mass); dev_free(A.id); dev_free(A.type); dev_free(A.xbase); dev_free(A.xmask);
 }
 
 extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_system **out)
@@ -356,6 +363,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     LAUNCH_1D(c, k_iota, N, N, s->slot_of_id);
     LAUNCH_1D(c, k_fill<double>, N, N, s->A[0].mass, 1.0);
     for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(s->A[0].v[k], 0, sizeof(double) * N, c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->A[0].type, 0, sizeof(int32_t) * N, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->A[0].xbase, 0, sizeof(int32_t) * N, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->A[0].xmask, 0, sizeof(uint64_t) * N, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
@@ -376,7 +384,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     for (int k = 0; k < 2; k++) { dev_free(s->gcell[k]); dev_free(s->lcell[k]); }
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
-    dev_free(s->partial); dev_free(s->partial_n); dev_free(s->totals); dev_free(s->digest);
+    dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
@@ -436,6 +444,36 @@ extern "C" int emdee_set_lj_atoms(emdee_system *s, const double *atoms)
     LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 2, 0, A.hs);
     LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 2, 1, A.ts);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    // LJ parameter classes: distinct (half_sigma, twice_sqrt_eps) rows.  Up to FC_MAX_TYPES classes the
+    // kernels use a pair table {sigma_ij, 4 eps_ij} in shared memory (src/lennard_jones.jl:29,33);
+    // beyond that they gather the per-atom parameters.
+    std::vector<double> cls;
+    std::vector<int32_t> type((size_t)s->N, 0);
+    bool many = false;
+    for (int64_t i = 0; i < s->N && !many; i++) {
+        const double h = atoms[2 * i], t = atoms[2 * i + 1];
+        size_t k = 0;
+        for (; k < cls.size() / 2; k++)
+            if (cls[2 * k] == h && cls[2 * k + 1] == t) break;
+        if (k == cls.size() / 2) {
+            if (k == FC_MAX_TYPES) { many = true; break; }
+            cls.push_back(h); cls.push_back(t);
+        }
+        type[i] = (int32_t)k;
+    }
+    s->ntypes = many ? 0 : (int)(cls.size() / 2);
+    if (!many) {
+        const int T = s->ntypes;
+        std::vector<double2> tab((size_t)T * T);
+        for (int p = 0; p < T; p++)
+            for (int q = 0; q < T; q++) tab[(size_t)p * T + q] = make_double2(cls[2 * p] + cls[2 * q], cls[2 * p + 1] * cls[2 * q + 1]);
+        dev_free(s->ljtab);
+        EMDEE_TRY(dev_alloc(&s->ljtab, tab.size()));
+        CUDA_TRY(cudaMemcpy(s->ljtab, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
+        EMDEE_TRY(upload(s, type.data(), sizeof(int32_t) * s->N));
+        LAUNCH_1D(c, k_set1<int32_t>, ntot, 0, ntot, A.id, (const int32_t *)s->tmp, 1, 0, A.type);
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     s->has_atoms = true;
     s->forces_valid = false;
     return check_launch("set_lj_atoms");
@@ -582,60 +620,111 @@ static int exclusive_scan(emdee_system *s, int32_t *data, int64_t n, int32_t *ma
     return check_launch("exclusive_scan");
 }
 
+// Picks the home-brick shape and the block size.  Shared memory (staged atoms + per-lane stacks) limits
+// residency, so the score is the number of warps per SM that actually hold a task:
+//   blocks/SM(shared memory, registers) x min(warps per block, warp tasks per brick).
+// The staged-atom capacity is the exact maximum over all bricks (k_brick_max), so a launch never
+// overflows.  The previous choice is kept across re-binnings while it still fits.
+static int brick_capacity(emdee_system *s, int *cap_out)
+{
+    emdee_ctx *c = s->ctx;
+    GridDesc &g = s->g;
+    CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
+    const int nb = g.nbx * g.nby * g.nbz;
+    LAUNCH_1D(c, k_brick_max, (int64_t)nb, g, s->cell_start, s->brick_max);
+    int mx = 0;
+    CUDA_TRY(cudaMemcpyAsync(&mx, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *cap_out = std::max(64, (mx + 4) & ~3);
+    return check_launch("k_brick_max");
+}
+static void set_brick_shape(emdee_system *s, const int sh[3])
+{
+    GridDesc &g = s->g;
+    const int R = g.R, M = g.M;
+    g.bx = std::max(1, std::min(sh[0], M - 2 * R));
+    g.by = std::max(1, std::min(sh[1], M - 2 * R));
+    g.bz = std::max(1, std::min(sh[2], g.zwrap ? M - 2 * R : g.nzhome));
+    g.nbx = (M + g.bx - 1) / g.bx;
+    g.nby = (M + g.by - 1) / g.by;
+    g.nbz = (g.nzhome + g.bz - 1) / g.bz;
+}
 static int choose_bricks(emdee_system *s)
 {
     emdee_ctx *c = s->ctx;
     GridDesc &g = s->g;
-    const int R = g.R, M = g.M;
-    static const int shapes[][3] = {{4, 4, 2}, {4, 2, 2}, {2, 2, 2}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
-    int forced[3] = {0, 0, 0};
+    const int R = g.R;
+    const bool typed = s->ntypes > 0;
+    const size_t per_sm = c->smem_optin + 1024;          // usable shared memory per SM (1 KB reserved per block)
+    const int64_t ntot = s->nlo + s->nown + s->nhi;
+    const double per_cell = (double)ntot / (double)std::max<int64_t>(1, (int64_t)g.M * g.M * g.nzt);
+    auto finish = [&](int cap, int block) -> int {
+        s->fc_cap = cap;
+        s->fc_ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
+        s->fc_block = block;
+        s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
+        s->fc_typed = typed;
+        s->fc_nblocks = g.nbx * g.nby * g.nbz;
+        const int64_t nwarps = (int64_t)s->fc_nblocks * (block / 32);
+        if (nwarps > s->partial_cap) {
+            dev_free(s->partial);
+            s->partial_cap = nwarps;
+            EMDEE_TRY(dev_alloc(&s->partial, (size_t)2 * s->partial_cap));
+        }
+        return EMDEE_OK;
+    };
+    // keep the previous configuration while it fits (one tiny kernel + sync per re-binning)
+    if (s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK")) {
+        set_brick_shape(s, s->fc_shape);
+        int cap = 0;
+        EMDEE_TRY(brick_capacity(s, &cap));
+        const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
+        if (cap <= 65535 && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= s->fc_smem_budget) return finish(cap, s->fc_block);
+    }
+    static const int shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {8, 2, 1}, {4, 4, 1}, {4, 2, 2}, {4, 2, 1}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+    static const int blocks[] = {384, 256, 192, 128, 64};
+    int forced[3] = {0, 0, 0}, forced_block = 0;
     if (const char *e = getenv("EMDEE_BRICK")) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
-    int block = 256;
-    if (const char *e = getenv("EMDEE_BLOCK")) block = atoi(e) == 128 ? 128 : 256;
-    const size_t budget2 = (c->smem_optin + 1024) / 2 - 1024;   // two blocks per SM (1 KB reserved per block)
-    int best = -1;
-    int best_cap = 0;
-    size_t best_smem = 0;
+    if (const char *e = getenv("EMDEE_BLOCK")) forced_block = atoi(e);
+    double best_score = -1;
+    int best_shape[3] = {0, 0, 0}, best_block = 0, best_cap = 0;
+    size_t best_budget = 0;
     const int nshape = forced[0] > 0 ? 1 : (int)(sizeof(shapes) / sizeof(shapes[0]));
-    for (int pass = 0; pass < 2 && best < 0; pass++) {
-        const size_t budget = pass == 0 ? budget2 : c->smem_optin;
-        for (int k = 0; k < nshape; k++) {
-            const int *sh = forced[0] > 0 ? forced : shapes[k];
-            g.bx = std::max(1, std::min(sh[0], M - 2 * R));
-            g.by = std::max(1, std::min(sh[1], M - 2 * R));
-            g.bz = std::max(1, std::min(sh[2], g.zwrap ? M - 2 * R : g.nzhome));
-            if (g.by * g.bz > FC_MAX_HOMEROWS) continue;
-            g.nbx = (M + g.bx - 1) / g.bx;
-            g.nby = (M + g.by - 1) / g.by;
-            g.nbz = (g.nzhome + g.bz - 1) / g.bz;
-            CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
-            const int nb = g.nbx * g.nby * g.nbz;
-            LAUNCH_1D(c, k_brick_max, (int64_t)nb, g, s->cell_start, s->brick_max);
-            int mx = 0;
-            CUDA_TRY(cudaMemcpyAsync(&mx, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            const int cap = std::max(64, (mx + 1) & ~1);
-            const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
-            const size_t smem = fc_smem_bytes(cap, ncs, block);
-            if (cap <= 65535 && smem <= budget) {
-                best = k; best_cap = cap; best_smem = smem;
-                s->fc_ncs = ncs;
-                s->fc_nblocks = nb;
-                break;
+    int prev[3] = {-1, -1, -1};
+    for (int k = 0; k < nshape; k++) {
+        const int *sh = forced[0] > 0 ? forced : shapes[k];
+        set_brick_shape(s, sh);
+        if (g.by * g.bz > FC_MAX_HOMEROWS) continue;
+        if (g.bx == prev[0] && g.by == prev[1] && g.bz == prev[2]) continue;   // clipped to the same shape as the previous one
+        prev[0] = g.bx; prev[1] = g.by; prev[2] = g.bz;
+        int cap = 0;
+        EMDEE_TRY(brick_capacity(s, &cap));
+        if (cap > 65535) continue;
+        const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
+        const double tasks = g.by * g.bz * std::max(1.0, std::ceil(per_cell * g.bx / 32.0));
+        for (int block : blocks) {
+            if (forced_block && block != forced_block) continue;
+            const size_t smem = fc_smem_bytes(cap, ncs, block, typed);
+            if (smem > c->smem_optin) continue;
+            const int by_smem = (int)(per_sm / (smem + 1024));
+            const int by_regs = std::max(1, 65536 / (FC_REGS_ESTIMATE * block));
+            const int resident = std::min(std::min(by_smem, by_regs), 32);
+            if (resident < 1) continue;
+            const double active = resident * std::min<double>(block / 32, tasks);
+            // ties: fewer idle warps, then larger bricks (less halo staging per home atom)
+            const double score = active * 1000.0 - resident * (block / 32) + 0.01 * (g.bx * g.by * g.bz);
+            if (score > best_score) {
+                best_score = score; best_block = block; best_cap = cap;
+                best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
+                best_budget = per_sm / resident - 1024;
             }
         }
     }
-    if (best < 0) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: no brick shape fits shared memory (cells too populated); use a larger ndiv");
-    s->fc_cap = best_cap;
-    s->fc_smem = best_smem;
-    s->fc_block = block;
-    if ((int64_t)s->fc_nblocks > s->partial_cap) {
-        dev_free(s->partial); dev_free(s->partial_n);
-        s->partial_cap = s->fc_nblocks;
-        EMDEE_TRY(dev_alloc(&s->partial, (size_t)2 * s->partial_cap));
-        EMDEE_TRY(dev_alloc(&s->partial_n, (size_t)s->partial_cap));
-    }
-    return EMDEE_OK;
+    if (best_score < 0) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: no brick shape fits shared memory (cells too populated); use a larger ndiv");
+    set_brick_shape(s, best_shape);
+    for (int k = 0; k < 3; k++) s->fc_shape[k] = best_shape[k];
+    s->fc_smem_budget = std::min(best_budget, c->smem_optin);
+    return finish(best_cap, best_block);
 }
 
 static int do_bin(emdee_system *s, int ndiv)
@@ -832,7 +921,7 @@ static int do_bin_slab(emdee_system *s, int ndiv)
                             (arr), s->nlo, (arr) + own_end, s->nhi, sizeof(T)))
     GHOST_X(B.s[0], double); GHOST_X(B.s[1], double); GHOST_X(B.s[2], double);
     GHOST_X(B.hs, double); GHOST_X(B.ts, double);
-    GHOST_X(B.id, int32_t); GHOST_X(B.xbase, int32_t); GHOST_X(B.xmask, uint64_t);
+    GHOST_X(B.id, int32_t); GHOST_X(B.type, int32_t); GHOST_X(B.xbase, int32_t); GHOST_X(B.xmask, uint64_t);
 #undef GHOST_X
     NCCL_TRY(ncclGroupEnd());
     s->binned = true;
@@ -920,28 +1009,32 @@ extern "C" int emdee_get_local_ids(emdee_system *s, int32_t *ids)
 // ------------------------------------------------------------------------------------------------
 // force evaluation
 // ------------------------------------------------------------------------------------------------
-template <int BLOCK, bool F, bool EW, bool EXCL, bool AUDIT>
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
 static int launch_cells_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
-    auto kern = k_force_cells<BLOCK, F, EW, EXCL, AUDIT>;
+    auto kern = k_force_cells<F, EW, EXCL, AUDIT, TYPED>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fc_smem));
-    kern<<<nblocks, BLOCK, s->fc_smem, s->ctx->stream>>>(a);
+    kern<<<nblocks, s->fc_block, s->fc_smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_force_cells");
 }
-template <int BLOCK>
-static int launch_cells_b(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
+template <bool TYPED>
+static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
 {
-    if (AUDIT) return EXCL ? launch_cells_t<BLOCK, true, true, true, true>(s, a, nb) : launch_cells_t<BLOCK, true, true, false, true>(s, a, nb);
+    if (AUDIT) return EXCL ? launch_cells_t<true, true, true, true, TYPED>(s, a, nb) : launch_cells_t<true, true, false, true, TYPED>(s, a, nb);
     if (EXCL) {
-        if (F && EW) return launch_cells_t<BLOCK, true, true, true, false>(s, a, nb);
-        if (F) return launch_cells_t<BLOCK, true, false, true, false>(s, a, nb);
-        return launch_cells_t<BLOCK, false, true, true, false>(s, a, nb);
+        if (F && EW) return launch_cells_t<true, true, true, false, TYPED>(s, a, nb);
+        if (F) return launch_cells_t<true, false, true, false, TYPED>(s, a, nb);
+        return launch_cells_t<false, true, true, false, TYPED>(s, a, nb);
     }
-    if (F && EW) return launch_cells_t<BLOCK, true, true, false, false>(s, a, nb);
-    if (F) return launch_cells_t<BLOCK, true, false, false, false>(s, a, nb);
-    return launch_cells_t<BLOCK, false, true, false, false>(s, a, nb);
+    if (F && EW) return launch_cells_t<true, true, false, false, TYPED>(s, a, nb);
+    if (F) return launch_cells_t<true, false, false, false, TYPED>(s, a, nb);
+    return launch_cells_t<false, true, false, false, TYPED>(s, a, nb);
+}
+static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
+{
+    return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT);
 }
 
 // halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
@@ -949,17 +1042,18 @@ static int launch_cells_b(emdee_system *s, const CellArgs &a, int nb, bool F, bo
 static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false)
 {
     emdee_ctx *c = s->ctx;
+    if ((s->ntypes > 0) != s->fc_typed) EMDEE_TRY(choose_bricks(s));   // LJ classes changed since binning: re-size shared memory
     AtomArrays &A = s->A[s->cur];
     CellArgs a;
     a.g = s->g;
     a.cell_start = s->cell_start;
     a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2];
     a.hs = A.hs; a.ts = A.ts;
-    a.id = A.id; a.xbase = A.xbase; a.xmask = A.xmask;
+    a.id = A.id; a.type = A.type; a.xbase = A.xbase; a.xmask = A.xmask;
+    a.ljtab = s->ljtab; a.ntypes = s->ntypes;
     a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2];
     a.en = s->en; a.vir = s->vir;
     a.partial = s->partial;
-    a.partial_n = s->partial_n;
     a.digest = s->digest;
     a.pairs = pairs;
     a.pair_cap = pair_cap;
@@ -967,7 +1061,14 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     a.L = s->L;
     a.cell_edge = s->L / s->g.M;
     a.model = s->model;
-    a.rc2f = (float)(s->model.rc2 * (1.0 + 1e-3));
+    {   // conservative FP32 pre-cull threshold: rc2 plus a bound on the rounding error of
+        // |c|^2 - 2 c.p + |p|^2 for coordinates within the staged region (relative to the brick centre)
+        const double hx = 0.5 * (s->g.bx + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double hy = 0.5 * (s->g.by + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double hz = 0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double cmax2 = hx * hx + hy * hy + hz * hz;
+        a.rc2f = (float)(s->model.rc2 * (1.0 + 1e-4) + 64.0 * 1.2e-7 * cmax2);
+    }
     a.cap = s->fc_cap;
     a.ncs_max = s->fc_ncs;
     a.err = s->err;
@@ -1001,14 +1102,11 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     for (int k = 0; k < 3; k++) {
         if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
         a.block_first = ranges[k][0];
-        if (s->fc_block == 128)
-            EMDEE_TRY(launch_cells_b<128>(s, a, ranges[k][1], F, EW, s->has_excl, audit));
-        else
-            EMDEE_TRY(launch_cells_b<256>(s, a, ranges[k][1], F, EW, s->has_excl, audit));
+        EMDEE_TRY(launch_cells(s, a, ranges[k][1], F, EW, s->has_excl, audit));
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
     if (EW || audit) {
-        k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks, s->partial, s->totals);
+        k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks * (s->fc_block / 32), s->partial, s->totals);
         c->launches++;
     }
     return check_launch("k_reduce_partials");

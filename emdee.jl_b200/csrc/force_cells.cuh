@@ -6,32 +6,45 @@
 // One thread block owns a HOME BRICK of bx*by*bz cells.  It stages the brick plus a halo of R cells
 // (27-cell neighbourhoods for R=1, 125 for R=2) in shared memory: because atoms are sorted by
 // (cell, id) with x fastest, every staged row of cells is at most two contiguous slot ranges, so
-// the loads are coalesced streams.  Per staged atom: FP64 scaled position (exact geometry), LJ
-// parameters, and an FP32 position relative to the brick origin (periodic image resolved per cell).
+// the loads are coalesced streams.  Per staged atom: two 16-byte FP64 records {s_x, s_y} and
+// {s_z, id|type} (exact geometry, two LDS.128 per neighbour) and a 16-byte FP32 record {x, y, z, |c|^2} relative to
+// the brick centre with the periodic image resolved per cell.
 //
-// Each thread owns one home atom i (full-neighbour scheme: no atomics, no reaction scatter; e_i and
-// w_i get half of every pair like src/nonbonded.jl:93-94).  Work is split by pipe:
-//   scan  (FP32/INT pipes): walk the (2R+1)^2 candidate rows, conservative FP32 distance test,
-//                           append survivors to a per-lane queue in shared memory;
-//   drain (FP64 pipe)     : exact minimum-image r2 in the oracle's rounding sequence, exact cull
-//                           r2 <= rc2 (bit-exact pair set), interaction(), accumulate f, E, W.
+// Work unit = WARP TASK: 32 consecutive home atoms of one home row (cells contiguous in x), one atom
+// per lane, handed out dynamically (no trailing block barrier).  Full-neighbour scheme: every lane
+// accumulates its own atom, no atomics, no reaction scatter; e_i and w_i get half of every pair like
+// src/nonbonded.jl:93-94.  Each task alternates two phases that use different pipes:
+//   scan  (FP32/INT pipes): all lanes walk the SAME candidate window -- the (2R+1)^2 staged rows
+//          around the task's row, cells [first-R, last+R] -- so every LDS.128 is a one-address
+//          broadcast and control flow is warp-uniform; a conservative FP32 distance test
+//          (|c|^2 - 2 c.p + |p|^2: one add and three FMAs per candidate) pushes survivors on a
+//          per-lane stack of staged indices in shared memory;
+//   drain (FP64 pipe): two stack entries per iteration, branch-free: exact minimum-image r2 in the
+//          oracle's rounding sequence, exact cull r2 <= rc2 (bit-exact pair set), interaction(),
+//          predicated accumulation of f, E, W.  When a stack nears capacity only the excess is
+//          popped (from every lane), so lanes stay evenly loaded until the final drain.
 // The FP64 pipe (64 lanes/clk/SM) therefore only sees pairs that are inside the cutoff (plus a
-// 1e-3 margin), at full lane occupancy, instead of the 6.5x larger candidate set.
+// 1e-3 margin) at high lane occupancy, instead of the ~10x larger candidate set.
 #pragma once
 #include "lj_pair.cuh"
 
 #define FC_QCAP 64          // per-lane queue entries (uint16 staged indices)
+#define FC_QCHUNK 16        // candidates scanned between queue-capacity checks
 #define FC_MAX_HOMEROWS 64  // by*bz of the largest supported brick
+#define FC_MAX_TYPES 16     // LJ parameter classes held as a pair table in shared memory
+
+#define FC_MAX_BLOCK 384     // launch bound: 12 warps, up to 170 registers per thread
 
 struct CellArgs {
     GridDesc g;
     const int32_t *cell_start;   // local cells + 1
     const double *sx, *sy, *sz, *hs, *ts;
-    const int32_t *id, *xbase;
+    const int32_t *id, *type, *xbase;
     const uint64_t *xmask;
+    const double2 *ljtab;             // ntypes^2 entries {half_sigma_a + half_sigma_b, twice_sqrt_eps_a * twice_sqrt_eps_b}
+    int ntypes;                       // 0: more than FC_MAX_TYPES classes, per-atom parameters are gathered from global
     double *fx, *fy, *fz, *en, *vir;
-    double *partial;                  // per block: {sum e_i, sum w_i}
-    unsigned long long *partial_n;    // per block: pairs with id_i < id_j
+    double *partial;                  // per warp: {sum e_i, sum w_i}
     unsigned long long *digest;       // AUDIT: {count, sum hash, xor hash}
     int32_t *pairs;                   // AUDIT: optional pair list (2 x pair_cap)
     long long pair_cap;
@@ -46,12 +59,14 @@ struct CellArgs {
     int block_first;                  // first brick of this launch (launches may cover a z-layer range)
 };
 
-__host__ __device__ inline size_t fc_smem_bytes(int cap, int ncs_max, int block)
+__host__ __device__ inline size_t fc_smem_bytes(int cap, int ncs_max, int block, bool typed)
 {
-    size_t b = (size_t)cap * (5 * sizeof(double) + sizeof(float4));
+    size_t b = (size_t)cap * (2 * sizeof(double2) + sizeof(float4));
+    if (!typed) b += (size_t)cap * sizeof(int);      // slot of every staged atom (per-atom parameter gathers)
+    b += (size_t)FC_MAX_TYPES * FC_MAX_TYPES * sizeof(double2);
     b += (size_t)(ncs_max + 1) * sizeof(int) * 2;    // cs[], gbase[]
-    b += (FC_MAX_HOMEROWS + 1) * sizeof(int);        // hstart[]
-    b += 16;                                         // scalars
+    b += 2 * (FC_MAX_HOMEROWS + 1) * sizeof(int);    // hstart[], tstart[]
+    b += 8 * sizeof(int);                            // scalars
     b = (b + 15) & ~(size_t)15;
     b += (size_t)FC_QCAP * block * sizeof(uint16_t);
     return b;
@@ -63,24 +78,29 @@ __device__ __forceinline__ int wrap_mod(int a, int M)
     return a < 0 ? a + M : a;
 }
 
-template <int BLOCK, bool F, bool EW, bool EXCL, bool AUDIT>
-__global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
+__global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
 {
+    const int BLOCK = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap = a.cap;
-    double *sxs = reinterpret_cast<double *>(smem_raw);
-    double *sys = sxs + cap, *szs = sys + cap, *hss = szs + cap, *tss = hss + cap;
-    float4 *prel = reinterpret_cast<float4 *>(tss + cap);
-    int *cs = reinterpret_cast<int *>(prel + cap);
+    double2 *pxy = reinterpret_cast<double2 *>(smem_raw);      // {s_x, s_y}, s = r/L (src/nonbonded.jl:60-61)
+    double2 *pzm = pxy + cap;                                  // {s_z, (type << 32) | id}
+    float4 *prel = reinterpret_cast<float4 *>(pzm + cap);
+    constexpr bool typed = TYPED;    // LJ classes through the shared-memory pair table; else per-atom gathers
+    int *sslot = reinterpret_cast<int *>(prel + cap);
+    double2 *ljt = reinterpret_cast<double2 *>(sslot + (typed ? 0 : cap));
+    int *cs = reinterpret_cast<int *>(ljt + FC_MAX_TYPES * FC_MAX_TYPES);
     int *gbase = cs + (a.ncs_max + 1);
     int *hstart = gbase + (a.ncs_max + 1);
-    int *scal = hstart + (FC_MAX_HOMEROWS + 1);
+    int *tstart = hstart + (FC_MAX_HOMEROWS + 1);
+    int *scal = tstart + (FC_MAX_HOMEROWS + 1);
     uint16_t *queue = reinterpret_cast<uint16_t *>(
-        smem_raw + ((reinterpret_cast<unsigned char *>(scal + 4) - smem_raw + 15) & ~(size_t)15));
+        smem_raw + ((reinterpret_cast<unsigned char *>(scal + 8) - smem_raw + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NW = BLOCK / 32;
+    const int NW = BLOCK / 32;
     const int R = g.R, M = g.M;
 
     // ---- brick geometry ---------------------------------------------------------------------
@@ -105,6 +125,8 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
         gbase[t] = s0;
         cs[t] = a.cell_start[lc + 1] - s0;
     }
+    if (typed)
+        for (int t = tid; t < a.ntypes * a.ntypes; t += BLOCK) ljt[t] = a.ljtab[t];
     __syncthreads();
     if (warp == 0) {   // exclusive scan of the counts, 32 at a time
         int run = 0;
@@ -123,23 +145,30 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
         if (lane == 0) cs[ncs] = run;
         __syncwarp();
         if (lane == 0) {
-            // home rows: the atoms of the home cells of row (hy,hz) are one contiguous staged range
-            int h = 0;
+            // home rows: the atoms of the home cells of row (hy,hz) are one contiguous staged range;
+            // warp tasks: chunks of 32 consecutive atoms of one home row
+            int h = 0, t = 0;
             for (int hz = 0; hz < nhz; hz++)
                 for (int hy = 0; hy < nhy; hy++) {
                     hstart[hz * nhy + hy] = h;
+                    tstart[hz * nhy + hy] = t;
                     const int row = (hz + R) * syn + (hy + R);
-                    h += cs[row * sxn + R + nhx] - cs[row * sxn + R];
+                    const int n = cs[row * sxn + R + nhx] - cs[row * sxn + R];
+                    h += n;
+                    t += (n + 31) >> 5;
                 }
             hstart[nhy * nhz] = h;
-            scal[0] = h;      // nhome
-            scal[1] = run;    // nstaged
+            tstart[nhy * nhz] = t;
+            scal[0] = h;      // home atoms
+            scal[1] = run;    // staged atoms
+            scal[2] = t;      // warp tasks
+            scal[3] = 0;      // task cursor
             if (run > cap) atomicExch(a.err, 2);
         }
     }
     __syncthreads();
-    const int nhome = scal[0];
     const int nstaged = min(scal[1], cap);
+    const int ntasks = scal[2];
 
     // ---- phase B: stage atoms row by row (each row = up to two contiguous slot ranges) --------
     for (int piece = warp; piece < 2 * nrows; piece += NW) {
@@ -150,120 +179,157 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
         const int len1 = min(sxn, M - gx0);            // cells before the periodic wrap
         const int cfirst = second ? len1 : 0, clast = second ? sxn : len1;
         if (cfirst >= clast) continue;
-        const int ibeg = cs[row * sxn + cfirst], iend = cs[row * sxn + clast];
+        const int ibeg = cs[row * sxn + cfirst], iend = min(cs[row * sxn + clast], cap);
         const int sbeg = gbase[row * sxn + cfirst];
-        const double ccy = (double)(cy - R) + 0.5, ccz = (double)(cz - R) + 0.5;   // cell centre, brick-relative, cell units
+        // cell centre relative to the brick centre, in cell units
+        const double ccy = (double)(cy - R) + 0.5 - 0.5 * nhy, ccz = (double)(cz - R) + 0.5 - 0.5 * nhz;
         const double csy = ((double)(hy0 - R + cy) + 0.5) / M;                      // unwrapped scaled centre
         const int uz = (g.zwrap ? hz0 : g.zglob0 + hz0) - R + cz;
         const double csz = ((double)uz + 0.5) / M;
-        for (int idx = ibeg + lane; idx < iend && idx < cap; idx += 32) {
+        for (int idx = ibeg + lane; idx < iend; idx += 32) {
             const int slot = sbeg + (idx - ibeg);
             int cx = cfirst;
             while (cx + 1 < clast && cs[row * sxn + cx + 1] <= idx) cx++;
-            const double x = a.sx[slot], y = a.sy[slot], z = a.sz[slot];
-            sxs[idx] = x; sys[idx] = y; szs[idx] = z;
-            hss[idx] = a.hs[slot]; tss[idx] = a.ts[slot];
+            const double sxv = a.sx[slot], syv = a.sy[slot], szv = a.sz[slot];
+            pxy[idx] = make_double2(sxv, syv);
+            pzm[idx] = make_double2(szv, __hiloint2double(typed ? a.type[slot] : 0, a.id[slot]));
+            if (!typed) sslot[idx] = slot;
             const double csx = ((double)(ux0 + cx) + 0.5) / M;
-            double dx = x - csx, dy = y - csy, dz = z - csz;
+            double dx = sxv - csx, dy = syv - csy, dz = szv - csz;
             dx -= rint(dx); dy -= rint(dy); dz -= rint(dz);      // image nearest to the staged cell
             float4 p;
-            p.x = (float)(a.L * dx + ((double)(cx - R) + 0.5) * a.cell_edge);
+            p.x = (float)(a.L * dx + ((double)(cx - R) + 0.5 - 0.5 * nhx) * a.cell_edge);
             p.y = (float)(a.L * dy + ccy * a.cell_edge);
             p.z = (float)(a.L * dz + ccz * a.cell_edge);
-            p.w = __int_as_float(slot);
+            p.w = fmaf(p.z, p.z, fmaf(p.y, p.y, p.x * p.x));
             prel[idx] = p;
         }
     }
     __syncthreads();
 
-    // ---- phases C+D: one home atom per lane, scan (FP32) / drain (FP64) -------------------------
+    // ---- phase C: warp tasks -----------------------------------------------------------------
     const double c60id2 = 60.0 * a.model.id2;
+    const double rc2 = a.model.rc2, L = a.L;
     const float rc2f = a.rc2f;
+    const int nwin = 2 * R + 1;
     double esum = 0, wsum = 0;
     unsigned long long npair = 0, hsum = 0, hxor = 0;
 
-    for (int hbase = warp * 32; hbase < nhome; hbase += NW * 32) {
-        const int h = hbase + lane;
-        const bool active = h < nhome;
-        int self = 0, cxi = R, cyi = R, czi = R;
-        if (active) {
-            int hr = 0;
-            while (hstart[hr + 1] <= h) hr++;
-            cyi = hr % nhy + R; czi = hr / nhy + R;
-            const int row = czi * syn + cyi;
-            self = cs[row * sxn + R] + (h - hstart[hr]);
-            while (cs[row * sxn + cxi + 1] <= self) cxi++;
-        }
-        const float4 pi = prel[active ? self : 0];
-        const double six = sxs[self], siy = sys[self], siz = szs[self], hsi = hss[self], tsi = tss[self];
-        const int slot_i = __float_as_int(pi.w);
-        int32_t idi = 0, xb = 0; uint64_t xm = 0;
-        if (EXCL || AUDIT) idi = a.id[slot_i];
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&scal[3], 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= ntasks) break;
+        int hr = 0;
+        while (tstart[hr + 1] <= t) hr++;
+        const int cyi = hr % nhy + R, czi = hr / nhy + R;
+        const int hrow = czi * syn + cyi;
+        const int a0 = cs[hrow * sxn + R] + ((t - tstart[hr]) << 5);
+        const int a1 = min(a0 + 32, cs[hrow * sxn + R + nhx]);
+        int cxa = R, cxb = R;
+        while (cs[hrow * sxn + cxa + 1] <= a0) cxa++;
+        while (cs[hrow * sxn + cxb + 1] <= a1 - 1) cxb++;
+        const int self = a0 + lane;
+        const bool active = self < a1;
+        const int me = active ? self : a0;
+
+        const float4 pi = prel[me];
+        // r2 = |c|^2 + (|p|^2 - 2 c.p); an inactive lane gets |p|^2 = 1e30 and never accepts anything
+        const float m2x = -2.0f * pi.x, m2y = -2.0f * pi.y, m2z = -2.0f * pi.z, pp = active ? pi.w : 1e30f;
+        int cxi = cxa;
+        while (cs[hrow * sxn + cxi + 1] <= me) cxi++;
+        const int slot_i = gbase[hrow * sxn + cxi] + (me - cs[hrow * sxn + cxi]);
+        const double2 q0 = pxy[me], q1 = pzm[me];
+        const double six = q0.x, siy = q0.y, siz = q1.x;
+        const int32_t idi = __double2loint(q1.y), typi = __double2hiint(q1.y);
+        double hsi = 0, tsi = 0;
+        if (!typed) { hsi = a.hs[slot_i]; tsi = a.ts[slot_i]; }
+        const double2 *ljrow = ljt + typi * a.ntypes;
+        int32_t xb = 0; uint64_t xm = 0;
         if (EXCL) { xb = a.xbase[slot_i]; xm = a.xmask[slot_i]; }
         double fx = 0, fy = 0, fz = 0, e = 0, w = 0;
+        int cnt = 0;                            // entries on this lane's stack: queue[k*BLOCK + tid], k < cnt
+        uint16_t *qp = queue + tid;             // next free entry
 
-        // candidate iterator: (2R+1)^2 rows, each a contiguous staged range
-        const int nwin = 2 * R + 1;
-        int rw = active ? 0 : nwin * nwin;   // next row-window index
-        int p = 0, pend = 0;
-        for (;;) {
-            int cnt = 0;
-            // -------- scan --------
-            while (cnt < FC_QCAP) {
-                if (p == pend) {
-                    if (rw == nwin * nwin) break;
-                    const int dy = rw % nwin - R, dz = rw / nwin - R;
-                    const int row = (czi + dz) * syn + (cyi + dy);
-                    p = cs[row * sxn + cxi - R];
-                    pend = min(cs[row * sxn + cxi + R + 1], nstaged);
-                    rw++;
-                    continue;
-                }
-                const float4 c = prel[p];
-                const float dx = c.x - pi.x, dy = c.y - pi.y, dz = c.z - pi.z;
-                const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (r2 <= rc2f && p != self) {
-                    queue[cnt * BLOCK + tid] = (uint16_t)p;
-                    cnt++;
-                }
-                p++;
+        // one stack entry, branch-free: invalid or culled entries contribute nothing
+        auto pair_eval = [&](int idx, bool valid) {
+            const int j = valid ? (int)queue[idx * BLOCK + tid] : me;
+            const double2 j0 = pxy[j], j1 = pzm[j];
+            double vx, vy, vz;
+            const double r2 = min_image_r2(six, siy, siz, j0.x, j0.y, j1.x, L, vx, vy, vz);
+            bool ok = valid && (j != me) && (r2 <= rc2);
+            const int32_t idj = __double2loint(j1.y);
+            if (EXCL) ok = ok && !pair_excluded(xb, xm, idj);
+            double sig, tt;
+            if (!typed) {
+                const int slot_j = sslot[j];
+                sig = hsi + a.hs[slot_j];
+                tt = tsi * a.ts[slot_j];
+            } else {
+                const double2 pr = ljrow[__double2hiint(j1.y)];   // one class: every lane reads entry 0 (broadcast)
+                sig = pr.x; tt = pr.y;
             }
-            // -------- drain --------
-            const int maxcnt = __reduce_max_sync(0xffffffffu, cnt);
-            if (maxcnt == 0) break;
-            for (int q = 0; q < maxcnt; q++) {
-                if (q < cnt) {
-                    const int j = queue[q * BLOCK + tid];
-                    double vx, vy, vz;
-                    const double r2 = min_image_r2(six, siy, siz, sxs[j], sys[j], szs[j], a.L, vx, vy, vz);
-                    bool ok = r2 <= a.model.rc2;
-                    int32_t idj = 0;
-                    if (EXCL || AUDIT) {
-                        if (ok) idj = a.id[__float_as_int(prel[j].w)];
-                        if (EXCL && ok && pair_excluded(xb, xm, idj)) ok = false;
-                    }
-                    if (ok) {
-                        const double inv = rcp_fast(r2);
-                        double Eg, Wg;
-                        lj_interaction(r2, inv, hsi + hss[j], tsi * tss[j], a.model, c60id2, Eg, Wg);
-                        if (F) {
-                            const double qf = Wg * inv;
-                            fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
-                        }
-                        if (EW) { e += Eg; w += Wg; }
-                        if (AUDIT && idi < idj) {
-                            const uint64_t hh = pair_hash(idi, idj);
-                            npair++; hsum += hh; hxor ^= hh;
-                            if (a.pairs) {
-                                const unsigned long long k = atomicAdd(a.pair_n, 1ull);
-                                if ((long long)k < a.pair_cap) { a.pairs[2 * k] = idi; a.pairs[2 * k + 1] = idj; }
-                            }
-                        }
-                    }
+            const double r2s = ok ? r2 : 1.0;
+            const double inv = rcp_fast(r2s);
+            double Eg, Wg;
+            lj_interaction(r2s, inv, sig, tt, a.model, c60id2, Eg, Wg);
+            if (F) {
+                const double qf = ok ? Wg * inv : 0.0;
+                fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+            }
+            if (EW) { e += ok ? Eg : 0.0; w += ok ? Wg : 0.0; }
+            if (AUDIT && ok && idi < idj) {
+                const uint64_t hh = pair_hash(idi, idj);
+                npair++; hsum += hh; hxor ^= hh;
+                if (a.pairs) {
+                    const unsigned long long k = atomicAdd(a.pair_n, 1ull);
+                    if ((long long)k < a.pair_cap) { a.pairs[2 * k] = idi; a.pairs[2 * k + 1] = idj; }
                 }
             }
-            if (__all_sync(0xffffffffu, rw == nwin * nwin && p == pend)) break;
+        };
+        // pop the newest `depth` entries of every lane (all of them when depth >= the fullest stack)
+        auto drain = [&](int depth) {
+            for (int k = 0; k < depth; k += 4) {      // four independent pair evaluations in flight
+                pair_eval(cnt - 1 - k, k < cnt);
+                pair_eval(cnt - 2 - k, k + 1 < cnt && k + 1 < depth);
+                pair_eval(cnt - 3 - k, k + 2 < cnt && k + 2 < depth);
+                pair_eval(cnt - 4 - k, k + 3 < cnt && k + 3 < depth);
+            }
+            cnt = max(cnt - depth, 0);
+            qp = queue + cnt * BLOCK + tid;
+        };
+
+        // -------- scan: (2R+1)^2 rows, one shared window of cells [cxa-R, cxb+R] per row --------
+        for (int rw = 0; rw < nwin * nwin; rw++) {
+            const int row = (czi + rw / nwin - R) * syn + (cyi + rw % nwin - R);
+            const int p0 = cs[row * sxn + cxa - R];
+            const int p1 = min(cs[row * sxn + cxb + R + 1], nstaged);
+            for (int pb = p0; pb < p1; pb += FC_QCHUNK) {
+                const int pe = min(pb + FC_QCHUNK, p1);
+                // four candidates per iteration: the loads are issued together (one-address broadcasts)
+                int p = pb;
+                for (; p + 4 <= pe; p += 4) {
+                    const float4 c0 = prel[p], c1 = prel[p + 1], c2 = prel[p + 2], c3 = prel[p + 3];
+                    const float r0 = fmaf(c0.x, m2x, fmaf(c0.y, m2y, fmaf(c0.z, m2z, c0.w + pp)));
+                    const float r1 = fmaf(c1.x, m2x, fmaf(c1.y, m2y, fmaf(c1.z, m2z, c1.w + pp)));
+                    const float r2 = fmaf(c2.x, m2x, fmaf(c2.y, m2y, fmaf(c2.z, m2z, c2.w + pp)));
+                    const float r3 = fmaf(c3.x, m2x, fmaf(c3.y, m2y, fmaf(c3.z, m2z, c3.w + pp)));
+                    if (r0 <= rc2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
+                    if (r1 <= rc2f) { *qp = (uint16_t)(p + 1); qp += BLOCK; cnt++; }
+                    if (r2 <= rc2f) { *qp = (uint16_t)(p + 2); qp += BLOCK; cnt++; }
+                    if (r3 <= rc2f) { *qp = (uint16_t)(p + 3); qp += BLOCK; cnt++; }
+                }
+                for (; p < pe; p++) {
+                    const float4 c = prel[p];
+                    const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
+                    if (r <= rc2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
+                }
+                const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
+                if (over > 0) drain(over);
+            }
         }
+        drain(__reduce_max_sync(0xffffffffu, cnt));
+
         if (active) {
             if (F) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
             if (EW) {
@@ -274,38 +340,27 @@ __global__ void __launch_bounds__(BLOCK) k_force_cells(CellArgs a)
         }
     }
 
-    // ---- block totals in a fixed order (deterministic) ----------------------------------------
-    __syncthreads();
-    if (EW || AUDIT) {
-        double *red = sxs;    // staged data no longer needed
-        unsigned long long *redn = reinterpret_cast<unsigned long long *>(red + 2 * NW);
+    // ---- per-warp totals (summed later in a fixed order: deterministic) ---------------------------
+    if (EW) {
         esum = warp_sum_f64(esum); wsum = warp_sum_f64(wsum);
+        if (lane == 0) { a.partial[2 * (bid * NW + warp)] = esum; a.partial[2 * (bid * NW + warp) + 1] = wsum; }
+    }
+    if (AUDIT) {
         for (int o = 16; o > 0; o >>= 1) {
             npair += __shfl_xor_sync(0xffffffffu, npair, o);
             hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
             hxor ^= __shfl_xor_sync(0xffffffffu, hxor, o);
         }
-        if (lane == 0) { red[warp] = esum; red[NW + warp] = wsum; redn[warp] = npair; redn[NW + warp] = hsum; redn[2 * NW + warp] = hxor; }
-        __syncthreads();
-        if (tid == 0) {
-            double E = 0, W = 0; unsigned long long n = 0, hs_ = 0, hx_ = 0;
-            for (int k = 0; k < NW; k++) { E += red[k]; W += red[NW + k]; n += redn[k]; hs_ += redn[NW + k]; hx_ ^= redn[2 * NW + k]; }
-            if (EW) { a.partial[2 * bid] = E; a.partial[2 * bid + 1] = W; }
-            if (AUDIT) {
-                a.partial_n[bid] = n;
-                atomicAdd(a.digest, n); atomicAdd(a.digest + 1, hs_); atomicXor(a.digest + 2, hx_);
-            }
-        }
+        if (lane == 0 && npair) { atomicAdd(a.digest, npair); atomicAdd(a.digest + 1, hsum); atomicXor(a.digest + 2, hxor); }
     }
 }
 
-// Sum the per-block partials in index order: deterministic totals.
-__global__ void k_reduce_partials(int nblocks, const double *__restrict__ partial, double *__restrict__ totals)
+// Sum the per-warp partials in index order: deterministic totals.
+__global__ void k_reduce_partials(int n, const double *__restrict__ partial, double *__restrict__ totals)
 {
     __shared__ double sE[256], sW[256];
     double E = 0, W = 0;
-    // fixed assignment of blocks to threads, fixed tree afterwards
-    for (int b = threadIdx.x; b < nblocks; b += 256) { E += partial[2 * b]; W += partial[2 * b + 1]; }
+    for (int b = threadIdx.x; b < n; b += 256) { E += partial[2 * b]; W += partial[2 * b + 1]; }
     sE[threadIdx.x] = E; sW[threadIdx.x] = W;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) {

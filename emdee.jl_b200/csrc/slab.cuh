@@ -10,7 +10,7 @@
 #pragma once
 #include "binning.cuh"
 
-#define MIG_FIELDS 12   // doubles per migrating atom: r(3) v(3) hs ts mass | id, xbase (as 2 doubles) | xmask
+#define MIG_FIELDS 12   // doubles per migrating atom: r(3) v(3) hs ts mass | (id,type) | xbase | xmask
 
 // Classify owned atoms at a slab re-bin.  Planes [z0, z0+nz) are mine; an atom that left goes to the
 // lower / upper neighbour if it is within R planes of my range (it cannot have moved further between
@@ -58,7 +58,7 @@ __global__ void k_pack_migrants(int n, const int32_t *__restrict__ list, AtomArr
     buf[(size_t)6 * n + a] = A.hs[i];
     buf[(size_t)7 * n + a] = A.ts[i];
     buf[(size_t)8 * n + a] = A.mass[i];
-    buf[(size_t)9 * n + a] = __longlong_as_double((long long)A.id[i]);
+    buf[(size_t)9 * n + a] = __hiloint2double(A.type[i], A.id[i]);
     buf[(size_t)10 * n + a] = __longlong_as_double((long long)A.xbase[i]);
     buf[(size_t)11 * n + a] = __longlong_as_double((long long)A.xmask[i]);
 }
@@ -83,7 +83,8 @@ __global__ void k_unpack_migrants(int n, const double *__restrict__ buf, int64_t
     A.hs[i] = buf[(size_t)6 * n + a];
     A.ts[i] = buf[(size_t)7 * n + a];
     A.mass[i] = buf[(size_t)8 * n + a];
-    A.id[i] = (int32_t)__double_as_longlong(buf[(size_t)9 * n + a]);
+    A.id[i] = __double2loint(buf[(size_t)9 * n + a]);
+    A.type[i] = __double2hiint(buf[(size_t)9 * n + a]);
     A.xbase[i] = (int32_t)__double_as_longlong(buf[(size_t)10 * n + a]);
     A.xmask[i] = (uint64_t)__double_as_longlong(buf[(size_t)11 * n + a]);
     const int x = cell_coord(s[0], M), y = cell_coord(s[1], M), z = cell_coord(s[2], M);
