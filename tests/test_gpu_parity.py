@@ -335,3 +335,24 @@ def test_large_system_properties(em, oracle):
         res[ndiv] = f
         s.close()
     assert np.abs(res[1] - res[2]).max() <= F_TOL * frms(res[1])
+
+
+def test_slab_decomposition_multi_gpu():
+    """2 (or more) GPUs: z-slab decomposition with NCCL halo exchange and migration vs the oracle.
+    Skipped on a single-GPU box; the host-side logic is covered on CPU by tests/test_slabs_gloo.py."""
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for world, ndiv in ((2, 1), (min(ngpu, 4), 2)):
+        env = dict(os.environ, SLAB_N="16", SLAB_NDIV=str(ndiv))
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                              "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "slab_worker.py")],
+                             env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0 and "SLAB_RESULT" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]
