@@ -36,8 +36,7 @@ def build_library(force=False, verbose=False):
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "emdee_b200.cu")]
-    if os.path.exists("/usr/include/nccl.h"):
-        cmd += ["-lnccl"]
+    cmd += ["-ldl"]      # NCCL is dlopen'ed at run time (see csrc/emdee_b200.cu), never linked
     subprocess.check_call(cmd)
     return LIB_PATH
 

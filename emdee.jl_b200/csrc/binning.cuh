@@ -46,7 +46,7 @@ __global__ void k_cell_index(int64_t first, int64_t n, const double *__restrict_
     if (!zwrap) {            // slab: bring z into [zglob0, zglob0+M) then it must fall in the local planes
         if (zl < 0) zl += M;
         if (zl >= M) zl -= M;
-        if (zl >= nzt) { atomicExch(err, 1); zl = nzt - 1; }
+        if (zl >= nzt) { atomicCAS(err, 0, 1); zl = nzt - 1; }
     }
     const int lc = x + M * (y + M * zl);
     lcell[i] = lc;

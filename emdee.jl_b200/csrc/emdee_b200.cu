@@ -16,7 +16,47 @@
 
 #define FC_REGS_ESTIMATE 128   // registers per thread of k_force_cells assumed by the residency model
 
+// NCCL is bound at run time (dlopen) instead of link time: a host process that also imports PyTorch must end
+// up with ONE libnccl.so.2 (torch bundles 2.28, the system has 2.27); dlopen by soname returns whichever copy
+// is already loaded, and single-GPU users need no NCCL at all.
+#include <dlfcn.h>
 #include <nccl.h>
+struct NcclApi {
+    void *handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load()
+{
+    if (g_nccl.handle) return EMDEE_OK;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) EMDEE_FAIL(EMDEE_ERR_NCCL, "cannot load libnccl.so.2: %s", dlerror());
+#define NCCL_SYM(field, name)                                                                     \
+    *(void **)(&g_nccl.field) = dlsym(h, name);                                                   \
+    if (!g_nccl.field) EMDEE_FAIL(EMDEE_ERR_NCCL, "libnccl.so.2 lacks %s", name);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank") NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv") NCCL_SYM(GroupStart, "ncclGroupStart") NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    g_nccl.handle = h;
+    return EMDEE_OK;
+}
+#define ncclGetUniqueId g_nccl.GetUniqueId
+#define ncclCommInitRank g_nccl.CommInitRank
+#define ncclCommDestroy g_nccl.CommDestroy
+#define ncclSend g_nccl.Send
+#define ncclRecv g_nccl.Recv
+#define ncclGroupStart g_nccl.GroupStart
+#define ncclGroupEnd g_nccl.GroupEnd
+#define ncclGetErrorString g_nccl.GetErrorString
 #define NCCL_TRY(expr)                                                                              \
     do {                                                                                            \
         ncclResult_t _r = (expr);                                                                   \
@@ -92,6 +132,12 @@ struct emdee_system {
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
     bool fc_typed = false;
     int fc_shape[3] = {0, 0, 0};
+    int fc_tmax = 0;                          // warp-task slots per brick (pair-list addressing)
+    uint16_t *list = nullptr;                 // pair-list rows (Verlet list over staged indices)
+    int32_t *list_rows = nullptr;
+    int64_t list_slots = 0;
+    int lcap = 256;                           // rows per task
+    bool list_valid = false, use_list = true;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
     double *partial = nullptr;
@@ -211,6 +257,7 @@ extern "C" int emdee_comm_unique_id(char id[128])
 {
     if (!id) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_unique_id: null buffer");
     static_assert(NCCL_UNIQUE_ID_BYTES == 128, "ncclUniqueId is expected to be 128 bytes");
+    EMDEE_TRY(nccl_load());
     ncclUniqueId u;
     NCCL_TRY(ncclGetUniqueId(&u));
     memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
@@ -224,6 +271,7 @@ extern "C" int emdee_comm_init(emdee_ctx *c, int rank, int nranks, const char id
     if (nranks == 1) return EMDEE_OK;
     if (!id) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_comm_init: null id");
     CUDA_TRY(cudaSetDevice(c->device));
+    EMDEE_TRY(nccl_load());
     ncclUniqueId u;
     memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
     NCCL_TRY(ncclCommInitRank(&c->comm, nranks, u, rank));
@@ -333,6 +381,8 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     s->ctx = c;
     s->N = N;
     s->L = L;
+    if (const char *e = getenv("EMDEE_LIST")) s->use_list = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_LIST_ROWS")) s->lcap = std::max(32, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -387,6 +437,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
+    dev_free(s->list); dev_free(s->list_rows);
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     delete s;
@@ -658,8 +709,16 @@ static int choose_bricks(emdee_system *s)
     const size_t per_sm = c->smem_optin + 1024;          // usable shared memory per SM (1 KB reserved per block)
     const int64_t ntot = s->nlo + s->nown + s->nhi;
     const double per_cell = (double)ntot / (double)std::max<int64_t>(1, (int64_t)g.M * g.M * g.nzt);
+    int maxpop = 0;
+    CUDA_TRY(cudaMemcpyAsync(&maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
     auto finish = [&](int cap, int block) -> int {
         s->fc_cap = cap;
+        // task slots per brick from the densest cell, with head-room so that density fluctuations between
+        // re-binnings do not resize the pair list
+        const int tmax = g.by * g.bz * ((g.bx * (std::max(maxpop, 1) + 8) + 31) / 32);
+        if (tmax > s->fc_tmax || tmax * 2 < s->fc_tmax) s->fc_tmax = tmax;
+        s->list_valid = false;
         s->fc_ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         s->fc_block = block;
         s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
@@ -1009,37 +1068,41 @@ extern "C" int emdee_get_local_ids(emdee_system *s, int32_t *ids)
 // ------------------------------------------------------------------------------------------------
 // force evaluation
 // ------------------------------------------------------------------------------------------------
-template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED, int MODE>
 static int launch_cells_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
-    auto kern = k_force_cells<F, EW, EXCL, AUDIT, TYPED>;
+    auto kern = k_force_cells<F, EW, EXCL, AUDIT, TYPED, MODE>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fc_smem));
     kern<<<nblocks, s->fc_block, s->fc_smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_force_cells");
 }
 template <bool TYPED>
-static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
+static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT, int mode)
 {
-    if (AUDIT) return EXCL ? launch_cells_t<true, true, true, true, TYPED>(s, a, nb) : launch_cells_t<true, true, false, true, TYPED>(s, a, nb);
-    if (EXCL) {
-        if (F && EW) return launch_cells_t<true, true, true, false, TYPED>(s, a, nb);
-        if (F) return launch_cells_t<true, false, true, false, TYPED>(s, a, nb);
-        return launch_cells_t<false, true, true, false, TYPED>(s, a, nb);
+    if (mode != 0) {   // pair-list build / use: the stepping loop evaluates forces only
+        if (mode == 1) return EXCL ? launch_cells_t<true, false, true, false, TYPED, 1>(s, a, nb) : launch_cells_t<true, false, false, false, TYPED, 1>(s, a, nb);
+        return EXCL ? launch_cells_t<true, false, true, false, TYPED, 2>(s, a, nb) : launch_cells_t<true, false, false, false, TYPED, 2>(s, a, nb);
     }
-    if (F && EW) return launch_cells_t<true, true, false, false, TYPED>(s, a, nb);
-    if (F) return launch_cells_t<true, false, false, false, TYPED>(s, a, nb);
-    return launch_cells_t<false, true, false, false, TYPED>(s, a, nb);
+    if (AUDIT) return EXCL ? launch_cells_t<true, true, true, true, TYPED, 0>(s, a, nb) : launch_cells_t<true, true, false, true, TYPED, 0>(s, a, nb);
+    if (EXCL) {
+        if (F && EW) return launch_cells_t<true, true, true, false, TYPED, 0>(s, a, nb);
+        if (F) return launch_cells_t<true, false, true, false, TYPED, 0>(s, a, nb);
+        return launch_cells_t<false, true, true, false, TYPED, 0>(s, a, nb);
+    }
+    if (F && EW) return launch_cells_t<true, true, false, false, TYPED, 0>(s, a, nb);
+    if (F) return launch_cells_t<true, false, false, false, TYPED, 0>(s, a, nb);
+    return launch_cells_t<false, true, false, false, TYPED, 0>(s, a, nb);
 }
-static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
+static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT, int mode)
 {
-    return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT);
+    return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT, mode) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT, mode);
 }
 
 // halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
 // communication stream while the interior brick layers compute; the boundary layers wait for them.
-static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false)
+static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false, int mode = 0)
 {
     emdee_ctx *c = s->ctx;
     if ((s->ntypes > 0) != s->fc_typed) EMDEE_TRY(choose_bricks(s));   // LJ classes changed since binning: re-size shared memory
@@ -1068,10 +1131,24 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         const double hz = 0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
         const double cmax2 = hx * hx + hy * hy + hz * hz;
         a.rc2f = (float)(s->model.rc2 * (1.0 + 1e-4) + 64.0 * 1.2e-7 * cmax2);
+        const double rl = s->cutoff + s->skin;
+        a.rl2f = (float)(rl * rl * (1.0 + 1e-4) + 64.0 * 1.2e-7 * cmax2);
     }
     a.cap = s->fc_cap;
     a.ncs_max = s->fc_ncs;
     a.err = s->err;
+    a.list = s->list; a.list_rows = s->list_rows; a.tmax = s->fc_tmax; a.lcap = s->lcap;
+    if (mode != 0) {
+        if (bitmask != EMDEE_FORCES || audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list modes evaluate forces only");
+        const int64_t slots = (int64_t)s->fc_nblocks * s->fc_tmax;
+        if (slots > s->list_slots) {
+            dev_free(s->list); dev_free(s->list_rows);
+            s->list_slots = slots + slots / 8;
+            EMDEE_TRY(dev_alloc(&s->list, (size_t)s->list_slots * s->lcap * 32));
+            EMDEE_TRY(dev_alloc(&s->list_rows, (size_t)s->list_slots));
+            a.list = s->list; a.list_rows = s->list_rows;
+        }
+    }
     const bool F = (bitmask & EMDEE_FORCES) != 0;
     const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0 || !F;
     if (audit) CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
@@ -1102,7 +1179,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     for (int k = 0; k < 3; k++) {
         if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
         a.block_first = ranges[k][0];
-        EMDEE_TRY(launch_cells(s, a, ranges[k][1], F, EW, s->has_excl, audit));
+        EMDEE_TRY(launch_cells(s, a, ranges[k][1], F, EW, s->has_excl, audit, mode));
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
     if (EW || audit) {
@@ -1161,6 +1238,8 @@ static int check_device_flag(emdee_system *s, const char *where)
         CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), s->ctx->stream));
         if (flag == 3) EMDEE_FAIL(EMDEE_ERR_SKIN, "%s: an atom moved more than skin/2 since the last binning; re-bin more often or raise the skin", where);
         if (flag == 2) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: a brick overflowed its shared-memory staging area", where);
+        if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its row capacity (set EMDEE_LIST_ROWS higher or EMDEE_LIST=0)", where);
+        if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
     }
     return EMDEE_OK;
@@ -1381,13 +1460,21 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     if (s->last_mode != EMDEE_CUTOFF) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: forces must come from EMDEE_CUTOFF mode");
     if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
     for (int64_t st = 0; st < nsteps; st++) {
-        const bool rebin = rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every;
+        // A pair list must be built at the positions the cells were binned at (both rely on "no atom moved
+        // more than skin/2 since the binning"), so a missing list forces a re-binning on this step.
+        const bool need_list = s->grid_ok && s->use_list && s->skin > 0 && !s->list_valid;
+        const bool rebin = need_list || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
         EMDEE_TRY(launch_vv(s, dt, 1, rebin ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
         s->kick_pending = false;
         s->steps_since_bin++;
         if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));
-        if (s->grid_ok)
-            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin));   // a re-bin already refreshed the ghosts
+        if (s->grid_ok) {
+            // pair-list reuse: build on the first evaluation after a (re-)binning, walk it afterwards
+            const bool listed = s->use_list && s->skin > 0;
+            const int mode = !listed ? 0 : (s->list_valid ? 2 : 1);
+            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, mode));   // a re-bin already refreshed the ghosts
+            if (listed) s->list_valid = true;
+        }
         else
             EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));
         s->kick_pending = true;

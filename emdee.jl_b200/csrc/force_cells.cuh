@@ -23,6 +23,15 @@
 //          oracle's rounding sequence, exact cull r2 <= rc2 (bit-exact pair set), interaction(),
 //          predicated accumulation of f, E, W.  When a stack nears capacity only the excess is
 //          popped (from every lane), so lanes stay evenly loaded until the final drain.
+// Pair-list reuse (MODE): while the binning is valid (atoms moved < skin/2) the set of pairs within
+// rc + skin cannot grow, so the scan result is kept in global memory as rows of 32 staged indices:
+//   MODE 1 (build, the evaluation right after a re-binning): the scan accepts r <= rc + skin and every
+//          entry popped by the drain is also stored (one coalesced 64-byte row per drain iteration);
+//   MODE 2 (use, the following steps): the window scan is replaced by a walk over the stored rows
+//          (~90 entries per atom instead of ~750 candidates), re-tested in FP32 against rc;
+//   MODE 0: plain window scan (single-point evaluations, audits).
+// This is the Verlet-list step SURVEY section 8(f) ranks first (the direction find_action_partners1!
+// was heading, src/cells.jl:224-297).
 // The FP64 pipe (64 lanes/clk/SM) therefore only sees pairs that are inside the cutoff (plus a
 // 1e-3 margin) at high lane occupancy, instead of the ~10x larger candidate set.
 #pragma once
@@ -30,6 +39,7 @@
 
 #define FC_QCAP 64          // per-lane queue entries (uint16 staged indices)
 #define FC_QCHUNK 16        // candidates scanned between queue-capacity checks
+#define FC_MINPOP 8         // a partial drain pops at least this many entries per lane
 #define FC_MAX_HOMEROWS 64  // by*bz of the largest supported brick
 #define FC_MAX_TYPES 16     // LJ parameter classes held as a pair table in shared memory
 
@@ -57,6 +67,10 @@ struct CellArgs {
     int ncs_max;                      // staged-cell capacity
     int *err;                         // device error flag (capacity overflow)
     int block_first;                  // first brick of this launch (launches may cover a z-layer range)
+    uint16_t *list;                   // pair-list rows: list[((brick*tmax + task)*lcap + row)*32 + lane]
+    int32_t *list_rows;               // rows stored per task
+    int tmax, lcap;                   // task slots per brick, row capacity per task
+    float rl2f;                       // FP32 threshold of the list: (rc + skin)^2 * (1 + margin)
 };
 
 __host__ __device__ inline size_t fc_smem_bytes(int cap, int ncs_max, int block, bool typed)
@@ -78,7 +92,7 @@ __device__ __forceinline__ int wrap_mod(int a, int M)
     return a < 0 ? a + M : a;
 }
 
-template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED, int MODE>
 __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
 {
     const int BLOCK = blockDim.x;
@@ -163,7 +177,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
             scal[1] = run;    // staged atoms
             scal[2] = t;      // warp tasks
             scal[3] = 0;      // task cursor
-            if (run > cap) atomicExch(a.err, 2);
+            if (run > cap) atomicCAS(a.err, 0, 2);
         }
     }
     __syncthreads();
@@ -211,6 +225,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const double c60id2 = 60.0 * a.model.id2;
     const double rc2 = a.model.rc2, L = a.L;
     const float rc2f = a.rc2f;
+    const float scan2f = MODE == 1 ? a.rl2f : a.rc2f;     // what the window scan accepts
     const int nwin = 2 * R + 1;
     double esum = 0, wsum = 0;
     unsigned long long npair = 0, hsum = 0, hxor = 0;
@@ -248,12 +263,22 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         int32_t xb = 0; uint64_t xm = 0;
         if (EXCL) { xb = a.xbase[slot_i]; xm = a.xmask[slot_i]; }
         double fx = 0, fy = 0, fz = 0, e = 0, w = 0;
+        uint16_t *lrow = nullptr;               // this task's pair-list rows, lane's column
+        int nrow = 0;                           // rows stored so far (MODE 1)
+        if (MODE != 0) {
+            if (t >= a.tmax) { atomicCAS(a.err, 0, 5); break; }
+            lrow = a.list + ((size_t)(bid * a.tmax + t) * a.lcap) * 32 + lane;
+        }
         int cnt = 0;                            // entries on this lane's stack: queue[k*BLOCK + tid], k < cnt
         uint16_t *qp = queue + tid;             // next free entry
 
         // one stack entry, branch-free: invalid or culled entries contribute nothing
-        auto pair_eval = [&](int idx, bool valid) {
+        auto pair_eval = [&](int idx, bool valid, int row) {
             const int j = valid ? (int)queue[idx * BLOCK + tid] : me;
+            if (MODE == 1) {
+                if (row < a.lcap) lrow[(size_t)row * 32] = valid ? (uint16_t)j : (uint16_t)0xFFFF;
+                else atomicCAS(a.err, 0, 5);
+            }
             const double2 j0 = pxy[j], j1 = pzm[j];
             double vx, vy, vz;
             const double r2 = min_image_r2(six, siy, siz, j0.x, j0.y, j1.x, L, vx, vy, vz);
@@ -290,17 +315,18 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         // pop the newest `depth` entries of every lane (all of them when depth >= the fullest stack)
         auto drain = [&](int depth) {
             for (int k = 0; k < depth; k += 4) {      // four independent pair evaluations in flight
-                pair_eval(cnt - 1 - k, k < cnt);
-                pair_eval(cnt - 2 - k, k + 1 < cnt && k + 1 < depth);
-                pair_eval(cnt - 3 - k, k + 2 < cnt && k + 2 < depth);
-                pair_eval(cnt - 4 - k, k + 3 < cnt && k + 3 < depth);
+                pair_eval(cnt - 1 - k, k < cnt, nrow);
+                pair_eval(cnt - 2 - k, k + 1 < cnt && k + 1 < depth, nrow + 1);
+                pair_eval(cnt - 3 - k, k + 2 < cnt && k + 2 < depth, nrow + 2);
+                pair_eval(cnt - 4 - k, k + 3 < cnt && k + 3 < depth, nrow + 3);
+                nrow += 4;
             }
             cnt = max(cnt - depth, 0);
             qp = queue + cnt * BLOCK + tid;
         };
 
         // -------- scan: (2R+1)^2 rows, one shared window of cells [cxa-R, cxb+R] per row --------
-        for (int rw = 0; rw < nwin * nwin; rw++) {
+        for (int rw = 0; MODE != 2 && rw < nwin * nwin; rw++) {
             const int row = (czi + rw / nwin - R) * syn + (cyi + rw % nwin - R);
             const int p0 = cs[row * sxn + cxa - R];
             const int p1 = min(cs[row * sxn + cxb + R + 1], nstaged);
@@ -314,21 +340,40 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
                     const float r1 = fmaf(c1.x, m2x, fmaf(c1.y, m2y, fmaf(c1.z, m2z, c1.w + pp)));
                     const float r2 = fmaf(c2.x, m2x, fmaf(c2.y, m2y, fmaf(c2.z, m2z, c2.w + pp)));
                     const float r3 = fmaf(c3.x, m2x, fmaf(c3.y, m2y, fmaf(c3.z, m2z, c3.w + pp)));
-                    if (r0 <= rc2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
-                    if (r1 <= rc2f) { *qp = (uint16_t)(p + 1); qp += BLOCK; cnt++; }
-                    if (r2 <= rc2f) { *qp = (uint16_t)(p + 2); qp += BLOCK; cnt++; }
-                    if (r3 <= rc2f) { *qp = (uint16_t)(p + 3); qp += BLOCK; cnt++; }
+                    if (r0 <= scan2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
+                    if (r1 <= scan2f) { *qp = (uint16_t)(p + 1); qp += BLOCK; cnt++; }
+                    if (r2 <= scan2f) { *qp = (uint16_t)(p + 2); qp += BLOCK; cnt++; }
+                    if (r3 <= scan2f) { *qp = (uint16_t)(p + 3); qp += BLOCK; cnt++; }
                 }
                 for (; p < pe; p++) {
                     const float4 c = prel[p];
                     const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
-                    if (r <= rc2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
+                    if (r <= scan2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
                 }
                 const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
-                if (over > 0) drain(over);
+                if (over > 0) drain(max(over, FC_MINPOP));
+            }
+        }
+        // -------- MODE 2: walk the stored pair-list rows instead of the window --------
+        if (MODE == 2) {
+            const int nrows = min(a.list_rows[bid * a.tmax + t], a.lcap);
+            for (int k0 = 0; k0 < nrows; k0 += FC_QCHUNK) {
+                uint16_t ent[FC_QCHUNK];
+#pragma unroll
+                for (int k = 0; k < FC_QCHUNK; k++) ent[k] = (k0 + k < nrows) ? lrow[(size_t)(k0 + k) * 32] : (uint16_t)0xFFFF;
+#pragma unroll
+                for (int k = 0; k < FC_QCHUNK; k++) {
+                    const int j = ent[k];
+                    const float4 c = prel[j == 0xFFFF ? me : j];
+                    const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
+                    if (j != 0xFFFF && r <= rc2f) { *qp = (uint16_t)j; qp += BLOCK; cnt++; }
+                }
+                const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
+                if (over > 0) drain(max(over, FC_MINPOP));
             }
         }
         drain(__reduce_max_sync(0xffffffffu, cnt));
+        if (MODE == 1 && lane == 0) a.list_rows[bid * a.tmax + t] = nrow;
 
         if (active) {
             if (F) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }

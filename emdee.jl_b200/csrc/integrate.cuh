@@ -43,7 +43,7 @@ __global__ void k_vv(VVArgs a)
         }
         a.v[c][i] = v;
     }
-    if (a.drift && a.check_skin && d2 > a.half_skin2) atomicExch(a.err, 3);
+    if (a.drift && a.check_skin && d2 > a.half_skin2) atomicCAS(a.err, 0, 3);
 }
 
 // K = sum 1/2 m v^2 over owned slots; per-block partials, summed on the host in block order.

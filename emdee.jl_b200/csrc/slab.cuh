@@ -40,10 +40,10 @@ __global__ void k_cell_index_slab(int64_t first, int64_t n, const double *__rest
     if (first_time) return;
     if (dz - nz < M - dz) {          // nearer to my top: moved up
         const int p = atomicAdd(sendcount + 1, 1);
-        if (p < list_cap) list_hi[p] = (int32_t)i; else atomicExch(err, 4);
+        if (p < list_cap) list_hi[p] = (int32_t)i; else atomicCAS(err, 0, 4);
     } else {
         const int p = atomicAdd(sendcount + 0, 1);
-        if (p < list_cap) list_lo[p] = (int32_t)i; else atomicExch(err, 4);
+        if (p < list_cap) list_lo[p] = (int32_t)i; else atomicCAS(err, 0, 4);
     }
 }
 
@@ -91,7 +91,7 @@ __global__ void k_unpack_migrants(int n, const double *__restrict__ buf, int64_t
     gcell[i] = x + M * (y + M * z);
     int dz = z - z0;
     if (dz < 0) dz += M;
-    if (dz >= nz) { atomicExch(err, 1); dz = nz - 1; }
+    if (dz >= nz) { atomicCAS(err, 0, 1); dz = nz - 1; }
     const int lc = x + M * (y + M * (dz + R));
     lcell[i] = lc;
     atomicAdd(count + lc, 1);

@@ -272,6 +272,17 @@ def test_velocity_verlet(em, oracle):
     assert np.abs(s.positions() - p).max() <= 1e-10
     assert np.abs(s.velocities() - v).max() <= 1e-9
     assert np.abs(s.forces() - f).max() <= 1e-8 * frms(f)
+    # pair-list reuse (skin, re-binning every 5 steps: one build + four walks of the stored list) vs the oracle
+    s.set_positions(pos)
+    s.set_velocities(vel)
+    s.set_skin(0.5)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(dt, nsteps, rebin_every=5)
+    assert np.abs(s.positions() - p).max() <= 1e-10
+    assert np.abs(s.velocities() - v).max() <= 1e-9
+    assert np.abs(s.forces() - f).max() <= 1e-8 * frms(f)
+    s.set_skin(0.0)
     # energy conservation over a longer run, with a skin and sparse re-binning
     s.set_skin(0.5)            # fastest atom ~6 sigma/tau -> 0.03 sigma per step: 5 steps stay below skin/2
     s.bin(1)
