@@ -357,10 +357,14 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         // -------- MODE 2: walk the stored pair-list rows instead of the window --------
         if (MODE == 2) {
             const int nrows = min(a.list_rows[bid * a.tmax + t], a.lcap);
-            for (int k0 = 0; k0 < nrows; k0 += FC_QCHUNK) {
-                uint16_t ent[FC_QCHUNK];
+            uint16_t ent[FC_QCHUNK], nxt[FC_QCHUNK];
 #pragma unroll
-                for (int k = 0; k < FC_QCHUNK; k++) ent[k] = (k0 + k < nrows) ? lrow[(size_t)(k0 + k) * 32] : (uint16_t)0xFFFF;
+            for (int k = 0; k < FC_QCHUNK; k++) ent[k] = (k < nrows) ? lrow[(size_t)k * 32] : (uint16_t)0xFFFF;
+            for (int k0 = 0; k0 < nrows; k0 += FC_QCHUNK) {
+                // the next chunk's rows are requested before this chunk is processed (hides the L2/HBM latency)
+#pragma unroll
+                for (int k = 0; k < FC_QCHUNK; k++)
+                    nxt[k] = (k0 + FC_QCHUNK + k < nrows) ? lrow[(size_t)(k0 + FC_QCHUNK + k) * 32] : (uint16_t)0xFFFF;
 #pragma unroll
                 for (int k = 0; k < FC_QCHUNK; k++) {
                     const int j = ent[k];
@@ -368,6 +372,8 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
                     const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
                     if (j != 0xFFFF && r <= rc2f) { *qp = (uint16_t)j; qp += BLOCK; cnt++; }
                 }
+#pragma unroll
+                for (int k = 0; k < FC_QCHUNK; k++) ent[k] = nxt[k];
                 const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
                 if (over > 0) drain(max(over, FC_MINPOP));
             }
