@@ -333,6 +333,13 @@ class NonbondedSystem:
         call("emdee_pair_set_digest", self._h, _ptr(d))
         return d
 
+    def list_pair_count(self):
+        """Pairs (i<j) the pair-list stepping kernel evaluates inside the cutoff at the current positions
+        (-1 when the system steps without a list).  Audit of the list pre-culls."""
+        n = C.c_int64()
+        call("emdee_list_pair_count", self._h, C.byref(n))
+        return int(n.value)
+
 
 def _system_for(positions, L, model, atoms, ctx=None):
     p = _as_3xN(positions, "positions")

@@ -10,11 +10,14 @@
 #include "common.cuh"
 #include "binning.cuh"
 #include "force_cells.cuh"
+#include "force_list.cuh"
+#include "list_build.cuh"
 #include "force_tiles.cuh"
 #include "integrate.cuh"
 #include "slab.cuh"
 
 #define FC_REGS_ESTIMATE 128   // registers per thread of k_force_cells assumed by the residency model
+#define FL_REGS_ESTIMATE 128   // same for k_force_list (__launch_bounds__(256, 2))
 
 // NCCL is bound at run time (dlopen) instead of link time: a host process that also imports PyTorch must end
 // up with ONE libnccl.so.2 (torch bundles 2.28, the system has 2.27); dlopen by soname returns whichever copy
@@ -132,11 +135,13 @@ struct emdee_system {
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
     bool fc_typed = false;
     int fc_shape[3] = {0, 0, 0};
-    int fc_tmax = 0;                          // warp-task slots per brick (pair-list addressing)
-    uint16_t *list = nullptr;                 // pair-list rows (Verlet list over staged indices)
-    int32_t *list_rows = nullptr;
-    int64_t list_slots = 0;
-    int lcap = 256;                           // rows per task
+    int fl_block = 192;                       // block size of k_force_list
+    size_t fl_smem = 0;
+    int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
+    uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
+    uint16_t *list_n = nullptr;               // entries per home atom
+    int64_t list_slots = 0;                   // allocated groups
+    int lcap8 = 24;                           // chunks per atom (192 entries)
     bool list_valid = false, use_list = true;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
@@ -158,6 +163,7 @@ struct emdee_system {
     // per-launch events of the force kernel (emdee_profile_begin/end)
     bool profiling = false;
     std::vector<cudaEvent_t> prof_events;
+    std::vector<int> prof_mode;               // launch mode of every event pair (0 scan, 1 list build, 2 list walk)
     size_t prof_used = 0;
     // scratch for host transfers
     double *tmp = nullptr;
@@ -382,7 +388,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     s->N = N;
     s->L = L;
     if (const char *e = getenv("EMDEE_LIST")) s->use_list = atoi(e) != 0;
-    if (const char *e = getenv("EMDEE_LIST_ROWS")) s->lcap = std::max(32, atoi(e));
+    if (const char *e = getenv("EMDEE_LIST_CHUNKS")) s->lcap8 = std::max(4, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -437,7 +443,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
-    dev_free(s->list); dev_free(s->list_rows);
+    dev_free(s->list8); dev_free(s->list_n);
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     delete s;
@@ -496,7 +502,7 @@ extern "C" int emdee_set_lj_atoms(emdee_system *s, const double *atoms)
     LAUNCH_1D(c, k_set1<double>, ntot, 0, ntot, A.id, s->tmp, 2, 1, A.ts);
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     // LJ parameter classes: distinct (half_sigma, twice_sqrt_eps) rows.  Up to FC_MAX_TYPES classes the
-    // kernels use a pair table {sigma_ij, 4 eps_ij} in shared memory (src/lennard_jones.jl:29,33);
+    // kernels use a pair table {sigma_ij^2, 4 eps_ij} in shared memory (src/lennard_jones.jl:29,33);
     // beyond that they gather the per-atom parameters.
     std::vector<double> cls;
     std::vector<int32_t> type((size_t)s->N, 0);
@@ -517,7 +523,10 @@ extern "C" int emdee_set_lj_atoms(emdee_system *s, const double *atoms)
         const int T = s->ntypes;
         std::vector<double2> tab((size_t)T * T);
         for (int p = 0; p < T; p++)
-            for (int q = 0; q < T; q++) tab[(size_t)p * T + q] = make_double2(cls[2 * p] + cls[2 * q], cls[2 * p + 1] * cls[2 * q + 1]);
+            for (int q = 0; q < T; q++) {
+                const double sig = cls[2 * p] + cls[2 * q];     // :29, squared here so that the kernels skip one multiply
+                tab[(size_t)p * T + q] = make_double2(sig * sig, cls[2 * p + 1] * cls[2 * q + 1]);
+            }
         dev_free(s->ljtab);
         EMDEE_TRY(dev_alloc(&s->ljtab, tab.size()));
         CUDA_TRY(cudaMemcpy(s->ljtab, tab.data(), sizeof(double2) * tab.size(), cudaMemcpyHostToDevice));
@@ -700,28 +709,46 @@ static void set_brick_shape(emdee_system *s, const int sh[3])
     g.nby = (M + g.by - 1) / g.by;
     g.nbz = (g.nzhome + g.bz - 1) / g.bz;
 }
+static bool list_capable(const emdee_system *s)
+{
+    // the pair-list kernels read LJ parameters from the class table and index staged atoms with 16 bits
+    return s->grid_ok && s->use_list && s->skin > 0 && s->ntypes > 0;
+}
 static int choose_bricks(emdee_system *s)
 {
     emdee_ctx *c = s->ctx;
     GridDesc &g = s->g;
     const int R = g.R;
     const bool typed = s->ntypes > 0;
+    const bool listed = list_capable(s);
     const size_t per_sm = c->smem_optin + 1024;          // usable shared memory per SM (1 KB reserved per block)
     const int64_t ntot = s->nlo + s->nown + s->nhi;
     const double per_cell = (double)ntot / (double)std::max<int64_t>(1, (int64_t)g.M * g.M * g.nzt);
     int maxpop = 0;
     CUDA_TRY(cudaMemcpyAsync(&maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    auto finish = [&](int cap, int block) -> int {
+    static const int blocks[] = {384, 256, 192, 128, 64};
+    static const int lblocks[] = {256, 192, 128, 96, 64};
+    // largest k_force_cells block that fits next to `cap` staged atoms (0: none)
+    auto cells_block = [&](int cap, int ncs, int forced_block) -> int {
+        for (int block : blocks) {
+            if (forced_block && block != forced_block) continue;
+            if (fc_smem_bytes(cap, ncs, block, typed) <= c->smem_optin) return block;
+        }
+        return 0;
+    };
+    auto finish = [&](int cap, int block, int lblock) -> int {
         s->fc_cap = cap;
-        // task slots per brick from the densest cell, with head-room so that density fluctuations between
+        // 32-atom groups per brick from the densest cell, with head-room so that density fluctuations between
         // re-binnings do not resize the pair list
-        const int tmax = g.by * g.bz * ((g.bx * (std::max(maxpop, 1) + 16) + 31) / 32);
-        if (tmax > s->fc_tmax || tmax * 2 < s->fc_tmax) s->fc_tmax = tmax;
+        const int gmax = (g.bx * g.by * g.bz * (std::max(maxpop, 1) + 8) + 31) / 32 + 1;
+        if (gmax > s->fc_gmax || gmax * 2 < s->fc_gmax) s->fc_gmax = gmax;
         s->list_valid = false;
         s->fc_ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         s->fc_block = block;
         s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
+        s->fl_block = lblock;
+        s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
         s->fc_typed = typed;
         s->fc_nblocks = g.nbx * g.nby * g.nbz;
         const int64_t nwarps = (int64_t)s->fc_nblocks * (block / 32);
@@ -738,15 +765,17 @@ static int choose_bricks(emdee_system *s)
         int cap = 0;
         EMDEE_TRY(brick_capacity(s, &cap));
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
-        if (cap <= 65535 && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= s->fc_smem_budget) return finish(cap, s->fc_block);
+        const size_t need = listed ? fl_smem_bytes(cap, ncs, s->fl_block, std::max(s->ntypes, 1)) : fc_smem_bytes(cap, ncs, s->fc_block, typed);
+        if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin)
+            return finish(cap, s->fc_block, s->fl_block);
     }
     static const int shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {8, 2, 1}, {4, 4, 1}, {4, 2, 2}, {4, 2, 1}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
-    static const int blocks[] = {384, 256, 192, 128, 64};
-    int forced[3] = {0, 0, 0}, forced_block = 0;
+    int forced[3] = {0, 0, 0}, forced_block = 0, forced_lblock = 0;
     if (const char *e = getenv("EMDEE_BRICK")) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     if (const char *e = getenv("EMDEE_BLOCK")) forced_block = atoi(e);
+    if (const char *e = getenv("EMDEE_LBLOCK")) forced_lblock = atoi(e);
     double best_score = -1;
-    int best_shape[3] = {0, 0, 0}, best_block = 0, best_cap = 0;
+    int best_shape[3] = {0, 0, 0}, best_block = 0, best_lblock = 192, best_cap = 0;
     size_t best_budget = 0;
     const int nshape = forced[0] > 0 ? 1 : (int)(sizeof(shapes) / sizeof(shapes[0]));
     int prev[3] = {-1, -1, -1};
@@ -754,12 +783,42 @@ static int choose_bricks(emdee_system *s)
         const int *sh = forced[0] > 0 ? forced : shapes[k];
         set_brick_shape(s, sh);
         if (g.by * g.bz > FC_MAX_HOMEROWS) continue;
+        if (std::max(g.bx, std::max(g.by, g.bz)) + 2 * R > 32) continue;       // ctab / ccoord hold 32 cells per dimension
         if (g.bx == prev[0] && g.by == prev[1] && g.bz == prev[2]) continue;   // clipped to the same shape as the previous one
         prev[0] = g.bx; prev[1] = g.by; prev[2] = g.bz;
         int cap = 0;
         EMDEE_TRY(brick_capacity(s, &cap));
-        if (cap > 65535) continue;
+        if (cap > 65534) continue;
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
+        const double home = per_cell * g.bx * g.by * g.bz;
+        if (listed) {
+            // the stepping kernel (k_force_list) decides: resident warps that hold a 32-atom group, as long as
+            // k_force_cells (list build, one block per SM is enough) fits too
+            const int cblock = cells_block(cap, ncs, forced_block);
+            if (!cblock) continue;
+            const double groups = std::max(1.0, std::ceil(home / 32.0));
+            for (int lblock : lblocks) {
+                if (forced_lblock && lblock != forced_lblock) continue;
+                const size_t smem = fl_smem_bytes(cap, ncs, lblock, std::max(s->ntypes, 1));
+                if (smem > c->smem_optin) continue;
+                const int by_smem = (int)(per_sm / (smem + 1024));
+                const int by_regs = std::max(1, 65536 / (FL_REGS_ESTIMATE * lblock));
+                const int resident = std::min(std::min(by_smem, by_regs), 32);
+                if (resident < 1) continue;
+                const int nw = lblock / 32;
+                // rounds of tasks per warp: a block lives ceil(groups / warps) task times, idle slots are lost
+                const double rounds = std::ceil(groups / nw);
+                const double busy = groups / (rounds * nw);
+                const double active = std::min(16.0, resident * nw * busy);
+                const double score = active * 1000.0 + 100.0 * std::min(resident, 3) + 2.0 * (g.bx * g.by * g.bz);
+                if (score > best_score) {
+                    best_score = score; best_block = cblock; best_lblock = lblock; best_cap = cap;
+                    best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
+                    best_budget = per_sm / resident - 1024;
+                }
+            }
+            continue;
+        }
         const double tasks = g.by * g.bz * std::max(1.0, std::ceil(per_cell * g.bx / 32.0));
         for (int block : blocks) {
             if (forced_block && block != forced_block) continue;
@@ -770,7 +829,6 @@ static int choose_bricks(emdee_system *s)
             const int resident = std::min(std::min(by_smem, by_regs), 32);
             if (resident < 1) continue;
             const double active = resident * std::min<double>(block / 32, tasks);
-            // ties: fewer idle warps, then larger bricks (less halo staging per home atom)
             // ties: larger bricks first (measured on B200: 8x2x2 @384 threads beats two resident 4x2x1 blocks by 1.3x --
             // the halo staged per home atom drops from 9x to 5x), then fewer idle warps
             const double score = active * 1000.0 + 2.0 * (g.bx * g.by * g.bz) - 0.1 * resident * (block / 32);
@@ -784,11 +842,11 @@ static int choose_bricks(emdee_system *s)
     if (best_score < 0) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: no brick shape fits shared memory (cells too populated); use a larger ndiv");
     set_brick_shape(s, best_shape);
     if (getenv("EMDEE_DEBUG"))
-        fprintf(stderr, "[emdee] bricks %dx%dx%d block %d cap %d (full search, per_cell %.1f, maxpop %d)\n", best_shape[0], best_shape[1],
-                best_shape[2], best_block, best_cap, per_cell, maxpop);
+        fprintf(stderr, "[emdee] bricks %dx%dx%d block %d list-block %d cap %d (full search, per_cell %.1f, maxpop %d, listed %d)\n", best_shape[0],
+                best_shape[1], best_shape[2], best_block, best_lblock, best_cap, per_cell, maxpop, (int)listed);
     for (int k = 0; k < 3; k++) s->fc_shape[k] = best_shape[k];
     s->fc_smem_budget = std::min(best_budget, c->smem_optin);
-    return finish(best_cap, best_block);
+    return finish(best_cap, best_block, best_lblock);
 }
 
 static int do_bin(emdee_system *s, int ndiv)
@@ -1073,36 +1131,58 @@ extern "C" int emdee_get_local_ids(emdee_system *s, int32_t *ids)
 // ------------------------------------------------------------------------------------------------
 // force evaluation
 // ------------------------------------------------------------------------------------------------
-template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED, int MODE>
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
 static int launch_cells_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
-    auto kern = k_force_cells<F, EW, EXCL, AUDIT, TYPED, MODE>;
+    auto kern = k_force_cells<F, EW, EXCL, AUDIT, TYPED>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fc_smem));
     kern<<<nblocks, s->fc_block, s->fc_smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_force_cells");
 }
-template <bool TYPED>
-static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT, int mode)
+template <bool EXCL>
+static int launch_build_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
-    if (mode != 0) {   // pair-list build / use: the stepping loop evaluates forces only
-        if (mode == 1) return EXCL ? launch_cells_t<true, false, true, false, TYPED, 1>(s, a, nb) : launch_cells_t<true, false, false, false, TYPED, 1>(s, a, nb);
-        return EXCL ? launch_cells_t<true, false, true, false, TYPED, 2>(s, a, nb) : launch_cells_t<true, false, false, false, TYPED, 2>(s, a, nb);
-    }
-    if (AUDIT) return EXCL ? launch_cells_t<true, true, true, true, TYPED, 0>(s, a, nb) : launch_cells_t<true, true, false, true, TYPED, 0>(s, a, nb);
-    if (EXCL) {
-        if (F && EW) return launch_cells_t<true, true, true, false, TYPED, 0>(s, a, nb);
-        if (F) return launch_cells_t<true, false, true, false, TYPED, 0>(s, a, nb);
-        return launch_cells_t<false, true, true, false, TYPED, 0>(s, a, nb);
-    }
-    if (F && EW) return launch_cells_t<true, true, false, false, TYPED, 0>(s, a, nb);
-    if (F) return launch_cells_t<true, false, false, false, TYPED, 0>(s, a, nb);
-    return launch_cells_t<false, true, false, false, TYPED, 0>(s, a, nb);
+    if (nblocks <= 0) return EMDEE_OK;
+    auto kern = k_list_build<EXCL>;
+    const size_t smem = lb_smem_bytes(s->fc_cap, s->fc_ncs, EXCL);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<nblocks, LB_MAX_BLOCK, smem, s->ctx->stream>>>(a);
+    s->ctx->launches++;
+    return check_launch("k_list_build");
 }
+template <bool MULTI, bool COUNT>
+static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks)
+{
+    if (nblocks <= 0) return EMDEE_OK;
+    auto kern = k_force_list<MULTI, COUNT>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fl_smem));
+    kern<<<nblocks, s->fl_block, s->fl_smem, s->ctx->stream>>>(a);
+    s->ctx->launches++;
+    return check_launch("k_force_list");
+}
+template <bool TYPED>
+static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
+{
+    if (AUDIT) return EXCL ? launch_cells_t<true, true, true, true, TYPED>(s, a, nb) : launch_cells_t<true, true, false, true, TYPED>(s, a, nb);
+    if (EXCL) {
+        if (F && EW) return launch_cells_t<true, true, true, false, TYPED>(s, a, nb);
+        if (F) return launch_cells_t<true, false, true, false, TYPED>(s, a, nb);
+        return launch_cells_t<false, true, true, false, TYPED>(s, a, nb);
+    }
+    if (F && EW) return launch_cells_t<true, true, false, false, TYPED>(s, a, nb);
+    if (F) return launch_cells_t<true, false, false, false, TYPED>(s, a, nb);
+    return launch_cells_t<false, true, false, false, TYPED>(s, a, nb);
+}
+// mode 0: window scan (k_force_cells); 1: pair-list build (k_list_build, no forces); 2: pair-list walk (k_force_list);
+// 3: the same, counting the pairs inside the cutoff
 static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT, int mode)
 {
-    return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT, mode) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT, mode);
+    if (mode == 1) return EXCL ? launch_build_t<true>(s, a, nb) : launch_build_t<false>(s, a, nb);
+    if (mode == 2) return s->ntypes > 1 ? launch_list_t<true, false>(s, a, nb) : launch_list_t<false, false>(s, a, nb);
+    if (mode == 3) return s->ntypes > 1 ? launch_list_t<true, true>(s, a, nb) : launch_list_t<false, true>(s, a, nb);
+    return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT);
 }
 
 // halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
@@ -1142,18 +1222,41 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     a.cap = s->fc_cap;
     a.ncs_max = s->fc_ncs;
     a.err = s->err;
-    a.list = s->list; a.list_rows = s->list_rows; a.tmax = s->fc_tmax; a.lcap = s->lcap;
+    a.list8 = s->list8; a.list_n = s->list_n; a.gmax = s->fc_gmax; a.lcap8 = s->lcap8;
+    {
+        uint64_t bits;
+        memcpy(&bits, &s->model.rc2, 8);
+        a.rc2hi = (int)(bits >> 32);
+        a.fast.id2 = s->model.id2;
+        a.fast.nrs2id2 = -s->model.rs2 * s->model.id2;
+        a.fast.c60id2 = 60.0 * s->model.id2;
+        // FP16 pre-cull of k_force_list: coordinates within +-cmax of the brick centre are stored with an error of
+        // half an FP16 ulp (both atoms), the separation and the three squares/sums round once more each
+        const double hx = 0.5 * (s->g.bx + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double hy = 0.5 * (s->g.by + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double hz = 0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
+        const double cmax = std::max(hx, std::max(hy, hz));
+        const double ulp_c = std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(cmax))) - 10);   // FP16 ulp at cmax
+        const double u = std::ldexp(1.0, -11);                                                        // FP16 unit roundoff
+        const double dd = ulp_c + 4.0 * u * (s->cutoff + 1.0);           // per-component error of a separation (2 x ulp/2 + rounding of d)
+        const double rc = s->cutoff;
+        const double e2 = 2.0 * std::sqrt(3.0) * rc * dd + 3.0 * dd * dd + 8.0 * u * (rc * rc + 1.0);   // bound on |r2_fp16 - r2|
+        a.rc2h = (float)((rc * rc + 1.5 * e2) * (1.0 + 2.0 * u));
+    }
     if (mode != 0) {
         if (bitmask != EMDEE_FORCES || audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list modes evaluate forces only");
-        const int64_t slots = (int64_t)s->fc_nblocks * s->fc_tmax;
+        if (!list_capable(s)) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: pair list requested for a system that cannot use one");
+        const int64_t slots = (int64_t)s->fc_nblocks * s->fc_gmax;
         if (slots > s->list_slots) {
-            dev_free(s->list); dev_free(s->list_rows);
+            dev_free(s->list8); dev_free(s->list_n);
             s->list_slots = slots + slots / 4;
-            if (getenv("EMDEE_DEBUG")) fprintf(stderr, "[emdee] pair list: %lld task slots x %d rows (%.2f GB)\n", (long long)s->list_slots, s->lcap, (double)s->list_slots * s->lcap * 64 / 1e9);
-            EMDEE_TRY(dev_alloc(&s->list, (size_t)s->list_slots * s->lcap * 32));
-            EMDEE_TRY(dev_alloc(&s->list_rows, (size_t)s->list_slots));
-            a.list = s->list; a.list_rows = s->list_rows;
+            if (getenv("EMDEE_DEBUG")) fprintf(stderr, "[emdee] pair list: %lld groups x %d chunks (%.2f GB)\n", (long long)s->list_slots, s->lcap8, (double)s->list_slots * s->lcap8 * 512 / 1e9);
+            EMDEE_TRY(dev_alloc(&s->list8, (size_t)s->list_slots * s->lcap8 * 32));
+            EMDEE_TRY(dev_alloc(&s->list_n, (size_t)s->list_slots * 32));
+            a.list8 = s->list8; a.list_n = s->list_n;
         }
+        // lanes of a group without a home atom must read "no entries"
+        if (mode == 1) CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
     }
     const bool F = (bitmask & EMDEE_FORCES) != 0;
     const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0 || !F;
@@ -1167,6 +1270,8 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         }
         pe0 = s->prof_events[s->prof_used];
         pe1 = s->prof_events[s->prof_used + 1];
+        if (s->prof_mode.size() < s->prof_used / 2 + 1) s->prof_mode.resize(s->prof_used / 2 + 1);
+        s->prof_mode[s->prof_used / 2] = mode;
         s->prof_used += 2;
         CUDA_TRY(cudaEventRecord(pe0, c->stream));
     }
@@ -1244,7 +1349,7 @@ static int check_device_flag(emdee_system *s, const char *where)
         CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), s->ctx->stream));
         if (flag == 3) EMDEE_FAIL(EMDEE_ERR_SKIN, "%s: an atom moved more than skin/2 since the last binning; re-bin more often or raise the skin", where);
         if (flag == 2) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: a brick overflowed its shared-memory staging area", where);
-        if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its row capacity (set EMDEE_LIST_ROWS higher or EMDEE_LIST=0)", where);
+        if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its capacity (set EMDEE_LIST_CHUNKS higher or EMDEE_LIST=0)", where);
         if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
     }
@@ -1434,6 +1539,23 @@ extern "C" int emdee_pair_set(emdee_system *s, int32_t *ij, int64_t cap, int64_t
     return EMDEE_OK;
 }
 
+extern "C" int emdee_list_pair_count(emdee_system *s, int64_t *npairs)
+{
+    SYS_ENTER(s, "emdee_list_pair_count");
+    if (!npairs) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_list_pair_count: null output");
+    *npairs = -1;
+    if (!list_capable(s)) return EMDEE_OK;
+    if (!s->list_valid) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_list_pair_count: no valid pair list (call emdee_vv_step first)");
+    CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
+    EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 3));
+    unsigned long long n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, s->digest, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EMDEE_TRY(check_device_flag(s, "emdee_list_pair_count"));
+    *npairs = (int64_t)(n / 2);      // the full-neighbour kernel sees every pair from both sides
+    return EMDEE_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // velocity-Verlet
 // ------------------------------------------------------------------------------------------------
@@ -1468,18 +1590,22 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     for (int64_t st = 0; st < nsteps; st++) {
         // A pair list must be built at the positions the cells were binned at (both rely on "no atom moved
         // more than skin/2 since the binning"), so a missing list forces a re-binning on this step.
-        const bool need_list = s->grid_ok && s->use_list && s->skin > 0 && !s->list_valid;
+        const bool need_list = list_capable(s) && !s->list_valid;
         const bool rebin = need_list || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
         EMDEE_TRY(launch_vv(s, dt, 1, rebin ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
         s->kick_pending = false;
         s->steps_since_bin++;
         if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));
         if (s->grid_ok) {
-            // pair-list reuse: build on the first evaluation after a (re-)binning, walk it afterwards
-            const bool listed = s->use_list && s->skin > 0;
-            const int mode = !listed ? 0 : (s->list_valid ? 2 : 1);
-            EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, mode));   // a re-bin already refreshed the ghosts
-            if (listed) s->list_valid = true;
+            // pair list: built (k_list_build, a filter) right after a (re-)binning, walked (k_force_list) on every step
+            if (list_capable(s)) {
+                if (!s->list_valid) {
+                    EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1));
+                    s->list_valid = true;
+                }
+                EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, 2));   // a re-bin already refreshed the ghosts
+            } else
+                EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, 0));
         }
         else
             EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));
@@ -1523,12 +1649,18 @@ extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
     SYS_ENTER(s, "emdee_profile_end");
     s->profiling = false;
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    double total = 0;
+    double total = 0, per_mode[4] = {0, 0, 0, 0};
+    int n_mode[4] = {0, 0, 0, 0};
     for (size_t k = 0; k + 1 < s->prof_used; k += 2) {
         float t = 0;
         CUDA_TRY(cudaEventElapsedTime(&t, s->prof_events[k], s->prof_events[k + 1]));
         total += t;
+        const int m = s->prof_mode[k / 2] & 3;
+        per_mode[m] += t; n_mode[m]++;
     }
+    if (getenv("EMDEE_DEBUG"))
+        for (int m = 0; m < 4; m++)
+            if (n_mode[m]) fprintf(stderr, "[emdee] force kernel mode %d: %d launches, %.4f ms each\n", m, n_mode[m], per_mode[m] / n_mode[m]);
     if (ms) *ms = total;
     if (launches) *launches = (int64_t)(s->prof_used / 2);
     return EMDEE_OK;

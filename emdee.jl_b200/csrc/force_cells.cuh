@@ -23,17 +23,13 @@
 //          oracle's rounding sequence, exact cull r2 <= rc2 (bit-exact pair set), interaction(),
 //          predicated accumulation of f, E, W.  When a stack nears capacity only the excess is
 //          popped (from every lane), so lanes stay evenly loaded until the final drain.
-// Pair-list reuse (MODE): while the binning is valid (atoms moved < skin/2) the set of pairs within
-// rc + skin cannot grow, so the scan result is kept in global memory as rows of 32 staged indices:
-//   MODE 1 (build, the evaluation right after a re-binning): the scan accepts r <= rc + skin and every
-//          entry popped by the drain is also stored (one coalesced 64-byte row per drain iteration);
-//   MODE 2 (use, the following steps): the window scan is replaced by a walk over the stored rows
-//          (~90 entries per atom instead of ~750 candidates), re-tested in FP32 against rc;
-//   MODE 0: plain window scan (single-point evaluations, audits).
-// This is the Verlet-list step SURVEY section 8(f) ranks first (the direction find_action_partners1!
-// was heading, src/cells.jl:224-297).
-// The FP64 pipe (64 lanes/clk/SM) therefore only sees pairs that are inside the cutoff (plus a
-// 1e-3 margin) at high lane occupancy, instead of the ~10x larger candidate set.
+// This kernel serves single-point evaluations (forces / energies / virials, audits).  The velocity-Verlet loop
+// uses the pair list instead: k_list_build (list_build.cuh) on a re-binning step, k_force_list (force_list.cuh)
+// on every step; both stage a brick in the same order as this kernel.
+// Geometry in the drain: every staged atom carries FP64 coordinates in the brick's frame (periodic image
+// resolved per staged cell), so a separation is three subtractions; the cutoff decision is made on that r2
+// with integer compares and handed to the oracle's exact rounding sequence only inside a 3e-6 band around
+// rc2 (pair_in_range, lj_pair.cuh) -- the pair set stays bit-exact.
 #pragma once
 #include "lj_pair.cuh"
 
@@ -43,6 +39,8 @@
 #define FC_MAX_HOMEROWS 64  // by*bz of the largest supported brick
 #define FC_MAX_TYPES 16     // LJ parameter classes held as a pair table in shared memory
 
+#define FC_DIMTAB 96         // 3 x 32 doubles: a staged dimension has at most 32 cells
+
 #define FC_MAX_BLOCK 384     // launch bound: 12 warps, up to 170 registers per thread
 
 struct CellArgs {
@@ -51,7 +49,7 @@ struct CellArgs {
     const double *sx, *sy, *sz, *hs, *ts;
     const int32_t *id, *type, *xbase;
     const uint64_t *xmask;
-    const double2 *ljtab;             // ntypes^2 entries {half_sigma_a + half_sigma_b, twice_sqrt_eps_a * twice_sqrt_eps_b}
+    const double2 *ljtab;             // ntypes^2 entries {(half_sigma_a + half_sigma_b)^2, twice_sqrt_eps_a * twice_sqrt_eps_b}
     int ntypes;                       // 0: more than FC_MAX_TYPES classes, per-atom parameters are gathered from global
     double *fx, *fy, *fz, *en, *vir;
     double *partial;                  // per warp: {sum e_i, sum w_i}
@@ -67,18 +65,71 @@ struct CellArgs {
     int ncs_max;                      // staged-cell capacity
     int *err;                         // device error flag (capacity overflow)
     int block_first;                  // first brick of this launch (launches may cover a z-layer range)
-    uint16_t *list;                   // pair-list rows: list[((brick*tmax + task)*lcap + row)*32 + lane]
-    int32_t *list_rows;               // rows stored per task
-    int tmax, lcap;                   // task slots per brick, row capacity per task
+    // pair list: home atom h of a brick (flattened over its home rows) belongs to group h/32, lane h%32;
+    // chunk c of that atom is the uint4 list8[((brick*gmax + h/32)*lcap8 + c)*32 + h%32] = 8 x (staged index + 1)
+    uint4 *list8;
+    uint16_t *list_n;                 // entries stored per home atom: list_n[(brick*gmax + h/32)*32 + h%32]
+    int gmax, lcap8;                  // groups per brick, chunk capacity per atom
     float rl2f;                       // FP32 threshold of the list: (rc + skin)^2 * (1 + margin)
+    int rc2hi;                        // high word of rc2 (pair_in_range)
+    LJFast fast;
+    float rc2h;                       // k_force_list: FP16 pre-cull threshold (conservative, set by the host)
 };
+
+// Brick geometry shared by the kernels that stage a brick.
+struct BrickGeom {
+    int hx0, hy0, hz0;      // first home cell (x, y global; z local)
+    int nhx, nhy, nhz;      // home cells per dimension
+    int sxn, syn, szn;      // staged cells per dimension (home + 2R)
+    int nrows, ncs;         // staged rows (y,z) and staged cells
+};
+__device__ __forceinline__ BrickGeom brick_geom(const GridDesc &g, int bid)
+{
+    BrickGeom b;
+    int t = bid;
+    const int bxi = t % g.nbx; t /= g.nbx;
+    const int byi = t % g.nby;
+    const int bzi = t / g.nby;
+    b.hx0 = bxi * g.bx; b.hy0 = byi * g.by; b.hz0 = g.zhome0 + bzi * g.bz;
+    b.nhx = min(g.bx, g.M - b.hx0); b.nhy = min(g.by, g.M - b.hy0); b.nhz = min(g.bz, g.zhome0 + g.nzhome - b.hz0);
+    b.sxn = b.nhx + 2 * g.R; b.syn = b.nhy + 2 * g.R; b.szn = b.nhz + 2 * g.R;
+    b.nrows = b.syn * b.szn; b.ncs = b.nrows * b.sxn;
+    return b;
+}
+
+// Global slot of staged atom j (binary search of the staged-cell table; used by the rare exact-cull path).
+__device__ __noinline__ int staged_slot(int j, const int *cs, const int *gbase, int ncs)
+{
+    int lo = 0, hi = ncs - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (cs[mid] <= j) lo = mid; else hi = mid - 1;
+    }
+    return gbase[lo] + (j - cs[lo]);
+}
+
+// The oracle's cutoff decision for one pair (dist2() of the oracle on the scaled coordinates), taken only
+// for pairs whose local-frame r2 is within 3*2^-20 of rc2.  Also returns the oracle's own clamped x
+// (src/lennard_jones.jl:36-37: x < 0 -> 0, x > 1 -> 0, x == 1 -> 0.5) so that the switching function is
+// evaluated on the same branch.
+__device__ __noinline__ bool exact_in_range(const double *sx, const double *sy, const double *sz, int slot_i, int slot_j,
+                                            double L, const LJModel m, double *xval)
+{
+    double vx, vy, vz;
+    const double r2 = min_image_r2(sx[slot_i], sy[slot_i], sz[slot_i], sx[slot_j], sy[slot_j], sz[slot_j], L, vx, vy, vz);
+    double x = __dmul_rn(__dsub_rn(r2, m.rs2), m.id2);
+    x = (x < 0.0 || x > 1.0) ? 0.0 : (x == 1.0 ? 0.5 : x);
+    *xval = x;
+    return r2 <= m.rc2;
+}
 
 __host__ __device__ inline size_t fc_smem_bytes(int cap, int ncs_max, int block, bool typed)
 {
     size_t b = (size_t)cap * (2 * sizeof(double2) + sizeof(float4));
-    if (!typed) b += (size_t)cap * sizeof(int);      // slot of every staged atom (per-atom parameter gathers)
+    if (!typed) b += (size_t)(cap + (cap & 1)) * sizeof(int);   // slot of every staged atom (per-atom parameter gathers)
     b += (size_t)FC_MAX_TYPES * FC_MAX_TYPES * sizeof(double2);
-    b += (size_t)(ncs_max + 1) * sizeof(int) * 2;    // cs[], gbase[]
+    b += FC_DIMTAB * sizeof(double);                 // scaled cell centres of the three staged dimensions
+    b += (size_t)(ncs_max + 1) * sizeof(int) * 3;    // cs[], gbase[], ccoord[]
     b += 2 * (FC_MAX_HOMEROWS + 1) * sizeof(int);    // hstart[], tstart[]
     b += 8 * sizeof(int);                            // scalars
     b = (b + 15) & ~(size_t)15;
@@ -92,22 +143,101 @@ __device__ __forceinline__ int wrap_mod(int a, int M)
     return a < 0 ? a + M : a;
 }
 
-template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED, int MODE>
+// ---- staging shared by k_force_cells and k_force_list ---------------------------------------------------
+// Phase A: count and first global slot of every staged cell, its coordinates inside the staged box, and the
+// unwrapped scaled centres of the staged cells along each dimension.  The caller turns cs[] into an exclusive
+// prefix afterwards.
+__device__ __forceinline__ void stage_cell_table(const CellArgs &a, const BrickGeom &bg, int *cs, int *gbase, int *ccoord, double *ctab)
+{
+    const GridDesc &g = a.g;
+    const int R = g.R, M = g.M, BLOCK = blockDim.x, tid = threadIdx.x;
+    for (int t = tid; t < bg.ncs; t += BLOCK) {
+        const int cx = t % bg.sxn, row = t / bg.sxn, cy = row % bg.syn, cz = row / bg.syn;
+        const int gx = wrap_mod(bg.hx0 - R + cx, M), gy = wrap_mod(bg.hy0 - R + cy, M);
+        int lz = bg.hz0 - R + cz;
+        if (g.zwrap) lz = wrap_mod(lz, M);
+        const int lc = gx + M * (gy + M * lz);
+        const int s0 = a.cell_start[lc];
+        gbase[t] = s0;
+        cs[t] = a.cell_start[lc + 1] - s0;
+        ccoord[t] = cx | (cy << 8) | (cz << 16);
+    }
+    const int uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0) - R;
+    for (int t = tid; t < FC_DIMTAB; t += BLOCK) {
+        const int d = t >> 5, k = t & 31;
+        const int u = (d == 0 ? bg.hx0 - R : d == 1 ? bg.hy0 - R : uz0) + k;
+        ctab[t] = ((double)u + 0.5) / M;
+    }
+}
+
+// Phase B: every staged atom [first, last) in the brick's frame.  For staged index idx the cell is found by a
+// fixed-length binary search of the prefix table (three atoms per thread in flight, so their global loads
+// overlap); p = L * ((s - c) - rint(s - c) + (c - b)) with c the unwrapped scaled centre of the staged cell
+// (the periodic image nearest to that cell) and b the brick centre.  store(idx, slot, px, py, pz).
+template <class Store>
+__device__ __forceinline__ void stage_atoms(const CellArgs &a, const BrickGeom &bg, const int *cs, const int *gbase, const int *ccoord,
+                                            const double *ctab, int first, int last, Store store)
+{
+    const GridDesc &g = a.g;
+    const int BLOCK = blockDim.x, tid = threadIdx.x, M = g.M;
+    const int uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0);
+    const double bcx = ((double)bg.hx0 + 0.5 * bg.nhx) / M, bcy = ((double)bg.hy0 + 0.5 * bg.nhy) / M, bcz = ((double)uz0 + 0.5 * bg.nhz) / M;
+    int nsteps = 0;
+    while ((1 << nsteps) < bg.ncs) nsteps++;
+    constexpr int U = 3;
+    for (int i0 = first + tid; i0 < last; i0 += U * BLOCK) {
+        int idx[U], lo[U], slot[U];
+        bool ok[U];
+        double sx[U], sy[U], sz[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            idx[u] = i0 + u * BLOCK;
+            ok[u] = idx[u] < last;
+            lo[u] = 0;
+        }
+        for (int st = nsteps - 1; st >= 0; st--) {       // last t with cs[t] <= idx (empty cells repeat a value)
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int mid = lo[u] + (1 << st);
+                if (mid < bg.ncs && cs[mid] <= idx[u]) lo[u] = mid;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            slot[u] = gbase[lo[u]] + (idx[u] - cs[lo[u]]);
+            sx[u] = sy[u] = sz[u] = 0.0;
+            if (ok[u]) { sx[u] = a.sx[slot[u]]; sy[u] = a.sy[slot[u]]; sz[u] = a.sz[slot[u]]; }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            if (!ok[u]) continue;
+            const int cc = ccoord[lo[u]];
+            const double cx = ctab[cc & 255], cy = ctab[32 + ((cc >> 8) & 255)], cz = ctab[64 + (cc >> 16)];
+            double dx = sx[u] - cx, dy = sy[u] - cy, dz = sz[u] - cz;
+            dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);      // image nearest to the staged cell
+            store(idx[u], slot[u], a.L * (dx + (cx - bcx)), a.L * (dy + (cy - bcy)), a.L * (dz + (cz - bcz)));
+        }
+    }
+}
+
+template <bool F, bool EW, bool EXCL, bool AUDIT, bool TYPED>
 __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
 {
     const int BLOCK = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap = a.cap;
-    double2 *pxy = reinterpret_cast<double2 *>(smem_raw);      // {s_x, s_y}, s = r/L (src/nonbonded.jl:60-61)
-    double2 *pzm = pxy + cap;                                  // {s_z, (type << 32) | id}
-    float4 *prel = reinterpret_cast<float4 *>(pzm + cap);
+    double2 *pxy = reinterpret_cast<double2 *>(smem_raw);      // {x, y} in the brick's frame
+    double2 *pzm = pxy + cap;                                  // {z, (type << 32) | id}
+    float4 *prel = reinterpret_cast<float4 *>(pzm + cap);      // FP32 copy {x, y, z, |p|^2} for the scan
     constexpr bool typed = TYPED;    // LJ classes through the shared-memory pair table; else per-atom gathers
     int *sslot = reinterpret_cast<int *>(prel + cap);
-    double2 *ljt = reinterpret_cast<double2 *>(sslot + (typed ? 0 : cap));
-    int *cs = reinterpret_cast<int *>(ljt + FC_MAX_TYPES * FC_MAX_TYPES);
+    double2 *ljt = reinterpret_cast<double2 *>(sslot + (typed ? 0 : cap + (cap & 1)));
+    double *ctab = reinterpret_cast<double *>(ljt + FC_MAX_TYPES * FC_MAX_TYPES);
+    int *cs = reinterpret_cast<int *>(ctab + FC_DIMTAB);
     int *gbase = cs + (a.ncs_max + 1);
-    int *hstart = gbase + (a.ncs_max + 1);
+    int *ccoord = gbase + (a.ncs_max + 1);
+    int *hstart = ccoord + (a.ncs_max + 1);
     int *tstart = hstart + (FC_MAX_HOMEROWS + 1);
     int *scal = tstart + (FC_MAX_HOMEROWS + 1);
     uint16_t *queue = reinterpret_cast<uint16_t *>(
@@ -115,30 +245,16 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NW = BLOCK / 32;
-    const int R = g.R, M = g.M;
+    const int R = g.R;
 
     // ---- brick geometry ---------------------------------------------------------------------
     const int bid = blockIdx.x + a.block_first;
-    int b = bid;
-    const int bxi = b % g.nbx; b /= g.nbx;
-    const int byi = b % g.nby;
-    const int bzi = b / g.nby;
-    const int hx0 = bxi * g.bx, hy0 = byi * g.by, hz0 = g.zhome0 + bzi * g.bz;   // first home cell (local z)
-    const int nhx = min(g.bx, M - hx0), nhy = min(g.by, M - hy0), nhz = min(g.bz, g.zhome0 + g.nzhome - hz0);
-    const int sxn = nhx + 2 * R, syn = nhy + 2 * R, szn = nhz + 2 * R;
-    const int nrows = syn * szn, ncs = nrows * sxn;
+    const BrickGeom bg = brick_geom(g, bid);
+    const int nhx = bg.nhx, nhy = bg.nhy, nhz = bg.nhz;
+    const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;
 
     // ---- phase A: staged-cell table (count and first global slot of every staged cell) --------
-    for (int t = tid; t < ncs; t += BLOCK) {
-        const int cx = t % sxn, row = t / sxn, cy = row % syn, cz = row / syn;
-        const int gx = wrap_mod(hx0 - R + cx, M), gy = wrap_mod(hy0 - R + cy, M);
-        int lz = hz0 - R + cz;
-        if (g.zwrap) lz = wrap_mod(lz, M);
-        const int lc = gx + M * (gy + M * lz);
-        const int s0 = a.cell_start[lc];
-        gbase[t] = s0;
-        cs[t] = a.cell_start[lc + 1] - s0;
-    }
+    stage_cell_table(a, bg, cs, gbase, ccoord, ctab);
     if (typed)
         for (int t = tid; t < a.ntypes * a.ntypes; t += BLOCK) ljt[t] = a.ljtab[t];
     __syncthreads();
@@ -184,48 +300,21 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const int nstaged = min(scal[1], cap);
     const int ntasks = scal[2];
 
-    // ---- phase B: stage atoms row by row (each row = up to two contiguous slot ranges) --------
-    for (int piece = warp; piece < 2 * nrows; piece += NW) {
-        const int row = piece >> 1, second = piece & 1;
-        const int cy = row % syn, cz = row / syn;
-        const int ux0 = hx0 - R;                       // unwrapped x of staged cx = 0
-        const int gx0 = wrap_mod(ux0, M);
-        const int len1 = min(sxn, M - gx0);            // cells before the periodic wrap
-        const int cfirst = second ? len1 : 0, clast = second ? sxn : len1;
-        if (cfirst >= clast) continue;
-        const int ibeg = cs[row * sxn + cfirst], iend = min(cs[row * sxn + clast], cap);
-        const int sbeg = gbase[row * sxn + cfirst];
-        // cell centre relative to the brick centre, in cell units
-        const double ccy = (double)(cy - R) + 0.5 - 0.5 * nhy, ccz = (double)(cz - R) + 0.5 - 0.5 * nhz;
-        const double csy = ((double)(hy0 - R + cy) + 0.5) / M;                      // unwrapped scaled centre
-        const int uz = (g.zwrap ? hz0 : g.zglob0 + hz0) - R + cz;
-        const double csz = ((double)uz + 0.5) / M;
-        for (int idx = ibeg + lane; idx < iend; idx += 32) {
-            const int slot = sbeg + (idx - ibeg);
-            int cx = cfirst;
-            while (cx + 1 < clast && cs[row * sxn + cx + 1] <= idx) cx++;
-            const double sxv = a.sx[slot], syv = a.sy[slot], szv = a.sz[slot];
-            pxy[idx] = make_double2(sxv, syv);
-            pzm[idx] = make_double2(szv, __hiloint2double(typed ? a.type[slot] : 0, a.id[slot]));
-            if (!typed) sslot[idx] = slot;
-            const double csx = ((double)(ux0 + cx) + 0.5) / M;
-            double dx = sxv - csx, dy = syv - csy, dz = szv - csz;
-            dx -= rint(dx); dy -= rint(dy); dz -= rint(dz);      // image nearest to the staged cell
-            float4 p;
-            p.x = (float)(a.L * dx + ((double)(cx - R) + 0.5 - 0.5 * nhx) * a.cell_edge);
-            p.y = (float)(a.L * dy + ccy * a.cell_edge);
-            p.z = (float)(a.L * dz + ccz * a.cell_edge);
-            p.w = fmaf(p.z, p.z, fmaf(p.y, p.y, p.x * p.x));
-            prel[idx] = p;
-        }
-    }
+    // ---- phase B: stage every atom of the brick and its halo in the brick's frame ---------------
+    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, [&](int idx, int slot, double px, double py, double pz) {
+        if (!typed) sslot[idx] = slot;
+        pxy[idx] = make_double2(px, py);
+        pzm[idx] = make_double2(pz, __hiloint2double(typed ? a.type[slot] : 0, a.id[slot]));
+        float4 p;
+        p.x = (float)px; p.y = (float)py; p.z = (float)pz;
+        p.w = fmaf(p.z, p.z, fmaf(p.y, p.y, p.x * p.x));
+        prel[idx] = p;
+    });
     __syncthreads();
 
     // ---- phase C: warp tasks -----------------------------------------------------------------
-    const double c60id2 = 60.0 * a.model.id2;
-    const double rc2 = a.model.rc2, L = a.L;
-    const float rc2f = a.rc2f;
-    const float scan2f = MODE == 1 ? a.rl2f : a.rc2f;     // what the window scan accepts
+    const double L = a.L;
+    const float scan2f = a.rc2f;                          // what the window scan accepts
     const int nwin = 2 * R + 1;
     double esum = 0, wsum = 0;
     unsigned long long npair = 0, hsum = 0, hxor = 0;
@@ -255,7 +344,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         while (cs[hrow * sxn + cxi + 1] <= me) cxi++;
         const int slot_i = gbase[hrow * sxn + cxi] + (me - cs[hrow * sxn + cxi]);
         const double2 q0 = pxy[me], q1 = pzm[me];
-        const double six = q0.x, siy = q0.y, siz = q1.x;
+        const double pix = q0.x, piy = q0.y, piz = q1.x;
         const int32_t idi = __double2loint(q1.y), typi = __double2hiint(q1.y);
         double hsi = 0, tsi = 0;
         if (!typed) { hsi = a.hs[slot_i]; tsi = a.ts[slot_i]; }
@@ -263,46 +352,42 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         int32_t xb = 0; uint64_t xm = 0;
         if (EXCL) { xb = a.xbase[slot_i]; xm = a.xmask[slot_i]; }
         double fx = 0, fy = 0, fz = 0, e = 0, w = 0;
-        uint16_t *lrow = nullptr;               // this task's pair-list rows, lane's column
-        int nrow = 0;                           // rows stored so far (MODE 1)
-        if (MODE != 0) {
-            if (t >= a.tmax) { atomicCAS(a.err, 0, 5); break; }
-            lrow = a.list + ((size_t)(bid * a.tmax + t) * a.lcap) * 32 + lane;
-        }
         int cnt = 0;                            // entries on this lane's stack: queue[k*BLOCK + tid], k < cnt
         uint16_t *qp = queue + tid;             // next free entry
 
-        // one stack entry, branch-free: invalid or culled entries contribute nothing
-        auto pair_eval = [&](int idx, bool valid, int row) {
+        // one stack entry, branch-free except for the rare exact-cull path: invalid or culled entries contribute nothing
+        auto pair_eval = [&](int idx, bool valid) {
             const int j = valid ? (int)queue[idx * BLOCK + tid] : me;
-            if (MODE == 1) {
-                if (row < a.lcap) lrow[(size_t)row * 32] = valid ? (uint16_t)j : (uint16_t)0xFFFF;
-                else atomicCAS(a.err, 0, 5);
-            }
             const double2 j0 = pxy[j], j1 = pzm[j];
-            double vx, vy, vz;
-            const double r2 = min_image_r2(six, siy, siz, j0.x, j0.y, j1.x, L, vx, vy, vz);
-            bool ok = valid && (j != me) && (r2 <= rc2);
+            const double vx = pix - j0.x, vy = piy - j0.y, vz = piz - j1.x;
+            const double r2 = fma(vz, vz, fma(vy, vy, vx * vx));
+            const int where = pair_in_range(r2, a.rc2hi);
+            bool in = where < 0, xover = false;
+            double xval = 0.0;
+            if (where == 0 && valid && j != me) {          // within 3e-6 of rc2: the oracle's rounding sequence decides
+                const int slot_j = typed ? staged_slot(j, cs, gbase, ncs) : sslot[j];
+                in = exact_in_range(a.sx, a.sy, a.sz, slot_i, slot_j, L, a.model, &xval);
+                xover = true;
+            }
+            bool ok = valid && (j != me) && in;
             const int32_t idj = __double2loint(j1.y);
             if (EXCL) ok = ok && !pair_excluded(xb, xm, idj);
-            double sig, tt;
+            double sig2, tt;
             if (!typed) {
                 const int slot_j = sslot[j];
-                sig = hsi + a.hs[slot_j];
+                const double sig = hsi + a.hs[slot_j];
+                sig2 = sig * sig;
                 tt = tsi * a.ts[slot_j];
             } else {
                 const double2 pr = ljrow[__double2hiint(j1.y)];   // one class: every lane reads entry 0 (broadcast)
-                sig = pr.x; tt = pr.y;
+                sig2 = pr.x; tt = pr.y;
             }
-            const double r2s = ok ? r2 : 1.0;
-            const double inv = rcp_fast(r2s);
-            double Eg, Wg;
-            lj_interaction(r2s, inv, sig, tt, a.model, c60id2, Eg, Wg);
-            if (F) {
-                const double qf = ok ? Wg * inv : 0.0;
-                fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+            double Eg = 0, Wg = 0;
+            const double qf = lj_pair_q<EW>(r2, sig2, tt, a.fast, xover, xval, Eg, Wg);
+            if (ok) {
+                if (F) { fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz); }
+                if (EW) { e += Eg; w += Wg; }
             }
-            if (EW) { e += ok ? Eg : 0.0; w += ok ? Wg : 0.0; }
             if (AUDIT && ok && idi < idj) {
                 const uint64_t hh = pair_hash(idi, idj);
                 npair++; hsum += hh; hxor ^= hh;
@@ -315,18 +400,19 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         // pop the newest `depth` entries of every lane (all of them when depth >= the fullest stack)
         auto drain = [&](int depth) {
             for (int k = 0; k < depth; k += 4) {      // four independent pair evaluations in flight
-                pair_eval(cnt - 1 - k, k < cnt, nrow);
-                pair_eval(cnt - 2 - k, k + 1 < cnt && k + 1 < depth, nrow + 1);
-                pair_eval(cnt - 3 - k, k + 2 < cnt && k + 2 < depth, nrow + 2);
-                pair_eval(cnt - 4 - k, k + 3 < cnt && k + 3 < depth, nrow + 3);
-                nrow += 4;
+                pair_eval(cnt - 1 - k, k < cnt);
+                pair_eval(cnt - 2 - k, k + 1 < cnt && k + 1 < depth);
+                pair_eval(cnt - 3 - k, k + 2 < cnt && k + 2 < depth);
+                pair_eval(cnt - 4 - k, k + 3 < cnt && k + 3 < depth);
             }
             cnt = max(cnt - depth, 0);
             qp = queue + cnt * BLOCK + tid;
         };
+        // a candidate that passed the FP32 test is stacked for evaluation
+        auto accept = [&](int p, float) { *qp = (uint16_t)p; qp += BLOCK; cnt++; };
 
         // -------- scan: (2R+1)^2 rows, one shared window of cells [cxa-R, cxb+R] per row --------
-        for (int rw = 0; MODE != 2 && rw < nwin * nwin; rw++) {
+        for (int rw = 0; rw < nwin * nwin; rw++) {
             const int row = (czi + rw / nwin - R) * syn + (cyi + rw % nwin - R);
             const int p0 = cs[row * sxn + cxa - R];
             const int p1 = min(cs[row * sxn + cxb + R + 1], nstaged);
@@ -340,47 +426,21 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
                     const float r1 = fmaf(c1.x, m2x, fmaf(c1.y, m2y, fmaf(c1.z, m2z, c1.w + pp)));
                     const float r2 = fmaf(c2.x, m2x, fmaf(c2.y, m2y, fmaf(c2.z, m2z, c2.w + pp)));
                     const float r3 = fmaf(c3.x, m2x, fmaf(c3.y, m2y, fmaf(c3.z, m2z, c3.w + pp)));
-                    if (r0 <= scan2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
-                    if (r1 <= scan2f) { *qp = (uint16_t)(p + 1); qp += BLOCK; cnt++; }
-                    if (r2 <= scan2f) { *qp = (uint16_t)(p + 2); qp += BLOCK; cnt++; }
-                    if (r3 <= scan2f) { *qp = (uint16_t)(p + 3); qp += BLOCK; cnt++; }
+                    if (r0 <= scan2f) accept(p, r0);
+                    if (r1 <= scan2f) accept(p + 1, r1);
+                    if (r2 <= scan2f) accept(p + 2, r2);
+                    if (r3 <= scan2f) accept(p + 3, r3);
                 }
                 for (; p < pe; p++) {
                     const float4 c = prel[p];
                     const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
-                    if (r <= scan2f) { *qp = (uint16_t)p; qp += BLOCK; cnt++; }
+                    if (r <= scan2f) accept(p, r);
                 }
-                const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
-                if (over > 0) drain(max(over, FC_MINPOP));
-            }
-        }
-        // -------- MODE 2: walk the stored pair-list rows instead of the window --------
-        if (MODE == 2) {
-            const int nrows = min(a.list_rows[bid * a.tmax + t], a.lcap);
-            uint16_t ent[FC_QCHUNK], nxt[FC_QCHUNK];
-#pragma unroll
-            for (int k = 0; k < FC_QCHUNK; k++) ent[k] = (k < nrows) ? lrow[(size_t)k * 32] : (uint16_t)0xFFFF;
-            for (int k0 = 0; k0 < nrows; k0 += FC_QCHUNK) {
-                // the next chunk's rows are requested before this chunk is processed (hides the L2/HBM latency)
-#pragma unroll
-                for (int k = 0; k < FC_QCHUNK; k++)
-                    nxt[k] = (k0 + FC_QCHUNK + k < nrows) ? lrow[(size_t)(k0 + FC_QCHUNK + k) * 32] : (uint16_t)0xFFFF;
-#pragma unroll
-                for (int k = 0; k < FC_QCHUNK; k++) {
-                    const int j = ent[k];
-                    const float4 c = prel[j == 0xFFFF ? me : j];
-                    const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
-                    if (j != 0xFFFF && r <= rc2f) { *qp = (uint16_t)j; qp += BLOCK; cnt++; }
-                }
-#pragma unroll
-                for (int k = 0; k < FC_QCHUNK; k++) ent[k] = nxt[k];
                 const int over = __reduce_max_sync(0xffffffffu, cnt) - (FC_QCAP - FC_QCHUNK);
                 if (over > 0) drain(max(over, FC_MINPOP));
             }
         }
         drain(__reduce_max_sync(0xffffffffu, cnt));
-        if (MODE == 1 && lane == 0) a.list_rows[bid * a.tmax + t] = nrow;
-
         if (active) {
             if (F) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
             if (EW) {

@@ -71,6 +71,55 @@ __device__ __forceinline__ void lj_interaction(double r2, double inv_r2, double 
     Wg = fma(W0, g, E * G);
 }
 
+// ---- the stepping path's pair function -------------------------------------------------------------
+// Same quantities as lj_interaction(), re-associated for the FP64 pipe (the tolerance is 1e-10 on E/W and
+// 1e-9 F_rms on forces, not bit equality; the pair SET stays bit-exact, see pair_in_range below):
+//   * one reciprocal: MUFU.RCP64H seed (input mantissa truncated to 20 bits, so e <= 2^-20) and ONE cubic
+//     correction y(1 + e + e^2), error e^3 ~ 1e-18 -- three DFMAs instead of four;
+//   * sigma^2 and the epsilon product come from the class table;
+//   * x = fma(r2, id2, -rs2*id2); x < 0 is clamped with an integer test of the sign bit (ALU pipe, not a
+//     DSETP); the x >= 1 branches (x == 1 gives 0.5, x > 1 gives 0) can only be reached within rounding of
+//     rc2, where the exact slow path evaluates the oracle's own clamped x and passes it in (xover, xval);
+//   * q = W/r2 = W0*g/r2 + E*G/r2 with G/r2 = 60 id2 (x(1-x))^2, so r2 cancels.
+// 22 FP64-pipe instructions for q (+ 6 for the geometry, + 3 to accumulate the force).
+struct LJFast {
+    double id2, nrs2id2, c60id2;   // 1/(rc2-rs2), -rs2*id2, 60*id2
+};
+template <bool EW>
+__device__ __forceinline__ double lj_pair_q(double r2, double sig2, double tt, const LJFast &m, bool xover, double xval,
+                                            double &Eg, double &Wg)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
+    const double e = fma(-r2, y, 1.0);
+    const double inv = fma(y, fma(e, e, e), y);
+    const double s2 = sig2 * inv;                    // :31
+    const double s6 = s2 * s2 * s2;                  // :32
+    const double e4s6 = tt * s6;                     // :33
+    const double E = fma(e4s6, s6, -e4s6);           // :34
+    const double W0 = e4s6 * fma(12.0, s6, -6.0);    // :35
+    double x = fma(r2, m.id2, m.nrs2id2);            // :36
+    x = __double2hiint(x) < 0 ? 0.0 : x;             // :37, x < 0 branch
+    x = xover ? xval : x;                            // :37 as the oracle evaluated it (borderline pairs only)
+    const double x2 = x * x;                         // :38
+    const double g = fma(x * x2, fma(-6.0, x2, fma(15.0, x, -10.0)), 1.0);   // :39
+    const double t = x - x2;                         // x(1-x)
+    const double q = fma(E * m.c60id2, t * t, (W0 * g) * inv);               // (:35*g + E*:40)/r2
+    if (EW) { Eg = E * g; Wg = q * r2; }             // :41
+    return q;
+}
+
+// Cutoff decision from a local-frame r2 (rounding differs from the oracle's by ~1e-15 relative):
+//   hi word of r2 well below / above that of rc2  -> decided here with two integer compares;
+//   within 3 * 2^-20 of rc2 (a few hundred pairs per million-atom step) -> the caller evaluates the oracle's
+//   exact rounding sequence (min_image_r2 on the scaled coordinates) and decides on that.
+// Returns -1 inside, +1 outside, 0 borderline.
+__device__ __forceinline__ int pair_in_range(double r2, int rc2hi)
+{
+    const int t = __double2hiint(r2) - (rc2hi - 1);
+    return t < 0 ? -1 : ((unsigned)t <= 2u ? 0 : 1);
+}
+
 // Exclusion test: bit (j - base_i) of mask_i over the window [base_i, base_i+64).
 __device__ __forceinline__ bool pair_excluded(int32_t base_i, uint64_t mask_i, int32_t id_j)
 {

@@ -108,6 +108,11 @@ int emdee_get_totals(emdee_system *sys, double *E, double *W, int64_t *npairs);
  * sorted (i<j) pairs for small N, or (count, sum hash, xor hash) with hash = splitmix64((i<<32)|j). */
 int emdee_pair_set(emdee_system *sys, int32_t *ij_2xcap, int64_t cap, int64_t *n);
 int emdee_pair_set_digest(emdee_system *sys, uint64_t out[3]);
+/* Audit of the stepping path: number of pairs (i<j) the pair-list kernel evaluated inside the cutoff at the
+ * current positions; equals emdee_pair_set_digest's count on the same positions (the list pre-culls are
+ * conservative, the final decision is the oracle's).  Needs a valid list, i.e. a preceding emdee_vv_step.
+ * Returns -1 in *npairs when the system steps without a list (no skin, EMDEE_LIST=0, > 16 LJ classes). */
+int emdee_list_pair_count(emdee_system *sys, int64_t *npairs);
 
 /* Velocity-Verlet (absent from the reference): nsteps of
  * v += dt/2m f ; r += dt v ; f = F(r) ; v += dt/2m f, re-binning every `rebin_every` steps

@@ -296,6 +296,85 @@ def test_velocity_verlet(em, oracle):
     s.close()
 
 
+def test_pair_list_stepping_audit(em, oracle):
+    """The stepping path (pair list built on the re-binning step, walked by k_force_list afterwards): after
+    steps that only walked the list, forces and the evaluated pair count equal the oracle's at the same
+    positions.  A pair the FP16/FP32 pre-culls dropped near rc would be invisible in the forces (g -> 0 there),
+    so the count is the sharp check."""
+    pos, L = em.workloads.fcc_lattice(16)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_masses(np.ones(N))
+    s.set_skin(0.4)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    for nsteps in (1, 3):                       # 1: the build step itself; 3 more: list walks
+        s.vv_step(0.005, nsteps, rebin_every=5)
+        s.synchronize()
+        p = s.positions()
+        ref = oracle.cutoff_cells(p, L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+        assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+        assert s.list_pair_count() == ref["npairs"]
+    s.close()
+
+
+def test_pair_list_shell_exactly_at_cutoff(em, oracle):
+    """Simple-cubic lattice with spacing rc/2: six neighbours of every atom sit at r = rc up to the rounding of
+    the oracle's s = r/L sequence, so every lane takes the exact-decision path.  Pair set and count must match
+    the oracle bit for bit in the single-point kernel and in the stepping kernel."""
+    n, a0 = 12, 1.25
+    L = n * a0
+    g = np.arange(n) * a0
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), axis=-1).reshape(-1, 3) + 0.25
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.set_velocities(np.zeros((N, 3)))
+    s.set_masses(np.ones(N))
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    s.set_skin(0.3)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(1e-6, 2, rebin_every=5)           # forces vanish by symmetry: the atoms stay put (to ~1e-20)
+    s.synchronize()
+    ref2 = oracle.cutoff_cells(s.positions(), L, 2.5, 2.0, atoms, ndiv=1)
+    assert s.list_pair_count() == ref2["npairs"]
+    assert np.abs(s.forces() - ref2["forces"]).max() <= 1e-9
+    s.close()
+
+
+def test_pair_list_molecular(em, oracle, dioxin_water):
+    """Stepping path with several LJ classes and exclusions (removed when the list is built)."""
+    g = dioxin_water
+    pos, L = g["positions"], float(g["box"])
+    N = pos.shape[0]
+    sig = g["type_sigma_nm"][g["type_index"]] * 10.0
+    eps = g["type_epsilon"][g["type_index"]]
+    atoms = np.stack([0.5 * sig, 2.0 * np.sqrt(eps)], axis=1)
+    base, mask = em.workloads.exclusion_masks(N, g["bonds"])
+    s = make_system(em, pos, L, 10.0, 9.0, atoms)
+    s.set_exclusions(base, mask)
+    rng = np.random.default_rng(5)
+    s.set_velocities(rng.normal(size=(N, 3)) * 0.5)
+    s.set_masses(np.full(N, 12.0))
+    s.set_skin(1.0)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.002, 3, rebin_every=5)
+    s.synchronize()
+    ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
+    assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    n = s.list_pair_count()
+    assert n == ref["npairs"] or n == -1        # -1: more LJ classes than the pair table holds, no list
+    s.close()
+
+
 def test_skin_violation_is_reported(em):
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
