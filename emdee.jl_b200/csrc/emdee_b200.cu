@@ -136,6 +136,7 @@ struct emdee_system {
     bool fc_typed = false;
     int fc_shape[3] = {0, 0, 0};
     int fl_block = 192;                       // block size of k_force_list
+    bool fl_ilp8 = true;
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
@@ -389,6 +390,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     s->L = L;
     if (const char *e = getenv("EMDEE_LIST")) s->use_list = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_LIST_CHUNKS")) s->lcap8 = std::max(4, atoi(e));
+    if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -1146,21 +1148,27 @@ static int launch_build_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
     auto kern = k_list_build<EXCL>;
-    const size_t smem = lb_smem_bytes(s->fc_cap, s->fc_ncs, EXCL);
+    const size_t smem = lb_smem_bytes(s->fc_cap, s->fc_ncs, LB_MAX_BLOCK, EXCL);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nblocks, LB_MAX_BLOCK, smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_list_build");
 }
-template <bool MULTI, bool COUNT>
-static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks)
+template <bool MULTI, bool COUNT, int ILP>
+static int launch_list_i(emdee_system *s, const CellArgs &a, int nblocks)
 {
-    if (nblocks <= 0) return EMDEE_OK;
-    auto kern = k_force_list<MULTI, COUNT>;
+    auto kern = k_force_list<MULTI, COUNT, ILP>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->fl_smem));
     kern<<<nblocks, s->fl_block, s->fl_smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
     return check_launch("k_force_list");
+}
+template <bool MULTI, bool COUNT>
+static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks)
+{
+    if (nblocks <= 0) return EMDEE_OK;
+    // blocks of up to 192 threads run the 8-chain variant (more registers per thread), larger ones the 4-chain variant
+    return s->fl_block <= 192 && s->fl_ilp8 ? launch_list_i<MULTI, COUNT, 8>(s, a, nblocks) : launch_list_i<MULTI, COUNT, 4>(s, a, nblocks);
 }
 template <bool TYPED>
 static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT)
@@ -1238,10 +1246,13 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         const double cmax = std::max(hx, std::max(hy, hz));
         const double ulp_c = std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(cmax))) - 10);   // FP16 ulp at cmax
         const double u = std::ldexp(1.0, -11);                                                        // FP16 unit roundoff
-        const double dd = ulp_c + 4.0 * u * (s->cutoff + 1.0);           // per-component error of a separation (2 x ulp/2 + rounding of d)
-        const double rc = s->cutoff;
-        const double e2 = 2.0 * std::sqrt(3.0) * rc * dd + 3.0 * dd * dd + 8.0 * u * (rc * rc + 1.0);   // bound on |r2_fp16 - r2|
-        a.rc2h = (float)((rc * rc + 1.5 * e2) * (1.0 + 2.0 * u));
+        const double dd = ulp_c + 4.0 * u * (s->cutoff + s->skin + 1.0);   // per-component error of a separation (2 x ulp/2 + rounding of d)
+        auto thr16 = [&](double rc) {      // threshold such that r <= rc implies r2_fp16 <= threshold
+            const double e2 = 2.0 * std::sqrt(3.0) * rc * dd + 3.0 * dd * dd + 8.0 * u * (rc * rc + 1.0);   // bound on |r2_fp16 - r2|
+            return (float)((rc * rc + 1.5 * e2) * (1.0 + 2.0 * u));
+        };
+        a.rc2h = thr16(s->cutoff);
+        a.rl2h = thr16(s->cutoff + s->skin);
     }
     if (mode != 0) {
         if (bitmask != EMDEE_FORCES || audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list modes evaluate forces only");

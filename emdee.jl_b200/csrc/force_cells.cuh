@@ -74,6 +74,7 @@ struct CellArgs {
     int rc2hi;                        // high word of rc2 (pair_in_range)
     LJFast fast;
     float rc2h;                       // k_force_list: FP16 pre-cull threshold (conservative, set by the host)
+    float rl2h;                       // k_list_build: FP16 threshold of the list, (rc + skin)^2 + rounding bound
 };
 
 // Brick geometry shared by the kernels that stage a brick.

@@ -101,8 +101,12 @@ __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned
     *npair = n;
 }
 
-template <bool MULTI, bool COUNT>
-__global__ void __launch_bounds__(FL_MAX_BLOCK, 2) k_force_list(CellArgs a)
+// ILP = stack entries evaluated per drain iteration.  The drain is a chain of ~20 dependent FP64 operations per
+// pair, so what keeps the FP64 pipe busy is the number of independent chains per scheduler: registers per
+// scheduler / (registers per chain).  ILP 8 with 192-thread blocks (<= 170 registers) gives 3 warps x 8 chains,
+// ILP 4 with 256-thread blocks (<= 128 registers) 4 warps x 4.
+template <bool MULTI, bool COUNT, int ILP>
+__global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list(CellArgs a)
 {
     const int BLOCK = blockDim.x;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -276,13 +280,11 @@ __global__ void __launch_bounds__(FL_MAX_BLOCK, 2) k_force_list(CellArgs a)
             fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
             if (COUNT) np += t < 0 ? 1 : 0;
         };
-        // pop the newest `depth` (a multiple of 4) entries of every lane
+        // pop the newest `depth` (a multiple of ILP) entries of every lane
         auto drain = [&](int depth) {
-            for (int k = 0; k < depth; k += 4) {      // four independent pair evaluations in flight
-                pair_eval(cnt - 1 - k);
-                pair_eval(cnt - 2 - k);
-                pair_eval(cnt - 3 - k);
-                pair_eval(cnt - 4 - k);
+            for (int k = 0; k < depth; k += ILP) {    // ILP independent pair evaluations in flight
+#pragma unroll
+                for (int u = 1; u <= ILP; u++) pair_eval(cnt - u - k);
             }
             cnt = max(cnt - depth, 0);
             qp = queue + cnt * BLOCK + tid;
@@ -306,9 +308,9 @@ __global__ void __launch_bounds__(FL_MAX_BLOCK, 2) k_force_list(CellArgs a)
             test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
             e0 = e1; e1 = e2;
             const int over = __reduce_max_sync(0xffffffffu, cnt) - (FL_QCAP - 8);
-            if (over > 0) drain((max(over, FL_MINPOP) + 3) & ~3);
+            if (over > 0) drain((max(over, FL_MINPOP) + ILP - 1) & ~(ILP - 1));
         }
-        drain((__reduce_max_sync(0xffffffffu, cnt) + 3) & ~3);
+        drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
 
         if (tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
             LaneRedo w;

@@ -5,27 +5,40 @@
 // the brick and its halo staged in shared memory in exactly the order k_force_list stages them, so a stored
 // entry (staged index + 1, 16 bits) means the same atom in both kernels.
 //
-// FP32 only, no force evaluation: the kernel is a filter.  Warp task = 32 consecutive home atoms of one home row,
-// one per lane; all lanes walk the same candidate window (the (2R+1)^2 staged rows around the task's row, cells
-// [first-R, last+R]), so every LDS.128 is a one-address broadcast.  Per candidate: |c|^2 - 2 c.p + |p|^2 against
-// (rc + skin)^2 plus a bound on the FP32 rounding (conservative: a listed pair may be outside, a pair inside is
-// never missed); accepted candidates (exclusions removed here, once, instead of on every step) are shifted into a
-// 16-byte register buffer and stored as one chunk per eight entries:
+// The kernel is a filter (no force evaluation) and it is issue-bound, so everything is organised around the
+// instruction count per candidate (ncu: 28 per candidate in the first version, 7 here):
+//   * candidates are staged in FP16, two per 16-byte record {x0,x1, y0,y1, z0,z1, -,-}: one broadcast LDS.128
+//     and seven packed-half instructions test TWO candidates against (rc + skin)^2 plus a bound on the FP16
+//     rounding (conservative: a listed pair may be outside, a pair inside is never missed);
+//   * warp task = 32 consecutive home atoms of one home row, one per lane; all lanes walk the same window (the
+//     (2R+1)^2 staged rows around the task's row, cells [first-R, last+R]), control flow is warp-uniform;
+//   * an accepted candidate costs two predicated instructions: a 2-byte store to the lane's row in shared
+//     memory and the pointer increment; rows are flushed to global memory as 16-byte chunks (LDS.128 + STG.128
+//     per eight entries) whenever one of them is half full.  Exclusions are applied during the flush.
 //   list8[((brick*gmax + h/32)*lcap8 + chunk)*32 + h%32],  h = index of the home atom in the brick's home list.
 #pragma once
+#include <cuda_fp16.h>
+
+#include <type_traits>
+
 #include "force_cells.cuh"
 
 #define LB_MAX_BLOCK 256
+#define LB_ROW_ENTRIES 48                         // capacity of a lane's row
+#define LB_ROW_BYTES (LB_ROW_ENTRIES * 2 + 16)    // 112 B = 28 words: eight distinct banks over the lanes
+#define LB_FLUSH_AT 28                            // flush when a lane holds this many entries (up to 18 may arrive before the next check)
 
-__host__ __device__ inline size_t lb_smem_bytes(int cap, int ncs_max, bool excl)
+__host__ __device__ inline size_t lb_smem_bytes(int cap, int ncs_max, int block, bool excl)
 {
-    size_t b = (size_t)cap * sizeof(float4);
-    if (excl) b += (size_t)cap * sizeof(int);          // global id of every staged atom
+    size_t b = (size_t)(cap / 2 + 20) * sizeof(uint4);     // FP16 pair records (+ slack: the unrolled scan reads up to 16 pairs past the window)
+    if (excl) b += (size_t)(cap + (cap & 1) + 2) * sizeof(int);   // global id of every staged atom
     b += FC_DIMTAB * sizeof(double);
-    b += (size_t)(ncs_max + 1) * sizeof(int) * 3;      // cs[], gbase[], ccoord[]
-    b += 2 * (FC_MAX_HOMEROWS + 1) * sizeof(int);      // hstart[], tstart[]
+    b += (size_t)(ncs_max + 1) * sizeof(int) * 3;          // cs[], gbase[], ccoord[]
+    b += 2 * (FC_MAX_HOMEROWS + 1) * sizeof(int);          // hstart[], tstart[]
     b += 8 * sizeof(int);
-    return (b + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)block * LB_ROW_BYTES;
+    return b;
 }
 
 template <bool EXCL>
@@ -34,15 +47,17 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap = a.cap;
-    float4 *prel = reinterpret_cast<float4 *>(smem_raw);       // {x, y, z, |p|^2} in the brick's frame
-    int *pid = reinterpret_cast<int *>(prel + cap);
-    double *ctab = reinterpret_cast<double *>(pid + (EXCL ? cap : 0));
+    const int npairrec = cap / 2 + 20;
+    uint4 *hp = reinterpret_cast<uint4 *>(smem_raw);           // FP16 coordinates of staged atoms 2q, 2q+1 in the brick's frame
+    int *pid = reinterpret_cast<int *>(hp + npairrec);
+    double *ctab = reinterpret_cast<double *>(pid + (EXCL ? cap + (cap & 1) + 2 : 0));
     int *cs = reinterpret_cast<int *>(ctab + FC_DIMTAB);
     int *gbase = cs + (a.ncs_max + 1);
     int *ccoord = gbase + (a.ncs_max + 1);
     int *hstart = ccoord + (a.ncs_max + 1);
     int *tstart = hstart + (FC_MAX_HOMEROWS + 1);
     int *scal = tstart + (FC_MAX_HOMEROWS + 1);
+    unsigned char *rows = smem_raw + ((reinterpret_cast<unsigned char *>(scal + 8) - smem_raw + 15) & ~(size_t)15);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = g.R;
@@ -52,6 +67,11 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;
 
     stage_cell_table(a, bg, cs, gbase, ccoord, ctab);
+    {   // records past the last staged atom are read by the unrolled scan: make them far away
+        const __half2 far = __floats2half2_rn(60000.0f, 60000.0f);
+        const unsigned fu = *reinterpret_cast<const unsigned *>(&far);
+        for (int q = tid; q < npairrec; q += blockDim.x) hp[q] = make_uint4(fu, fu, fu, 0u);
+    }
     __syncthreads();
     if (warp == 0) {
         int run = 0;
@@ -92,18 +112,23 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
     const int nstaged = min(scal[1], cap);
     const int ntasks = scal[2];
 
+    __half *hph = reinterpret_cast<__half *>(hp);
     stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, [&](int idx, int slot, double px, double py, double pz) {
-        float4 p;
-        p.x = (float)px; p.y = (float)py; p.z = (float)pz;
-        p.w = fmaf(p.z, p.z, fmaf(p.y, p.y, p.x * p.x));
-        prel[idx] = p;
+        __half *rec = hph + (idx >> 1) * 8 + (idx & 1);
+        rec[0] = __float2half_rn((float)px);
+        rec[2] = __float2half_rn((float)py);
+        rec[4] = __float2half_rn((float)pz);
         if (EXCL) pid[idx] = a.id[slot];
     });
     __syncthreads();
 
-    const float rl2f = a.rl2f;
+    const __half thr1 = __float2half_ru(a.rl2h);
+    const __half2 thr = __halves2half2(thr1, thr1);
+    const __half2 thr_lo_off = __halves2half2(__float2half(-1.0f), thr1);   // low candidate of the pair is outside the window
+    const __half2 thr_hi_off = __halves2half2(thr1, __float2half(-1.0f));   // high candidate is outside
     const int nwin = 2 * R + 1;
-    const int lmax = a.lcap8 * 8;
+    unsigned char *myrow = rows + (size_t)tid * LB_ROW_BYTES;
+
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&scal[3], 1);
@@ -121,9 +146,10 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
         const int self = a0 + lane;
         const bool active = self < a1;
         const int me = active ? self : a0;
-        const float4 pi = prel[me];
-        // r2 = |c|^2 + (|p|^2 - 2 c.p); an inactive lane gets |p|^2 = 1e30 and never accepts anything
-        const float m2x = -2.0f * pi.x, m2y = -2.0f * pi.y, m2z = -2.0f * pi.z, pp = active ? pi.w : 1e30f;
+        // own coordinates, duplicated in both halves; an inactive lane sits far away and accepts nothing
+        const __half *mrec = hph + (me >> 1) * 8 + (me & 1);
+        const __half hfar = __float2half(-60000.0f);
+        const __half2 ix = __half2half2(active ? mrec[0] : hfar), iy = __half2half2(mrec[2]), iz = __half2half2(mrec[4]);
         int32_t xb = 0; uint64_t xm = 0;
         if (EXCL) {
             int cxi = cxa;
@@ -135,49 +161,85 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
         if ((h >> 5) >= a.gmax) { atomicCAS(a.err, 0, 5); break; }
         const size_t gs = (size_t)bid * a.gmax + (h >> 5);
         uint4 *lp = a.list8 + gs * a.lcap8 * 32 + (h & 31);
-        uint4 lb = make_uint4(0u, 0u, 0u, 0u);      // the chunk being filled: new entries enter at the top, zeros (dummy) below
-        int nlist = 0;
+        int nchunks = 0;                    // chunks already in global memory
+        uint16_t *wp = reinterpret_cast<uint16_t *>(myrow);   // next free entry of the row
 
-        auto accept = [&](int p) {
-            bool take = p != me;
-            if (EXCL) take = take && !pair_excluded(xb, xm, pid[p]);
-            if (take) {
-                lb.x = __funnelshift_r(lb.x, lb.y, 16); lb.y = __funnelshift_r(lb.y, lb.z, 16);
-                lb.z = __funnelshift_r(lb.z, lb.w, 16); lb.w = (lb.w >> 16) | ((unsigned)(p + 1) << 16);
-                nlist++;
-                if ((nlist & 7) == 0) {           // one 16-byte store per eight entries
-                    if (nlist <= lmax) lp[(size_t)((nlist >> 3) - 1) * 32] = lb;
-                    lb = make_uint4(0u, 0u, 0u, 0u);
+        // entries in the row -> global chunks; keep = false also writes the last partial chunk (unused entries = dummy)
+        auto flush = [&](bool keep) {
+            const int n = (int)(wp - reinterpret_cast<uint16_t *>(myrow));
+            const int nfull = n >> 3, rem = n & 7;
+            const int nout = keep ? nfull : nfull + (rem ? 1 : 0);
+            const int nmax = __reduce_max_sync(0xffffffffu, nout);
+            for (int c = 0; c < nmax; c++) {
+                if (c < nout) {
+                    uint4 v = *reinterpret_cast<const uint4 *>(myrow + c * 16);
+                    unsigned e[4] = {v.x, v.y, v.z, v.w};
+                    const int valid = c < nfull ? 8 : rem;       // entries of this chunk that are real
+#pragma unroll
+                    for (int k = 0; k < 8; k++) {
+                        unsigned ent = (e[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                        bool drop = k >= valid;
+                        if (EXCL && !drop) drop = pair_excluded(xb, xm, pid[ent - 1]);
+                        if (drop) e[k >> 1] &= (k & 1) ? 0x0000ffffu : 0xffff0000u;
+                    }
+                    if (nchunks + c < a.lcap8) lp[(size_t)(nchunks + c) * 32] = make_uint4(e[0], e[1], e[2], e[3]);
+                    else atomicCAS(a.err, 0, 5);
                 }
             }
+            if (keep) {
+                if (rem && nfull) *reinterpret_cast<uint4 *>(myrow) = *reinterpret_cast<const uint4 *>(myrow + nfull * 16);
+                wp = reinterpret_cast<uint16_t *>(myrow) + rem;
+            }
+            nchunks += nout;
+        };
+
+        // two candidates (staged indices 2q, 2q+1) against this lane's atom; SELF: the row holds this lane's own atom
+        auto test2 = [&](int q, __half2 th, auto SELF) {
+            const uint4 c = hp[q];
+            const __half2 dx = __hsub2(*reinterpret_cast<const __half2 *>(&c.x), ix);
+            const __half2 dy = __hsub2(*reinterpret_cast<const __half2 *>(&c.y), iy);
+            const __half2 dz = __hsub2(*reinterpret_cast<const __half2 *>(&c.z), iz);
+            const __half2 r2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
+            bool lo = __hle(__low2half(r2), __low2half(th)), hi = __hle(__high2half(r2), __high2half(th));
+            if (decltype(SELF)::value) { lo = lo && (2 * q != me); hi = hi && (2 * q + 1 != me); }
+            if (lo) { *wp = (uint16_t)(2 * q + 1); wp++; }
+            if (hi) { *wp = (uint16_t)(2 * q + 2); wp++; }
+        };
+        auto row_full = [&]() { return __any_sync(0xffffffffu, (int)(wp - reinterpret_cast<uint16_t *>(myrow)) >= LB_FLUSH_AT); };
+        // one window row [p0, p1): the first and the last record may hold a candidate of a neighbouring window
+        auto scan_row = [&](int p0, int p1, auto SELF) {
+            int q = p0 >> 1;
+            const int qlast = (p1 - 1) >> 1;
+            if (q == qlast) {
+                const bool lo_ok = 2 * q >= p0, hi_ok = 2 * q + 1 < p1;
+                test2(q, lo_ok ? (hi_ok ? thr : thr_hi_off) : thr_lo_off, SELF);
+                return;
+            }
+            test2(q, (p0 & 1) ? thr_lo_off : thr, SELF);
+            q++;
+            for (; q + 8 <= qlast; q += 8) {              // interior records, 16 candidates per iteration
+#pragma unroll
+                for (int u = 0; u < 8; u++) test2(q + u, thr, SELF);
+                if (row_full()) flush(true);
+            }
+            for (; q < qlast; q++) test2(q, thr, SELF);
+            test2(qlast, (p1 & 1) ? thr_hi_off : thr, SELF);
         };
 
         for (int rw = 0; rw < nwin * nwin; rw++) {
             const int row = (czi + rw / nwin - R) * syn + (cyi + rw % nwin - R);
             const int p0 = cs[row * sxn + cxa - R];
             const int p1 = min(cs[row * sxn + cxb + R + 1], nstaged);
-            int p = p0;
-            for (; p + 4 <= p1; p += 4) {      // four candidates per iteration: the broadcast loads are issued together
-                const float4 c0 = prel[p], c1 = prel[p + 1], c2 = prel[p + 2], c3 = prel[p + 3];
-                const float r0 = fmaf(c0.x, m2x, fmaf(c0.y, m2y, fmaf(c0.z, m2z, c0.w + pp)));
-                const float r1 = fmaf(c1.x, m2x, fmaf(c1.y, m2y, fmaf(c1.z, m2z, c1.w + pp)));
-                const float r2 = fmaf(c2.x, m2x, fmaf(c2.y, m2y, fmaf(c2.z, m2z, c2.w + pp)));
-                const float r3 = fmaf(c3.x, m2x, fmaf(c3.y, m2y, fmaf(c3.z, m2z, c3.w + pp)));
-                if (r0 <= rl2f) accept(p);
-                if (r1 <= rl2f) accept(p + 1);
-                if (r2 <= rl2f) accept(p + 2);
-                if (r3 <= rl2f) accept(p + 3);
+            if (p0 < p1) {
+                if (row == hrow) scan_row(p0, p1, std::true_type());
+                else scan_row(p0, p1, std::false_type());
             }
-            for (; p < p1; p++) {
-                const float4 c = prel[p];
-                const float r = fmaf(c.x, m2x, fmaf(c.y, m2y, fmaf(c.z, m2z, c.w + pp)));
-                if (r <= rl2f) accept(p);
-            }
+            if (row_full()) flush(true);
         }
-        if (active) {
-            if (nlist > lmax) { atomicCAS(a.err, 0, 5); nlist = lmax; }
-            a.list_n[gs * 32 + (h & 31)] = (uint16_t)nlist;
-            if (nlist & 7) lp[(size_t)(nlist >> 3) * 32] = lb;     // last chunk: the unused entries point at the dummy atom
+        {
+            const int n = nchunks * 8 + (int)(wp - reinterpret_cast<uint16_t *>(myrow));
+            flush(false);
+            if (active) a.list_n[gs * 32 + (h & 31)] = (uint16_t)min(n, a.lcap8 * 8);
         }
     }
 }
