@@ -15,9 +15,11 @@ workload: c3 = LJ fluid N=4,000,000 (fcc 100^3), rc=2.5 sigma, rs=2.0, rho*=0.84
 e2e     : the same metric through the C ABI with HOST buffers: positions in pinned host memory ->
           emdee_set_positions (H2D) -> emdee_bin -> emdee_compute_nonbonded(F|E|V) -> forces, energies,
           virials back to pinned host memory (D2H), every iteration inside the timed region.
-roofline: dominant kernel k_force_cells; achieved = 71 flop x pairs per launch / mean launch duration
-          (CUDA events around every launch, emdee_profile_begin/end); peak = DFMA throughput measured
-          on this GPU in the same run (MEASURED_PEAKS.json holds no FP64 number).
+roofline: dominant kernel k_force_list_p (the pair-list stepping kernel, one launch per step); achieved =
+          71 flop x pairs per launch / mean launch duration (CUDA events around every launch on the library's
+          stream, emdee_profile_begin/end/kind); peak = DFMA throughput measured on this GPU in the same run
+          (MEASURED_PEAKS.json holds no FP64 number).  The pair-list build kernel (one launch per re-binning)
+          is reported beside it; "traffic" is the DRAM bytes per launch of the ncu capture under profiles/.
 The oracle (oracle/) is used here only for the cpu_baseline leg and for --impl reference.
 """
 import argparse
@@ -247,6 +249,9 @@ def run_b200(args):
     barrier()
     wall = time.perf_counter() - wall0
     force_ms, force_launches = s.profile_end()
+    kinds = [s.profile_kind(k) for k in range(3)]          # (ms, launches): window scan, list build, list walk
+    dom = 2 if kinds[2][1] > 0 else 0                       # the stepping kernel; systems that cannot use a list scan windows
+    dom_ms, dom_launches = kinds[dom]
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     ms = allmax(ms)
@@ -255,7 +260,8 @@ def run_b200(args):
     t = ms * 1e-3
     value = pairs * args.steps / t
     atom_steps = N * args.steps / t
-    force_ms_per_launch = allmax(force_ms / max(force_launches, 1))
+    force_ms_per_launch = allmax(dom_ms / max(dom_launches, 1))
+    build_ms_per_launch = allmax(kinds[1][0] / max(kinds[1][1], 1))
 
     # ---- roofline of the dominant kernel (this rank's share of the pairs per launch) ---------------
     nloc, _ = s.local_count()
@@ -269,12 +275,22 @@ def run_b200(args):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     rebins = args.steps / args.rebin_every if args.rebin_every > 0 else 0
     step_bytes = nloc * (BYTES_FORCE_EVAL - 16 + BYTES_VV) + nloc * BYTES_REBIN * rebins / args.steps   # forces only: no e,w
+    traffic = None
+    try:      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        if world == 1 and prof.get("workload") == args.workload and dom == 2:
+            traffic = prof["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
     roofline = {
-        "bound": "fp64", "kernel": "k_force_cells", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
-        "frac": achieved / (fp64_peak / 1e12), "traffic": None,
+        "bound": "fp64", "kernel": "k_force_list_p" if dom == 2 else "k_force_cells", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+        "frac": achieved / (fp64_peak / 1e12), "traffic": traffic,
         "peak_source": "DFMA chains measured in this run (emdee_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": pairs_local, "ms_per_launch": force_ms_per_launch,
-        "launches_timed": force_launches, "kernel_share_of_step": force_ms / ms if ms > 0 else None,
+        "launches_timed": dom_launches, "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
+        "force_kernels_share_of_step": force_ms / ms if ms > 0 else None,
+        "list_build": {"kernel": "k_list_build", "ms_per_launch": build_ms_per_launch, "launches_timed": kinds[1][1],
+                       "share_of_step": kinds[1][0] / ms if ms > 0 else None},
         "hbm": {"achieved": step_bytes / (ms / args.steps * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                 "frac": step_bytes / (ms / args.steps * 1e-3) / 1e9 / hbm_peak,
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",

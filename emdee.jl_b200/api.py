@@ -252,6 +252,12 @@ class NonbondedSystem:
         call("emdee_profile_end", self._h, C.byref(ms), C.byref(n))
         return ms.value, n.value
 
+    def profile_kind(self, kind):
+        """(milliseconds, launches) of one kernel in the last profile: 0 k_force_cells, 1 k_list_build, 2 k_force_list."""
+        ms, n = C.c_double(), C.c_int64()
+        call("emdee_profile_kind", self._h, int(kind), C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
     # -- getters ---------------------------------------------------------------------------------
     def _get3(self, fn, out=None):
         out = np.empty((self.N, 3)) if out is None else out

@@ -11,6 +11,7 @@
 #include "binning.cuh"
 #include "force_cells.cuh"
 #include "force_list.cuh"
+#include "force_list_p.cuh"
 #include "list_build.cuh"
 #include "force_tiles.cuh"
 #include "integrate.cuh"
@@ -137,10 +138,15 @@ struct emdee_system {
     int fc_shape[3] = {0, 0, 0};
     int fl_block = 192;                       // block size of k_force_list
     bool fl_ilp8 = true;
+    bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
     uint16_t *list_n = nullptr;               // entries per home atom
+    int2 *recipe = nullptr;                   // staging recipe of every brick (k_list_build -> k_force_list_p)
+    uint16_t *homeidx = nullptr;
+    int *brickhdr = nullptr;
+    int64_t recipe_cap = 0, hdr_cap = 0;
     int64_t list_slots = 0;                   // allocated groups
     int lcap8 = 24;                           // chunks per atom (192 entries)
     bool list_valid = false, use_list = true;
@@ -166,6 +172,8 @@ struct emdee_system {
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_mode;               // launch mode of every event pair (0 scan, 1 list build, 2 list walk)
     size_t prof_used = 0;
+    double prof_ms[4] = {0, 0, 0, 0};         // per-kind totals of the last profile (emdee_profile_kind)
+    int64_t prof_n[4] = {0, 0, 0, 0};
     // scratch for host transfers
     double *tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -391,6 +399,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_LIST")) s->use_list = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_LIST_CHUNKS")) s->lcap8 = std::max(4, atoi(e));
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -445,7 +454,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
-    dev_free(s->list8); dev_free(s->list_n);
+    dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     delete s;
@@ -751,6 +760,7 @@ static int choose_bricks(emdee_system *s)
         s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
         s->fl_block = lblock;
         s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
+        s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1)) <= c->smem_optin;
         s->fc_typed = typed;
         s->fc_nblocks = g.nbx * g.nby * g.nbz;
         const int64_t nwarps = (int64_t)s->fc_nblocks * (block / 32);
@@ -794,10 +804,20 @@ static int choose_bricks(emdee_system *s)
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const double home = per_cell * g.bx * g.by * g.bz;
         if (listed) {
-            // the stepping kernel (k_force_list) decides: resident warps that hold a 32-atom group, as long as
-            // k_force_cells (list build, one block per SM is enough) fits too
+            // the stepping kernel decides, as long as k_force_cells (single-point evaluations) fits too
             const int cblock = cells_block(cap, ncs, forced_block);
             if (!cblock) continue;
+            if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1)) <= c->smem_optin) {
+                // persistent kernel (two staging buffers): the largest brick that fits, and among equal volumes the
+                // one that stages the fewest cells (least halo per home atom)
+                const double score = 1e6 + 1000.0 * (g.bx * g.by * g.bz) - ncs;
+                if (score > best_score) {
+                    best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
+                    best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
+                    best_budget = c->smem_optin;
+                }
+                continue;
+            }
             const double groups = std::max(1.0, std::ceil(home / 32.0));
             for (int lblock : lblocks) {
                 if (forced_lblock && lblock != forced_lblock) continue;
@@ -1167,6 +1187,14 @@ template <bool MULTI, bool COUNT>
 static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
+    if (s->fl_persistent) {     // one resident block per SM walks over the bricks (force_list_p.cuh)
+        auto kern = k_force_list_p<MULTI, COUNT>;
+        const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<std::min(nblocks, s->ctx->sm_count), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks);
+        s->ctx->launches++;
+        return check_launch("k_force_list_p");
+    }
     // blocks of up to 192 threads run the 8-chain variant (more registers per thread), larger ones the 4-chain variant
     return s->fl_block <= 192 && s->fl_ilp8 ? launch_list_i<MULTI, COUNT, 8>(s, a, nblocks) : launch_list_i<MULTI, COUNT, 4>(s, a, nblocks);
 }
@@ -1259,13 +1287,26 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         if (!list_capable(s)) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: pair list requested for a system that cannot use one");
         const int64_t slots = (int64_t)s->fc_nblocks * s->fc_gmax;
         if (slots > s->list_slots) {
-            dev_free(s->list8); dev_free(s->list_n);
+            dev_free(s->list8); dev_free(s->list_n); dev_free(s->homeidx);
             s->list_slots = slots + slots / 4;
+            EMDEE_TRY(dev_alloc(&s->homeidx, (size_t)s->list_slots * 32));
             if (getenv("EMDEE_DEBUG")) fprintf(stderr, "[emdee] pair list: %lld groups x %d chunks (%.2f GB)\n", (long long)s->list_slots, s->lcap8, (double)s->list_slots * s->lcap8 * 512 / 1e9);
             EMDEE_TRY(dev_alloc(&s->list8, (size_t)s->list_slots * s->lcap8 * 32));
             EMDEE_TRY(dev_alloc(&s->list_n, (size_t)s->list_slots * 32));
             a.list8 = s->list8; a.list_n = s->list_n;
         }
+        const int64_t rneed = (int64_t)s->fc_nblocks * (s->fc_cap + 1);
+        if (rneed > s->recipe_cap) {
+            dev_free(s->recipe);
+            s->recipe_cap = rneed + rneed / 8;
+            EMDEE_TRY(dev_alloc(&s->recipe, (size_t)s->recipe_cap));
+        }
+        if (s->fc_nblocks > s->hdr_cap) {
+            dev_free(s->brickhdr);
+            s->hdr_cap = s->fc_nblocks + s->fc_nblocks / 4;
+            EMDEE_TRY(dev_alloc(&s->brickhdr, (size_t)2 * s->hdr_cap));
+        }
+        a.recipe = s->recipe; a.homeidx = s->homeidx; a.brickhdr = s->brickhdr; a.rcap = s->fc_cap + 1;
         // lanes of a group without a home atom must read "no entries"
         if (mode == 1) CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
     }
@@ -1669,11 +1710,21 @@ extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
         const int m = s->prof_mode[k / 2] & 3;
         per_mode[m] += t; n_mode[m]++;
     }
+    for (int m = 0; m < 4; m++) { s->prof_ms[m] = per_mode[m]; s->prof_n[m] = n_mode[m]; }
     if (getenv("EMDEE_DEBUG"))
         for (int m = 0; m < 4; m++)
             if (n_mode[m]) fprintf(stderr, "[emdee] force kernel mode %d: %d launches, %.4f ms each\n", m, n_mode[m], per_mode[m] / n_mode[m]);
     if (ms) *ms = total;
     if (launches) *launches = (int64_t)(s->prof_used / 2);
+    return EMDEE_OK;
+}
+
+extern "C" int emdee_profile_kind(emdee_system *s, int kind, double *ms, int64_t *launches)
+{
+    SYS_ENTER(s, "emdee_profile_kind");
+    if (kind < 0 || kind > 2) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_profile_kind: kind %d (0 window scan, 1 list build, 2 list walk)", kind);
+    if (ms) *ms = s->prof_ms[kind];
+    if (launches) *launches = s->prof_n[kind];
     return EMDEE_OK;
 }
 

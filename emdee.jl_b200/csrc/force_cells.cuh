@@ -75,6 +75,12 @@ struct CellArgs {
     LJFast fast;
     float rc2h;                       // k_force_list: FP16 pre-cull threshold (conservative, set by the host)
     float rl2h;                       // k_list_build: FP16 threshold of the list, (rc + skin)^2 + rounding bound
+    // staging recipe, written by k_list_build and valid until the next re-binning (the persistent kernel stages from it
+    // instead of rebuilding the cell table on every step):
+    int2 *recipe;                     // recipe[brick*rcap + i], i = staged index + 1: {global slot, cx | cy<<8 | cz<<16}
+    uint16_t *homeidx;                // homeidx[(brick*gmax + h/32)*32 + h%32] = staged index + 1 of home atom h
+    int *brickhdr;                    // brickhdr[2*brick] = staged atoms + 1, [2*brick+1] = home atoms
+    int rcap;
 };
 
 // Brick geometry shared by the kernels that stage a brick.
@@ -148,10 +154,13 @@ __device__ __forceinline__ int wrap_mod(int a, int M)
 // Phase A: count and first global slot of every staged cell, its coordinates inside the staged box, and the
 // unwrapped scaled centres of the staged cells along each dimension.  The caller turns cs[] into an exclusive
 // prefix afterwards.
-__device__ __forceinline__ void stage_cell_table(const CellArgs &a, const BrickGeom &bg, int *cs, int *gbase, int *ccoord, double *ctab)
+// tid / BLOCK: index and size of the thread group that stages (the whole block, or the producer warps of the
+// persistent kernel).
+__device__ __forceinline__ void stage_cell_table(const CellArgs &a, const BrickGeom &bg, int *cs, int *gbase, int *ccoord, double *ctab,
+                                                 int tid, int BLOCK)
 {
     const GridDesc &g = a.g;
-    const int R = g.R, M = g.M, BLOCK = blockDim.x, tid = threadIdx.x;
+    const int R = g.R, M = g.M;
     for (int t = tid; t < bg.ncs; t += BLOCK) {
         const int cx = t % bg.sxn, row = t / bg.sxn, cy = row % bg.syn, cz = row / bg.syn;
         const int gx = wrap_mod(bg.hx0 - R + cx, M), gy = wrap_mod(bg.hy0 - R + cy, M);
@@ -174,18 +183,17 @@ __device__ __forceinline__ void stage_cell_table(const CellArgs &a, const BrickG
 // Phase B: every staged atom [first, last) in the brick's frame.  For staged index idx the cell is found by a
 // fixed-length binary search of the prefix table (three atoms per thread in flight, so their global loads
 // overlap); p = L * ((s - c) - rint(s - c) + (c - b)) with c the unwrapped scaled centre of the staged cell
-// (the periodic image nearest to that cell) and b the brick centre.  store(idx, slot, px, py, pz).
-template <class Store>
+// (the periodic image nearest to that cell) and b the brick centre.  store(idx, slot, cell code, px, py, pz).
+template <int U = 3, class Store>
 __device__ __forceinline__ void stage_atoms(const CellArgs &a, const BrickGeom &bg, const int *cs, const int *gbase, const int *ccoord,
-                                            const double *ctab, int first, int last, Store store)
+                                            const double *ctab, int first, int last, int tid, int BLOCK, Store store)
 {
     const GridDesc &g = a.g;
-    const int BLOCK = blockDim.x, tid = threadIdx.x, M = g.M;
+    const int M = g.M;
     const int uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0);
     const double bcx = ((double)bg.hx0 + 0.5 * bg.nhx) / M, bcy = ((double)bg.hy0 + 0.5 * bg.nhy) / M, bcz = ((double)uz0 + 0.5 * bg.nhz) / M;
     int nsteps = 0;
     while ((1 << nsteps) < bg.ncs) nsteps++;
-    constexpr int U = 3;
     for (int i0 = first + tid; i0 < last; i0 += U * BLOCK) {
         int idx[U], lo[U], slot[U];
         bool ok[U];
@@ -216,7 +224,7 @@ __device__ __forceinline__ void stage_atoms(const CellArgs &a, const BrickGeom &
             const double cx = ctab[cc & 255], cy = ctab[32 + ((cc >> 8) & 255)], cz = ctab[64 + (cc >> 16)];
             double dx = sx[u] - cx, dy = sy[u] - cy, dz = sz[u] - cz;
             dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);      // image nearest to the staged cell
-            store(idx[u], slot[u], a.L * (dx + (cx - bcx)), a.L * (dy + (cy - bcy)), a.L * (dz + (cz - bcz)));
+            store(idx[u], slot[u], cc, a.L * (dx + (cx - bcx)), a.L * (dy + (cy - bcy)), a.L * (dz + (cz - bcz)));
         }
     }
 }
@@ -255,7 +263,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;
 
     // ---- phase A: staged-cell table (count and first global slot of every staged cell) --------
-    stage_cell_table(a, bg, cs, gbase, ccoord, ctab);
+    stage_cell_table(a, bg, cs, gbase, ccoord, ctab, tid, BLOCK);
     if (typed)
         for (int t = tid; t < a.ntypes * a.ntypes; t += BLOCK) ljt[t] = a.ljtab[t];
     __syncthreads();
@@ -302,7 +310,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const int ntasks = scal[2];
 
     // ---- phase B: stage every atom of the brick and its halo in the brick's frame ---------------
-    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, [&](int idx, int slot, double px, double py, double pz) {
+    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, tid, BLOCK, [&](int idx, int slot, int, double px, double py, double pz) {
         if (!typed) sslot[idx] = slot;
         pxy[idx] = make_double2(px, py);
         pzm[idx] = make_double2(pz, __hiloint2double(typed ? a.type[slot] : 0, a.id[slot]));

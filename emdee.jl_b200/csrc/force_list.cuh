@@ -52,7 +52,8 @@ struct LaneRedo {
     const double *pz;
     const uint8_t *ptyp;
     const double2 *ljt;
-    const int *cs, *gbase;
+    const int *cs, *gbase;       // staged-cell table (k_force_list) ...
+    const int2 *recipe;          // ... or the staging recipe (k_force_list_p): global slot of a staged atom
     int ncs, ntypes, me, slot_i, nent;
     const uint16_t *entries;     // this lane's first chunk, viewed as uint16 (chunk stride 256)
     const double *sx, *sy, *sz;  // scaled coordinates in slot order (the oracle's inputs)
@@ -87,7 +88,8 @@ __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned
         bool xover = false;
         double xval = 0.0;
         if (where == 0) {
-            if (!exact_in_range(w.sx, w.sy, w.sz, w.slot_i, staged_slot(j, w.cs, w.gbase, w.ncs), w.L, w.model, &xval)) continue;
+            const int slot_j = w.recipe ? w.recipe[j].x : staged_slot(j, w.cs, w.gbase, w.ncs);
+            if (!exact_in_range(w.sx, w.sy, w.sz, w.slot_i, slot_j, w.L, w.model, &xval)) continue;
             xover = true;
         }
         double2 pr = ljrow[0];
@@ -156,7 +158,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;
 
     // ---- phase A: staged-cell table; staged indices start at 1 ---------------------------------
-    stage_cell_table(a, bg, cs, gbase, ccoord, ctab);
+    stage_cell_table(a, bg, cs, gbase, ccoord, ctab, tid, (int)blockDim.x);
     for (int t = tid; t < a.ntypes * a.ntypes; t += BLOCK) ljt[t] = a.ljtab[t];
     if (tid == 0) {
         pxy[0] = make_double2(1e30, 1e30);
@@ -202,7 +204,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
     const int ngroups = (nh + 31) >> 5;
 
     // ---- phase B: stage atoms (same order as k_force_cells, shifted by the dummy at index 0) -------
-    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 1, min(scal[1], cap1), [&](int idx, int slot, double px, double py, double pzv) {
+    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 1, min(scal[1], cap1), tid, BLOCK, [&](int idx, int slot, int, double px, double py, double pzv) {
         pxy[idx] = make_double2(px, py);
         pz[idx] = pzv;
         const __half2 hxy = __floats2half2_rn((float)px, (float)py), hz0h = __floats2half2_rn((float)pzv, 0.0f);
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
 
         if (tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
             LaneRedo w;
-            w.pxy = pxy; w.pz = pz; w.ptyp = ptyp; w.ljt = ljt; w.cs = cs; w.gbase = gbase;
+            w.pxy = pxy; w.pz = pz; w.ptyp = ptyp; w.ljt = ljt; w.cs = cs; w.gbase = gbase; w.recipe = nullptr;
             w.ncs = ncs; w.ntypes = a.ntypes; w.me = me; w.slot_i = slot_i; w.nent = nent;
             w.entries = reinterpret_cast<const uint16_t *>(lp);
             w.sx = a.sx; w.sy = a.sy; w.sz = a.sz; w.L = a.L; w.model = a.model; w.fast = a.fast; w.rc2hi = a.rc2hi;

@@ -1,0 +1,315 @@
+// force_list_p.cuh -- persistent, warp-specialised form of the stepping kernel (k_force_list).
+//
+// ncu on k_force_list (profiles/): a third of all warp time went into staging a brick (three dependent global
+// round trips and two block barriers per block) during which the block's FP64 work stands still, and shared
+// memory allowed only two blocks per SM, so staging was overlapped by at most one other block.  Here one
+// 512-thread block per SM stays resident and walks over bricks (brick = blockIdx.x + k * gridDim.x):
+//   * 4 producer warps stage brick k+1 into one of two shared-memory buffers (cell table, prefix scan, atoms in
+//     the brick's frame in FP64 + FP16) while
+//   * 12 consumer warps walk the pair list of brick k (same walk / drain as k_force_list, ILP 4).
+// Hand-over by named barriers (bar.arrive / bar.sync): full[b] producers -> consumers, empty[b] consumers ->
+// producers; no block-wide barrier after the prologue.  A consumer warp that runs out of tasks in brick k moves
+// on to brick k+1 as soon as that buffer is full; the list head of its next task (also across bricks) is requested
+// one task ahead.
+#pragma once
+#include "force_list.cuh"
+
+#define FLP_THREADS 512
+#define FLP_NPROD 4
+#define FLP_NCONS (FLP_THREADS / 32 - FLP_NPROD)
+#define FLP_QS (FLP_NCONS * 32)          // row stride of the consumers' stacks
+
+__host__ __device__ inline size_t flp_buf_bytes(int cap, int ncs_max, int ntypes)
+{
+    const size_t cap1 = (size_t)cap + 1;
+    size_t b = cap1 * (sizeof(double2) + sizeof(double) + sizeof(uint2));
+    if (ntypes > 1) b += (cap1 + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    b += 8 * sizeof(int);                         // scal[]
+    return (b + 15) & ~(size_t)15;
+}
+__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes)
+{
+    return 2 * flp_buf_bytes(cap, ncs_max, ntypes) + (size_t)ntypes * ntypes * sizeof(double2) +
+           (size_t)(FL_QCAP + 1) * FLP_QS * sizeof(uint16_t);
+}
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct BrickBuf {
+    double2 *pxy;
+    double *pz;
+    uint2 *ph;
+    uint8_t *ptyp;
+    int *scal;            // [0] home atoms, [1] staged atoms + 1, [3] task cursor, [4] brick (-1: done)
+};
+__device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int ncs_max, bool multi)
+{
+    const size_t cap1 = (size_t)cap + 1;
+    BrickBuf b;
+    b.pxy = reinterpret_cast<double2 *>(base);
+    b.pz = reinterpret_cast<double *>(b.pxy + cap1);
+    b.ph = reinterpret_cast<uint2 *>(b.pz + cap1);
+    b.ptyp = reinterpret_cast<uint8_t *>(b.ph + cap1);
+    size_t off = (size_t)(reinterpret_cast<unsigned char *>(b.ptyp) - base);
+    if (multi) off += (cap1 + 15) & ~(size_t)15;
+    off = (off + 15) & ~(size_t)15;
+    b.scal = reinterpret_cast<int *>(base + off);
+    return b;
+}
+
+template <bool MULTI, bool COUNT>
+__global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks)
+{
+    constexpr int ILP = 4;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const GridDesc &g = a.g;
+    const int cap1 = a.cap + 1;
+    const size_t bufsz = flp_buf_bytes(a.cap, a.ncs_max, a.ntypes);
+    double2 *ljt = reinterpret_cast<double2 *>(smem_raw + 2 * bufsz);
+    uint16_t *qguard = reinterpret_cast<uint16_t *>(ljt + a.ntypes * a.ntypes);
+    uint16_t *queue = qguard + FLP_QS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int t = tid; t < a.ntypes * a.ntypes; t += FLP_THREADS) ljt[t] = a.ljtab[t];
+    if (tid < FLP_QS) qguard[tid] = 0;
+    __syncthreads();
+
+    if (warp < FLP_NPROD) {
+        // ================================ producers ================================
+        constexpr int PN = FLP_NPROD * 32;
+        const int R = g.R;
+        int hdr_n1 = 0, hdr_nh = 0;
+        if ((int)blockIdx.x < nbricks) {
+            hdr_n1 = a.brickhdr[2 * (blockIdx.x + a.block_first)];
+            hdr_nh = a.brickhdr[2 * (blockIdx.x + a.block_first) + 1];
+        }
+        for (int k = 0;; k++) {
+            const int b = k & 1;
+            const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
+            const int brick = blockIdx.x + k * gridDim.x;
+            if (k >= 2) bar_sync(3 + b, FLP_THREADS);                 // empty[b]: the consumers are done with this buffer
+            if (brick >= nbricks) {
+                if (tid == 0) B.scal[4] = -1;
+                __threadfence_block();
+                bar_arrive(1 + b, FLP_THREADS);
+                break;
+            }
+            const int bid = brick + a.block_first;
+            const BrickGeom bg = brick_geom(g, bid);
+            // the recipe written by k_list_build at the last re-binning: slot and staged-cell coordinates of every staged
+            // atom, so staging is one coalesced load, three gathers and ~30 instructions per atom, with no table or scan
+            const int2 *recipe = a.recipe + (size_t)bid * a.rcap;
+            const int n1 = min(hdr_n1, cap1);                         // staged atoms + 1
+            const int nh = hdr_nh;
+            {   // one brick ahead: header into registers, recipe into L2 (it streams from HBM; the coordinates it points
+                // at were written by k_vv just before this kernel and are L2 hits)
+                const int nb = brick + gridDim.x;
+                if (nb < nbricks) {
+                    const int nbid = nb + a.block_first;
+                    hdr_n1 = a.brickhdr[2 * nbid];
+                    hdr_nh = a.brickhdr[2 * nbid + 1];
+                    const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
+                    for (int t = tid * 128; t < a.rcap * 8; t += PN * 128) prefetch_l2(nr + t);
+                }
+            }
+            if (tid == 0) {
+                B.pxy[0] = make_double2(1e30, 1e30);
+                B.pz[0] = 1e30;
+                const __half2 far = __floats2half2_rn(60000.0f, 60000.0f), farz = __floats2half2_rn(60000.0f, 0.0f);
+                B.ph[0] = make_uint2(*reinterpret_cast<const unsigned *>(&far), *reinterpret_cast<const unsigned *>(&farz));
+                if (MULTI) B.ptyp[0] = 0;
+                B.scal[0] = nh;
+                B.scal[1] = n1;
+                B.scal[3] = 0;              // task cursor
+                B.scal[4] = brick;
+            }
+            {   // the consumers claim this brick's tasks dynamically: bring every group's entry counts and first chunks into L2
+                const int ng = min((nh + 31) >> 5, a.gmax);
+                for (int t = tid; t < ng * 8; t += PN) {      // 2 chunks x 512 B = 8 lines of 128 B per group
+                    const size_t gs = (size_t)bid * a.gmax + (t >> 3);
+                    const int part = t & 7;
+                    if (part == 0) prefetch_l2(a.list_n + gs * 32);
+                    prefetch_l2(reinterpret_cast<const unsigned char *>(a.list8 + gs * a.lcap8 * 32) + part * 128);
+                }
+            }
+            const double invM = 1.0 / g.M;
+            const int ux0 = bg.hx0 - R, uy0 = bg.hy0 - R, uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0) - R;
+            const double bcx = ((double)bg.hx0 + 0.5 * bg.nhx) * invM, bcy = ((double)bg.hy0 + 0.5 * bg.nhy) * invM,
+                         bcz = ((double)(uz0 + R) + 0.5 * bg.nhz) * invM;
+            constexpr int U = 6;
+            for (int i0 = 1 + tid; i0 < n1; i0 += U * PN) {
+                int2 rc[U];
+                double sx[U], sy[U], sz[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * PN;
+                    rc[u] = i < n1 ? recipe[i] : make_int2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x];
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * PN;
+                    if (i >= n1) continue;
+                    const int cc = rc[u].y;
+                    const double cx = ((double)(ux0 + (cc & 255)) + 0.5) * invM, cy = ((double)(uy0 + ((cc >> 8) & 255)) + 0.5) * invM,
+                                 cz = ((double)(uz0 + (cc >> 16)) + 0.5) * invM;
+                    double dx = sx[u] - cx, dy = sy[u] - cy, dz = sz[u] - cz;
+                    dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);      // image nearest to the staged cell
+                    const double px = a.L * (dx + (cx - bcx)), py = a.L * (dy + (cy - bcy)), pzv = a.L * (dz + (cz - bcz));
+                    B.pxy[i] = make_double2(px, py);
+                    B.pz[i] = pzv;
+                    const __half2 hxy = __floats2half2_rn((float)px, (float)py), hz0h = __floats2half2_rn((float)pzv, 0.0f);
+                    B.ph[i] = make_uint2(*reinterpret_cast<const unsigned *>(&hxy), *reinterpret_cast<const unsigned *>(&hz0h));
+                    if (MULTI) B.ptyp[i] = (uint8_t)a.type[rc[u].x];
+                }
+            }
+            __threadfence_block();
+            bar_arrive(1 + b, FLP_THREADS);                           // full[b]
+        }
+        return;
+    }
+
+    // ================================ consumers ================================
+    const int ctid = tid - FLP_NPROD * 32;
+    const __half thr = __float2half_ru(a.rc2h);
+    const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+    unsigned long long npair = 0;
+    double sig2_0 = 0, tt_0 = 0;
+    if (!MULTI) { const double2 pr = ljt[0]; sig2_0 = pr.x; tt_0 = pr.y; }
+    int pre_n = 0;
+    uint4 pre0 = zero4, pre1 = zero4;
+    // entry count and first two chunks of (brick, group) into registers, the following chunks into L2
+    auto request = [&](int bid_, int grp_) {
+        const size_t gs = (size_t)bid_ * a.gmax + grp_;
+        pre_n = a.list_n[gs * 32 + lane];
+        pre0 = a.list8[gs * a.lcap8 * 32 + lane];
+        pre1 = a.list8[(gs * a.lcap8 + 1) * 32 + lane];
+#pragma unroll
+        for (int k = 2; k < 2 + FL_AHEAD; k++) prefetch_l2(a.list8 + (gs * a.lcap8 + k) * 32 + lane);
+    };
+
+    for (int k = 0;; k++) {
+        const int b = k & 1;
+        const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
+        bar_sync(1 + b, FLP_THREADS);                                 // full[b]
+        const int brick = B.scal[4];
+        if (brick < 0) break;
+        const int bid = brick + a.block_first;
+        const double2 *pxy = B.pxy;
+        const double *pz = B.pz;
+        const uint2 *ph = B.ph;
+        const uint8_t *ptyp = B.ptyp;
+        const int2 *recipe = a.recipe + (size_t)bid * a.rcap;
+        const int nh = B.scal[0];
+        const int ngroups = (nh + 31) >> 5;
+        if (ngroups > a.gmax) atomicCAS(a.err, 0, 5);
+        const int ntask = min(ngroups, a.gmax);
+        // tasks are claimed from the buffer's cursor; the first claim of a brick finds the list head in L2 (the producers
+        // prefetched it), later ones are requested one task ahead
+        int grp = 0;
+        if (lane == 0) grp = atomicAdd(&B.scal[3], 1);
+        grp = __shfl_sync(0xffffffffu, grp, 0);
+        if (grp < ntask) request(bid, grp);
+
+        while (grp < ntask) {
+            const int h = (grp << 5) + lane;
+            const bool active = h < nh;
+            const int hh = active ? h : (grp << 5);
+            const int me = a.homeidx[((size_t)bid * a.gmax + grp) * 32 + (hh & 31)];
+            const int slot_i = recipe[me].x;
+            const double2 q0 = pxy[me];
+            const double pix = q0.x, piy = q0.y, piz = pz[me];
+            const uint2 hme = ph[me];
+            const __half2 ixy = *reinterpret_cast<const __half2 *>(&hme.x), izw = *reinterpret_cast<const __half2 *>(&hme.y);
+            const double2 *ljrow = ljt;
+            if (MULTI) ljrow = ljt + (int)ptyp[me] * a.ntypes;
+            double fx = 0, fy = 0, fz = 0;
+
+            const int nent = pre_n;
+            const int nch = (nent + 7) >> 3;
+            const int nchmax = __reduce_max_sync(0xffffffffu, nch);
+            const uint4 *lp = a.list8 + ((size_t)bid * a.gmax + grp) * a.lcap8 * 32 + lane;
+            uint4 e0 = 0 < nch ? pre0 : zero4;
+            uint4 e1 = 1 < nch ? pre1 : zero4;
+            // claim the next task (in this brick, else this warp's first task of the next brick) and request its head
+            int ngrp = 0;
+            if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
+            ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
+            if (ngrp < ntask) request(bid, ngrp);
+
+            int cnt = 0;
+            uint16_t *qp = queue + ctid;
+            unsigned tmin = 0xffffffffu;
+            unsigned long long np = 0;
+
+            auto pair_eval = [&](int idx) {
+                const int j = queue[max(idx, -1) * FLP_QS + ctid];
+                const double2 j0 = pxy[j];
+                const double jz = pz[j];
+                const double vx = pix - j0.x, vy = piy - j0.y, vz = piz - jz;
+                const double r2 = fma(vz, vz, fma(vy, vy, vx * vx));
+                const int t = __double2hiint(r2) - (a.rc2hi - 1);     // pair_in_range: t < 0 inside, t <= 2 borderline
+                tmin = min(tmin, (unsigned)t);
+                double sig2 = sig2_0, tt = tt_0;
+                if (MULTI) { const double2 pr = ljrow[ptyp[j]]; sig2 = pr.x; tt = pr.y; }
+                double Eg, Wg;
+                double qf = lj_pair_q<false>(r2, sig2, tt, a.fast, false, 0.0, Eg, Wg);
+                qf = t < 0 ? qf : 0.0;
+                fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+                if (COUNT) np += t < 0 ? 1 : 0;
+            };
+            auto drain = [&](int depth) {
+                for (int kk = 0; kk < depth; kk += ILP) {
+#pragma unroll
+                    for (int u = 1; u <= ILP; u++) pair_eval(cnt - u - kk);
+                }
+                cnt = max(cnt - depth, 0);
+                qp = queue + cnt * FLP_QS + ctid;
+            };
+            auto test = [&](unsigned j, uint2 hj) {
+                const __half2 dxy = __hsub2(*reinterpret_cast<const __half2 *>(&hj.x), ixy);
+                const __half2 dzw = __hsub2(*reinterpret_cast<const __half2 *>(&hj.y), izw);
+                const __half2 s = __hfma2(dzw, dzw, __hmul2(dxy, dxy));
+                if (__hle(__hadd(__low2half(s), __high2half(s)), thr)) { *qp = (uint16_t)j; qp += FLP_QS; cnt++; }
+            };
+
+            for (int c = 0; c < nchmax; c++) {
+                const uint4 e2 = c + 2 < nch ? lp[(size_t)(c + 2) * 32] : zero4;
+                if (c + 2 + FL_AHEAD < nch) prefetch_l2(lp + (size_t)(c + 2 + FL_AHEAD) * 32);
+                const unsigned j0 = e0.x & 0xffffu, j1 = e0.x >> 16, j2 = e0.y & 0xffffu, j3 = e0.y >> 16;
+                const unsigned j4 = e0.z & 0xffffu, j5 = e0.z >> 16, j6 = e0.w & 0xffffu, j7 = e0.w >> 16;
+                const uint2 h0 = ph[j0], h1 = ph[j1], h2 = ph[j2], h3 = ph[j3], h4 = ph[j4], h5 = ph[j5], h6 = ph[j6], h7 = ph[j7];
+                test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
+                test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
+                e0 = e1; e1 = e2;
+                const int over = __reduce_max_sync(0xffffffffu, cnt) - (FL_QCAP - 8);
+                if (over > 0) drain((max(over, FL_MINPOP) + ILP - 1) & ~(ILP - 1));
+            }
+            drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
+
+            if (tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
+                LaneRedo w;
+                w.pxy = pxy; w.pz = pz; w.ptyp = ptyp; w.ljt = ljt; w.cs = nullptr; w.gbase = nullptr; w.recipe = recipe;
+                w.ncs = 0; w.ntypes = a.ntypes; w.me = me; w.slot_i = slot_i; w.nent = nent;
+                w.entries = reinterpret_cast<const uint16_t *>(lp);
+                w.sx = a.sx; w.sy = a.sy; w.sz = a.sz; w.L = a.L; w.model = a.model; w.fast = a.fast; w.rc2hi = a.rc2hi;
+                double f3[3];
+                careful_lane<MULTI>(w, f3, &np);
+                fx = f3[0]; fy = f3[1]; fz = f3[2];
+            }
+            if (COUNT) npair += np;
+            if (active) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
+            grp = ngrp;
+        }
+        bar_arrive(3 + b, FLP_THREADS);                               // empty[b]
+    }
+    if (COUNT) {
+        for (int o = 16; o > 0; o >>= 1) npair += __shfl_xor_sync(0xffffffffu, npair, o);
+        if (lane == 0 && npair) atomicAdd(a.digest, npair);
+    }
+}

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
     const int nhx = bg.nhx, nhy = bg.nhy, nhz = bg.nhz;
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;
 
-    stage_cell_table(a, bg, cs, gbase, ccoord, ctab);
+    stage_cell_table(a, bg, cs, gbase, ccoord, ctab, tid, (int)blockDim.x);
     {   // records past the last staged atom are read by the unrolled scan: make them far away
         const __half2 far = __floats2half2_rn(60000.0f, 60000.0f);
         const unsigned fu = *reinterpret_cast<const unsigned *>(&far);
@@ -113,13 +113,26 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
     const int ntasks = scal[2];
 
     __half *hph = reinterpret_cast<__half *>(hp);
-    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, [&](int idx, int slot, double px, double py, double pz) {
+    int2 *recipe = a.recipe + (size_t)bid * a.rcap;
+    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, tid, (int)blockDim.x, [&](int idx, int slot, int ccode, double px, double py, double pz) {
         __half *rec = hph + (idx >> 1) * 8 + (idx & 1);
         rec[0] = __float2half_rn((float)px);
         rec[2] = __float2half_rn((float)py);
         rec[4] = __float2half_rn((float)pz);
         if (EXCL) pid[idx] = a.id[slot];
+        // the staging recipe of this brick: slot and staged-cell coordinates of every staged atom
+        if (idx + 1 < a.rcap) recipe[idx + 1] = make_int2(slot, ccode);
     });
+    {   // header and home list (home atom h -> staged index + 1)
+        const int nh = hstart[nhy * nhz];
+        if (tid == 0) { a.brickhdr[2 * bid] = nstaged + 1; a.brickhdr[2 * bid + 1] = nh; }
+        for (int h = tid; h < nh && (h >> 5) < a.gmax; h += blockDim.x) {
+            int hr = 0;
+            while (hstart[hr + 1] <= h) hr++;
+            const int hrow = (hr / nhy + R) * syn + (hr % nhy + R);
+            a.homeidx[((size_t)bid * a.gmax + (h >> 5)) * 32 + (h & 31)] = (uint16_t)(cs[hrow * sxn + R] + (h - hstart[hr]) + 1);
+        }
+    }
     __syncthreads();
 
     const __half thr1 = __float2half_ru(a.rl2h);
@@ -162,68 +175,84 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
         const size_t gs = (size_t)bid * a.gmax + (h >> 5);
         uint4 *lp = a.list8 + gs * a.lcap8 * 32 + (h & 31);
         int nchunks = 0;                    // chunks already in global memory
-        uint16_t *wp = reinterpret_cast<uint16_t *>(myrow);   // next free entry of the row
+        // the lane's row is addressed by its 32-bit shared-memory address: a push is one st.shared.u16 and one add.
+        // The compiler does not see these stores as memory accesses, which lets it batch the candidate loads of an
+        // unrolled block; the flush (the only reader of the row) is fenced explicitly.
+        const unsigned row_sh = (unsigned)__cvta_generic_to_shared(myrow);
+        unsigned wsh = row_sh;              // next free entry
 
         // entries in the row -> global chunks; keep = false also writes the last partial chunk (unused entries = dummy)
         auto flush = [&](bool keep) {
-            const int n = (int)(wp - reinterpret_cast<uint16_t *>(myrow));
+            asm volatile("" ::: "memory");
+            __syncwarp();
+            const int n = (int)(wsh - row_sh) >> 1;
             const int nfull = n >> 3, rem = n & 7;
             const int nout = keep ? nfull : nfull + (rem ? 1 : 0);
             const int nmax = __reduce_max_sync(0xffffffffu, nout);
             for (int c = 0; c < nmax; c++) {
                 if (c < nout) {
                     uint4 v = *reinterpret_cast<const uint4 *>(myrow + c * 16);
-                    unsigned e[4] = {v.x, v.y, v.z, v.w};
-                    const int valid = c < nfull ? 8 : rem;       // entries of this chunk that are real
+                    if (EXCL || c >= nfull) {
+                        unsigned e[4] = {v.x, v.y, v.z, v.w};
+                        const int valid = c < nfull ? 8 : rem;       // entries of this chunk that are real
 #pragma unroll
-                    for (int k = 0; k < 8; k++) {
-                        unsigned ent = (e[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
-                        bool drop = k >= valid;
-                        if (EXCL && !drop) drop = pair_excluded(xb, xm, pid[ent - 1]);
-                        if (drop) e[k >> 1] &= (k & 1) ? 0x0000ffffu : 0xffff0000u;
+                        for (int k = 0; k < 8; k++) {
+                            const unsigned ent = (e[k >> 1] >> ((k & 1) * 16)) & 0xffffu;
+                            bool drop = k >= valid;
+                            if (EXCL && !drop) drop = pair_excluded(xb, xm, pid[ent - 1]);
+                            if (drop) e[k >> 1] &= (k & 1) ? 0x0000ffffu : 0xffff0000u;
+                        }
+                        v = make_uint4(e[0], e[1], e[2], e[3]);
                     }
-                    if (nchunks + c < a.lcap8) lp[(size_t)(nchunks + c) * 32] = make_uint4(e[0], e[1], e[2], e[3]);
+                    if (nchunks + c < a.lcap8) lp[(size_t)(nchunks + c) * 32] = v;
                     else atomicCAS(a.err, 0, 5);
                 }
             }
             if (keep) {
                 if (rem && nfull) *reinterpret_cast<uint4 *>(myrow) = *reinterpret_cast<const uint4 *>(myrow + nfull * 16);
-                wp = reinterpret_cast<uint16_t *>(myrow) + rem;
+                wsh = row_sh + 2 * rem;
             }
             nchunks += nout;
+            __syncwarp();
+            asm volatile("" ::: "memory");
         };
-
+        auto push = [&](bool take, unsigned value) {
+            asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }" ::"r"(wsh), "h"((unsigned short)value), "r"((unsigned)take));
+            wsh += take ? 2u : 0u;
+        };
         // two candidates (staged indices 2q, 2q+1) against this lane's atom; SELF: the row holds this lane's own atom
-        auto test2 = [&](int q, __half2 th, auto SELF) {
-            const uint4 c = hp[q];
+        auto test2 = [&](uint4 c, int q, __half2 th, auto SELF) {
             const __half2 dx = __hsub2(*reinterpret_cast<const __half2 *>(&c.x), ix);
             const __half2 dy = __hsub2(*reinterpret_cast<const __half2 *>(&c.y), iy);
             const __half2 dz = __hsub2(*reinterpret_cast<const __half2 *>(&c.z), iz);
             const __half2 r2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
             bool lo = __hle(__low2half(r2), __low2half(th)), hi = __hle(__high2half(r2), __high2half(th));
             if (decltype(SELF)::value) { lo = lo && (2 * q != me); hi = hi && (2 * q + 1 != me); }
-            if (lo) { *wp = (uint16_t)(2 * q + 1); wp++; }
-            if (hi) { *wp = (uint16_t)(2 * q + 2); wp++; }
+            push(lo, 2 * q + 1);
+            push(hi, 2 * q + 2);
         };
-        auto row_full = [&]() { return __any_sync(0xffffffffu, (int)(wp - reinterpret_cast<uint16_t *>(myrow)) >= LB_FLUSH_AT); };
+        auto row_full = [&]() { return __any_sync(0xffffffffu, (int)(wsh - row_sh) >= 2 * LB_FLUSH_AT); };
         // one window row [p0, p1): the first and the last record may hold a candidate of a neighbouring window
         auto scan_row = [&](int p0, int p1, auto SELF) {
             int q = p0 >> 1;
             const int qlast = (p1 - 1) >> 1;
             if (q == qlast) {
                 const bool lo_ok = 2 * q >= p0, hi_ok = 2 * q + 1 < p1;
-                test2(q, lo_ok ? (hi_ok ? thr : thr_hi_off) : thr_lo_off, SELF);
+                test2(hp[q], q, lo_ok ? (hi_ok ? thr : thr_hi_off) : thr_lo_off, SELF);
                 return;
             }
-            test2(q, (p0 & 1) ? thr_lo_off : thr, SELF);
+            test2(hp[q], q, (p0 & 1) ? thr_lo_off : thr, SELF);
             q++;
             for (; q + 8 <= qlast; q += 8) {              // interior records, 16 candidates per iteration
+                uint4 c[8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) test2(q + u, thr, SELF);
+                for (int u = 0; u < 8; u++) c[u] = hp[q + u];     // broadcast loads, issued together
+#pragma unroll
+                for (int u = 0; u < 8; u++) test2(c[u], q + u, thr, SELF);
                 if (row_full()) flush(true);
             }
-            for (; q < qlast; q++) test2(q, thr, SELF);
-            test2(qlast, (p1 & 1) ? thr_hi_off : thr, SELF);
+            for (; q < qlast; q++) test2(hp[q], q, thr, SELF);
+            test2(hp[qlast], qlast, (p1 & 1) ? thr_hi_off : thr, SELF);
         };
 
         for (int rw = 0; rw < nwin * nwin; rw++) {
@@ -237,7 +266,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
             if (row_full()) flush(true);
         }
         {
-            const int n = nchunks * 8 + (int)(wp - reinterpret_cast<uint16_t *>(myrow));
+            const int n = nchunks * 8 + ((int)(wsh - row_sh) >> 1);
             flush(false);
             if (active) a.list_n[gs * 32 + (h & 31)] = (uint16_t)min(n, a.lcap8 * 8);
         }

@@ -132,6 +132,9 @@ int emdee_timer_stop(emdee_ctx *ctx, double *ms);
  * duration and the number of launches (roofline.achieved in bench.py). */
 int emdee_profile_begin(emdee_system *sys);
 int emdee_profile_end(emdee_system *sys, double *force_kernel_ms, int64_t *force_kernel_launches);
+/* The same split by kernel (valid after emdee_profile_end): kind 0 = k_force_cells (window scan, single-point
+ * evaluations), 1 = k_list_build (pair-list build on a re-binning step), 2 = k_force_list(_p) (the stepping kernel). */
+int emdee_profile_kind(emdee_system *sys, int kind, double *ms, int64_t *launches);
 
 /* Slab decomposition info (valid after emdee_bin): atoms owned by this rank and their ids */
 int emdee_get_local_count(emdee_system *sys, int64_t *nlocal, int64_t *nghost);
