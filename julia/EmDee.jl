@@ -136,6 +136,13 @@ function pair_set_digest(s::NonbondedSystem)
     return d
 end
 
+# pairs (i<j) the pair-list stepping kernel evaluates inside the cutoff at the current positions (-1: no list in use)
+function list_pair_count(s::NonbondedSystem)
+    n = Ref{Int64}(0)
+    check(ccall((:emdee_list_pair_count, libemdee), Cint, (Ptr{Cvoid}, Ref{Int64}), s.handle, n))
+    return n[]
+end
+
 # velocity-Verlet (additive; the reference has no integrator)
 step!(s::NonbondedSystem, nsteps::Integer; dt::Real=0.005, rebin_every::Integer=1) =
     check(ccall((:emdee_vv_step, libemdee), Cint, (Ptr{Cvoid}, Cdouble, Int64, Cint), s.handle, dt, nsteps, rebin_every))
