@@ -139,6 +139,7 @@ struct emdee_system {
     int fl_block = 192;                       // block size of k_force_list
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
+    int fl_nbuf = 2, want_nbuf = 3;                       // three when they fit
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
@@ -400,6 +401,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_LIST_CHUNKS")) s->lcap8 = std::max(4, atoi(e));
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_NBUF")) s->want_nbuf = atoi(e) >= 3 ? 3 : 2;
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -725,6 +727,12 @@ static bool list_capable(const emdee_system *s)
     // the pair-list kernels read LJ parameters from the class table and index staged atoms with 16 bits
     return s->grid_ok && s->use_list && s->skin > 0 && s->ntypes > 0;
 }
+// A single-point evaluation can use the list kernels at any skin (the list is built at the positions it is used at);
+// energies and virials exist only in the persistent kernel.
+static bool single_point_list(const emdee_system *s)
+{
+    return s->grid_ok && s->use_list && s->ntypes > 0 && s->fl_persistent;
+}
 static int choose_bricks(emdee_system *s)
 {
     emdee_ctx *c = s->ctx;
@@ -760,7 +768,8 @@ static int choose_bricks(emdee_system *s)
         s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
         s->fl_block = lblock;
         s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
-        s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1)) <= c->smem_optin;
+        s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin;
+        s->fl_nbuf = s->want_nbuf == 3 && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 3) <= c->smem_optin ? 3 : 2;
         s->fc_typed = typed;
         s->fc_nblocks = g.nbx * g.nby * g.nbz;
         const int64_t nwarps = (int64_t)s->fc_nblocks * (block / 32);
@@ -807,7 +816,7 @@ static int choose_bricks(emdee_system *s)
             // the stepping kernel decides, as long as k_force_cells (single-point evaluations) fits too
             const int cblock = cells_block(cap, ncs, forced_block);
             if (!cblock) continue;
-            if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1)) <= c->smem_optin) {
+            if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin) {
                 // persistent kernel (two staging buffers): the largest brick that fits, and among equal volumes the
                 // one that stages the fewest cells (least halo per home atom)
                 const double score = 1e6 + 1000.0 * (g.bx * g.by * g.bz) - ncs;
@@ -1183,18 +1192,25 @@ static int launch_list_i(emdee_system *s, const CellArgs &a, int nblocks)
     s->ctx->launches++;
     return check_launch("k_force_list");
 }
+template <bool MULTI, bool COUNT, bool EW>
+static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
+{
+    auto kern = k_force_list_p<MULTI, COUNT, 2, EW>;
+    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<std::min(nblocks, s->ctx->sm_count), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks, store_f ? 1 : 0);
+    s->ctx->launches++;
+    return check_launch("k_force_list_p");
+}
 template <bool MULTI, bool COUNT>
-static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks)
+static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks, bool F, bool EW)
 {
     if (nblocks <= 0) return EMDEE_OK;
     if (s->fl_persistent) {     // one resident block per SM walks over the bricks (force_list_p.cuh)
-        auto kern = k_force_list_p<MULTI, COUNT>;
-        const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1));
-        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<std::min(nblocks, s->ctx->sm_count), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks);
-        s->ctx->launches++;
-        return check_launch("k_force_list_p");
+        if (EW && !COUNT) return launch_list_p<MULTI, false, true>(s, a, nblocks, F);
+        return launch_list_p<MULTI, COUNT, false>(s, a, nblocks, true);
     }
+    if (EW) EMDEE_FAIL(EMDEE_ERR_STATE, "launch_list: energies and virials need the persistent list kernel");
     // blocks of up to 192 threads run the 8-chain variant (more registers per thread), larger ones the 4-chain variant
     return s->fl_block <= 192 && s->fl_ilp8 ? launch_list_i<MULTI, COUNT, 8>(s, a, nblocks) : launch_list_i<MULTI, COUNT, 4>(s, a, nblocks);
 }
@@ -1216,8 +1232,8 @@ static int launch_cells_ty(emdee_system *s, const CellArgs &a, int nb, bool F, b
 static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool EW, bool EXCL, bool AUDIT, int mode)
 {
     if (mode == 1) return EXCL ? launch_build_t<true>(s, a, nb) : launch_build_t<false>(s, a, nb);
-    if (mode == 2) return s->ntypes > 1 ? launch_list_t<true, false>(s, a, nb) : launch_list_t<false, false>(s, a, nb);
-    if (mode == 3) return s->ntypes > 1 ? launch_list_t<true, true>(s, a, nb) : launch_list_t<false, true>(s, a, nb);
+    if (mode == 2) return s->ntypes > 1 ? launch_list_t<true, false>(s, a, nb, F, EW) : launch_list_t<false, false>(s, a, nb, F, EW);
+    if (mode == 3) return s->ntypes > 1 ? launch_list_t<true, true>(s, a, nb, true, false) : launch_list_t<false, true>(s, a, nb, true, false);
     return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT);
 }
 
@@ -1237,7 +1253,6 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     a.ljtab = s->ljtab; a.ntypes = s->ntypes;
     a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2];
     a.en = s->en; a.vir = s->vir;
-    a.partial = s->partial;
     a.digest = s->digest;
     a.pairs = pairs;
     a.pair_cap = pair_cap;
@@ -1283,8 +1298,8 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         a.rl2h = thr16(s->cutoff + s->skin);
     }
     if (mode != 0) {
-        if (bitmask != EMDEE_FORCES || audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list modes evaluate forces only");
-        if (!list_capable(s)) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: pair list requested for a system that cannot use one");
+        if (audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list kernels do not audit");
+        if (!(s->grid_ok && s->use_list && s->ntypes > 0)) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: pair list requested for a system that cannot use one");
         const int64_t slots = (int64_t)s->fc_nblocks * s->fc_gmax;
         if (slots > s->list_slots) {
             dev_free(s->list8); dev_free(s->list_n); dev_free(s->homeidx);
@@ -1311,7 +1326,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         if (mode == 1) CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
     }
     const bool F = (bitmask & EMDEE_FORCES) != 0;
-    const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0 || !F;
+    const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0;
     if (audit) CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (s->profiling && s->prof_used + 2 <= 16384) {
@@ -1343,13 +1358,14 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
         a.block_first = ranges[k][0];
         EMDEE_TRY(launch_cells(s, a, ranges[k][1], F, EW, s->has_excl, audit, mode));
+        if (getenv("EMDEE_DEBUG_SYNC")) {
+            fprintf(stderr, "[emdee] force launch mode %d range %d (%d blocks) issued\n", mode, k, ranges[k][1]);
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            fprintf(stderr, "[emdee] force launch mode %d range %d done\n", mode, k);
+        }
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
-    if (EW || audit) {
-        k_reduce_partials<<<1, 256, 0, c->stream>>>(s->fc_nblocks * (s->fc_block / 32), s->partial, s->totals);
-        c->launches++;
-    }
-    return check_launch("k_reduce_partials");
+    return EMDEE_OK;
 }
 
 template <bool CULL, bool EXCL>
@@ -1419,9 +1435,18 @@ extern "C" int emdee_compute_nonbonded(emdee_system *s, int mode, int bitmask)
         EMDEE_TRY(run_tiles(s, bitmask, false));
     } else if (mode == EMDEE_CUTOFF) {
         if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: EMDEE_CUTOFF needs emdee_bin after the last emdee_set_positions");
-        if (s->grid_ok)
-            EMDEE_TRY(run_cells(s, bitmask, false, nullptr, 0));
-        else {
+        if (s->grid_ok) {
+            if (single_point_list(s)) {
+                // list kernels: build at the current binning if there is no valid list (k_list_build), then one walk
+                // (k_force_list_p); a later evaluation within the skin re-uses the list
+                if (!s->list_valid) {
+                    EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1));
+                    s->list_valid = true;
+                }
+                EMDEE_TRY(run_cells(s, bitmask, false, nullptr, 0, false, 2));
+            } else
+                EMDEE_TRY(run_cells(s, bitmask, false, nullptr, 0));
+        } else {
             if (!s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: box too small for a cell grid and a custom tile list is set");
             EMDEE_TRY(run_tiles(s, bitmask, true));
         }
@@ -1656,8 +1681,10 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                     s->list_valid = true;
                 }
                 EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, 2));   // a re-bin already refreshed the ghosts
-            } else
+            } else {
                 EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, !rebin, 0));
+                s->list_valid = false;      // a list built for a single-point evaluation does not survive a drift without skin
+            }
         }
         else
             EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));

@@ -52,7 +52,6 @@ struct CellArgs {
     const double2 *ljtab;             // ntypes^2 entries {(half_sigma_a + half_sigma_b)^2, twice_sqrt_eps_a * twice_sqrt_eps_b}
     int ntypes;                       // 0: more than FC_MAX_TYPES classes, per-atom parameters are gathered from global
     double *fx, *fy, *fz, *en, *vir;
-    double *partial;                  // per warp: {sum e_i, sum w_i}
     unsigned long long *digest;       // AUDIT: {count, sum hash, xor hash}
     int32_t *pairs;                   // AUDIT: optional pair list (2 x pair_cap)
     long long pair_cap;
@@ -253,7 +252,6 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         smem_raw + ((reinterpret_cast<unsigned char *>(scal + 8) - smem_raw + 15) & ~(size_t)15));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int NW = BLOCK / 32;
     const int R = g.R;
 
     // ---- brick geometry ---------------------------------------------------------------------
@@ -325,7 +323,6 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const double L = a.L;
     const float scan2f = a.rc2f;                          // what the window scan accepts
     const int nwin = 2 * R + 1;
-    double esum = 0, wsum = 0;
     unsigned long long npair = 0, hsum = 0, hxor = 0;
 
     for (;;) {
@@ -455,16 +452,10 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
             if (EW) {
                 e *= 0.5; w *= 0.5;                         // src/nonbonded.jl:93-94
                 a.en[slot_i] = e; a.vir[slot_i] = w;
-                esum += e; wsum += w;
             }
         }
     }
 
-    // ---- per-warp totals (summed later in a fixed order: deterministic) ---------------------------
-    if (EW) {
-        esum = warp_sum_f64(esum); wsum = warp_sum_f64(wsum);
-        if (lane == 0) { a.partial[2 * (bid * NW + warp)] = esum; a.partial[2 * (bid * NW + warp) + 1] = wsum; }
-    }
     if (AUDIT) {
         for (int o = 16; o > 0; o >>= 1) {
             npair += __shfl_xor_sync(0xffffffffu, npair, o);
@@ -473,19 +464,4 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
         }
         if (lane == 0 && npair) { atomicAdd(a.digest, npair); atomicAdd(a.digest + 1, hsum); atomicXor(a.digest + 2, hxor); }
     }
-}
-
-// Sum the per-warp partials in index order: deterministic totals.
-__global__ void k_reduce_partials(int n, const double *__restrict__ partial, double *__restrict__ totals)
-{
-    __shared__ double sE[256], sW[256];
-    double E = 0, W = 0;
-    for (int b = threadIdx.x; b < n; b += 256) { E += partial[2 * b]; W += partial[2 * b + 1]; }
-    sE[threadIdx.x] = E; sW[threadIdx.x] = W;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) { sE[threadIdx.x] += sE[threadIdx.x + o]; sW[threadIdx.x] += sW[threadIdx.x + o]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { totals[0] = sE[0]; totals[1] = sW[0]; }
 }

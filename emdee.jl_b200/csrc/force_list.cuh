@@ -67,18 +67,18 @@ struct LaneRedo {
 // is within 3*2^-20 of rc2 as outside, only remembering that it met one.  A lane that met one (about one lane
 // in a hundred warp tasks for a fluid; every lane for a lattice with a shell exactly at rc) discards its result
 // and re-evaluates its list here, taking the oracle's exact decision (and the oracle's clamped x) for those pairs.
-template <bool MULTI>
+template <bool MULTI, bool EW = false>
 __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned long long *npair)
 {
     const double2 q0 = w.pxy[w.me];
     const double pix = q0.x, piy = q0.y, piz = w.pz[w.me];
-    double fx = 0, fy = 0, fz = 0;
+    double fx = 0, fy = 0, fz = 0, e = 0, vw = 0;
     unsigned long long n = 0;
     const double2 *ljrow = w.ljt;
     if (MULTI) ljrow = w.ljt + (int)w.ptyp[w.me] * w.ntypes;
     const int nslots = ((w.nent + 7) >> 3) << 3;       // the last chunk is padded with zeros in any position
-    for (int e = 0; e < nslots; e++) {
-        const int j = w.entries[((e >> 3) << 8) + (e & 7)];
+    for (int k = 0; k < nslots; k++) {
+        const int j = w.entries[((k >> 3) << 8) + (k & 7)];
         if (j == 0) continue;
         const double2 j0 = w.pxy[j];
         const double vx = pix - j0.x, vy = piy - j0.y, vz = piz - w.pz[j];
@@ -94,12 +94,14 @@ __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned
         }
         double2 pr = ljrow[0];
         if (MULTI) pr = ljrow[w.ptyp[j]];
-        double Eg, Wg;
-        const double qf = lj_pair_q<false>(r2, pr.x, pr.y, w.fast, xover, xval, Eg, Wg);
+        double Eg = 0, Wg = 0;
+        const double qf = lj_pair_q<EW>(r2, pr.x, pr.y, w.fast, xover, xval, Eg, Wg);
         fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+        if (EW) { e += Eg; vw += Wg; }
         n++;
     }
     f[0] = fx; f[1] = fy; f[2] = fz;
+    if (EW) { f[3] = e; f[4] = vw; }
     *npair = n;
 }
 

@@ -28,10 +28,13 @@ __host__ __device__ inline size_t flp_buf_bytes(int cap, int ncs_max, int ntypes
     b += 8 * sizeof(int);                         // scal[]
     return (b + 15) & ~(size_t)15;
 }
-__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes)
+// nbuf staging buffers; the per-lane stacks shrink to 24 entries when three buffers are wanted (a brick period is
+// set by its slowest warp task, a third buffer lets the other warps run ahead instead of waiting for it)
+__host__ __device__ inline int flp_qcap(int nbuf) { return nbuf >= 3 ? 24 : FL_QCAP; }
+__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf)
 {
-    return 2 * flp_buf_bytes(cap, ncs_max, ntypes) + (size_t)ntypes * ntypes * sizeof(double2) +
-           (size_t)(FL_QCAP + 1) * FLP_QS * sizeof(uint16_t);
+    return nbuf * flp_buf_bytes(cap, ncs_max, ntypes) + (size_t)ntypes * ntypes * sizeof(double2) +
+           (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t);
 }
 
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
@@ -59,15 +62,18 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
     return b;
 }
 
-template <bool MULTI, bool COUNT>
-__global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks)
+// EW: also per-atom energies and virials (half of every pair to each atom, src/nonbonded.jl:93-94) -- the single-point
+// evaluation behind emdee_compute_nonbonded(EMDEE_CUTOFF); store_f: write the forces (bitmask without FORCES: false).
+template <bool MULTI, bool COUNT, int NBUF, bool EW>
+__global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = 4;
+    constexpr int QCAP = NBUF >= 3 ? 24 : FL_QCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap1 = a.cap + 1;
     const size_t bufsz = flp_buf_bytes(a.cap, a.ncs_max, a.ntypes);
-    double2 *ljt = reinterpret_cast<double2 *>(smem_raw + 2 * bufsz);
+    double2 *ljt = reinterpret_cast<double2 *>(smem_raw + NBUF * bufsz);
     uint16_t *qguard = reinterpret_cast<uint16_t *>(ljt + a.ntypes * a.ntypes);
     uint16_t *queue = qguard + FLP_QS;
 
@@ -86,10 +92,10 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             hdr_nh = a.brickhdr[2 * (blockIdx.x + a.block_first) + 1];
         }
         for (int k = 0;; k++) {
-            const int b = k & 1;
+            const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
             const int brick = blockIdx.x + k * gridDim.x;
-            if (k >= 2) bar_sync(3 + b, FLP_THREADS);                 // empty[b]: the consumers are done with this buffer
+            if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);                 // empty[b]: the consumers are done with this buffer
             if (brick >= nbricks) {
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
@@ -194,7 +200,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
     };
 
     for (int k = 0;; k++) {
-        const int b = k & 1;
+        const int b = k % NBUF;
         const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
         bar_sync(1 + b, FLP_THREADS);                                 // full[b]
         const int brick = B.scal[4];
@@ -228,7 +234,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const __half2 ixy = *reinterpret_cast<const __half2 *>(&hme.x), izw = *reinterpret_cast<const __half2 *>(&hme.y);
             const double2 *ljrow = ljt;
             if (MULTI) ljrow = ljt + (int)ptyp[me] * a.ntypes;
-            double fx = 0, fy = 0, fz = 0;
+            double fx = 0, fy = 0, fz = 0, e = 0, w = 0;
 
             const int nent = pre_n;
             const int nch = (nent + 7) >> 3;
@@ -257,10 +263,11 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 tmin = min(tmin, (unsigned)t);
                 double sig2 = sig2_0, tt = tt_0;
                 if (MULTI) { const double2 pr = ljrow[ptyp[j]]; sig2 = pr.x; tt = pr.y; }
-                double Eg, Wg;
-                double qf = lj_pair_q<false>(r2, sig2, tt, a.fast, false, 0.0, Eg, Wg);
+                double Eg = 0, Wg = 0;
+                double qf = lj_pair_q<EW>(r2, sig2, tt, a.fast, false, 0.0, Eg, Wg);
                 qf = t < 0 ? qf : 0.0;
                 fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+                if (EW) { e += t < 0 ? Eg : 0.0; w += t < 0 ? Wg : 0.0; }
                 if (COUNT) np += t < 0 ? 1 : 0;
             };
             auto drain = [&](int depth) {
@@ -287,26 +294,30 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
                 test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
                 e0 = e1; e1 = e2;
-                const int over = __reduce_max_sync(0xffffffffu, cnt) - (FL_QCAP - 8);
+                const int over = __reduce_max_sync(0xffffffffu, cnt) - (QCAP - 8);
                 if (over > 0) drain((max(over, FL_MINPOP) + ILP - 1) & ~(ILP - 1));
             }
             drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
 
             if (tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
-                LaneRedo w;
-                w.pxy = pxy; w.pz = pz; w.ptyp = ptyp; w.ljt = ljt; w.cs = nullptr; w.gbase = nullptr; w.recipe = recipe;
-                w.ncs = 0; w.ntypes = a.ntypes; w.me = me; w.slot_i = slot_i; w.nent = nent;
-                w.entries = reinterpret_cast<const uint16_t *>(lp);
-                w.sx = a.sx; w.sy = a.sy; w.sz = a.sz; w.L = a.L; w.model = a.model; w.fast = a.fast; w.rc2hi = a.rc2hi;
-                double f3[3];
-                careful_lane<MULTI>(w, f3, &np);
+                LaneRedo rd;
+                rd.pxy = pxy; rd.pz = pz; rd.ptyp = ptyp; rd.ljt = ljt; rd.cs = nullptr; rd.gbase = nullptr; rd.recipe = recipe;
+                rd.ncs = 0; rd.ntypes = a.ntypes; rd.me = me; rd.slot_i = slot_i; rd.nent = nent;
+                rd.entries = reinterpret_cast<const uint16_t *>(lp);
+                rd.sx = a.sx; rd.sy = a.sy; rd.sz = a.sz; rd.L = a.L; rd.model = a.model; rd.fast = a.fast; rd.rc2hi = a.rc2hi;
+                double f3[5];
+                careful_lane<MULTI, EW>(rd, f3, &np);
                 fx = f3[0]; fy = f3[1]; fz = f3[2];
+                if (EW) { e = f3[3]; w = f3[4]; }
             }
             if (COUNT) npair += np;
-            if (active) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
+            if (active) {
+                if (store_f) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
+                if (EW) { a.en[slot_i] = 0.5 * e; a.vir[slot_i] = 0.5 * w; }
+            }
             grp = ngrp;
         }
-        bar_arrive(3 + b, FLP_THREADS);                               // empty[b]
+        bar_arrive(1 + NBUF + b, FLP_THREADS);                        // empty[b]
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) npair += __shfl_xor_sync(0xffffffffu, npair, o);
