@@ -291,7 +291,11 @@ extern "C" int emdee_comm_init(emdee_ctx *c, int rank, int nranks, const char id
     ncclUniqueId u;
     memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
     NCCL_TRY(ncclCommInitRank(&c->comm, nranks, u, rank));
-    CUDA_TRY(cudaStreamCreateWithFlags(&c->comm_stream, cudaStreamNonBlocking));
+    {   // the halo exchange must get SMs ahead of the (persistent, SM-filling) force kernel that becomes ready together with it
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&c->comm_stream, cudaStreamNonBlocking, hi));
+    }
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&c->ev_comm, cudaEventDisableTiming));
     c->rank = rank;
@@ -790,7 +794,16 @@ static int choose_bricks(emdee_system *s)
         if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin)
             return finish(cap, s->fc_block, s->fl_block);
     }
-    static const int shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {8, 2, 1}, {4, 4, 1}, {4, 2, 2}, {4, 2, 1}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+    // shapes in units of ndiv cells (a cell edge is (rc + skin)/ndiv), so the candidates keep their physical size
+    static const int base_shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {8, 2, 1}, {4, 4, 1}, {4, 2, 2}, {3, 2, 2}, {4, 2, 1}, {2, 2, 2}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+    constexpr int NBASE = sizeof(base_shapes) / sizeof(base_shapes[0]);
+    int shapes[2 * NBASE][3];
+    int nshapes_all = 0;
+    for (int k = 0; k < NBASE; k++, nshapes_all++)
+        for (int d = 0; d < 3; d++) shapes[nshapes_all][d] = base_shapes[k][d] * std::max(R, 1);
+    if (R > 1)      // finer cells also allow the plain shapes
+        for (int k = 0; k < NBASE; k++, nshapes_all++)
+            for (int d = 0; d < 3; d++) shapes[nshapes_all][d] = base_shapes[k][d];
     int forced[3] = {0, 0, 0}, forced_block = 0, forced_lblock = 0;
     if (const char *e = getenv("EMDEE_BRICK")) sscanf(e, "%d,%d,%d", &forced[0], &forced[1], &forced[2]);
     if (const char *e = getenv("EMDEE_BLOCK")) forced_block = atoi(e);
@@ -798,7 +811,7 @@ static int choose_bricks(emdee_system *s)
     double best_score = -1;
     int best_shape[3] = {0, 0, 0}, best_block = 0, best_lblock = 192, best_cap = 0;
     size_t best_budget = 0;
-    const int nshape = forced[0] > 0 ? 1 : (int)(sizeof(shapes) / sizeof(shapes[0]));
+    const int nshape = forced[0] > 0 ? 1 : nshapes_all;
     int prev[3] = {-1, -1, -1};
     for (int k = 0; k < nshape; k++) {
         const int *sh = forced[0] > 0 ? forced : shapes[k];
@@ -1343,8 +1356,9 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         CUDA_TRY(cudaEventRecord(pe0, c->stream));
     }
     const int layer = s->g.nbx * s->g.nby;
-    // launch order: interior layers first, then the layers that read ghost planes
-    int ranges[3][2] = {{0, s->fc_nblocks}, {0, 0}, {0, 0}};
+    // launch order: interior layers first, then (one launch over two ranges) the layers that read ghost planes
+    int ranges[2][3] = {{0, s->fc_nblocks, 0}, {0, 0, 0}};       // {first brick, bricks of the first range, bricks of the second range}
+    int second_first = 0;
     if (halo && c->nranks > 1) {
         CUDA_TRY(cudaEventRecord(c->ev_compute, c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_compute, 0));
@@ -1352,14 +1366,16 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         CUDA_TRY(cudaEventRecord(c->ev_comm, c->comm_stream));
         ranges[0][0] = s->brick_lo_end * layer; ranges[0][1] = (s->brick_hi_begin - s->brick_lo_end) * layer;
         ranges[1][0] = 0; ranges[1][1] = s->brick_lo_end * layer;
-        ranges[2][0] = s->brick_hi_begin * layer; ranges[2][1] = s->fc_nblocks - s->brick_hi_begin * layer;
+        second_first = s->brick_hi_begin * layer; ranges[1][2] = s->fc_nblocks - s->brick_hi_begin * layer;
     }
-    for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < 2; k++) {
         if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
         a.block_first = ranges[k][0];
-        EMDEE_TRY(launch_cells(s, a, ranges[k][1], F, EW, s->has_excl, audit, mode));
+        a.block_split = ranges[k][1];
+        a.block_first2 = second_first;
+        EMDEE_TRY(launch_cells(s, a, ranges[k][1] + ranges[k][2], F, EW, s->has_excl, audit, mode));
         if (getenv("EMDEE_DEBUG_SYNC")) {
-            fprintf(stderr, "[emdee] force launch mode %d range %d (%d blocks) issued\n", mode, k, ranges[k][1]);
+            fprintf(stderr, "[emdee] force launch mode %d range %d (%d blocks) issued\n", mode, k, ranges[k][1] + ranges[k][2]);
             CUDA_TRY(cudaStreamSynchronize(c->stream));
             fprintf(stderr, "[emdee] force launch mode %d range %d done\n", mode, k);
         }

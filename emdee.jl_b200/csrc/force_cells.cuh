@@ -63,7 +63,8 @@ struct CellArgs {
     int cap;                          // staged-atom capacity of the shared-memory arrays
     int ncs_max;                      // staged-cell capacity
     int *err;                         // device error flag (capacity overflow)
-    int block_first;                  // first brick of this launch (launches may cover a z-layer range)
+    int block_first;                  // first brick of this launch (launches may cover a z-layer range) ...
+    int block_split, block_first2;    // ... or two ranges: launch index i >= block_split maps to block_first2 + (i - block_split)
     // pair list: home atom h of a brick (flattened over its home rows) belongs to group h/32, lane h%32;
     // chunk c of that atom is the uint4 list8[((brick*gmax + h/32)*lcap8 + c)*32 + h%32] = 8 x (staged index + 1)
     uint4 *list8;
@@ -81,6 +82,9 @@ struct CellArgs {
     int *brickhdr;                    // brickhdr[2*brick] = staged atoms + 1, [2*brick+1] = home atoms
     int rcap;
 };
+
+// Brick handled by launch index i (a launch covers one or two contiguous ranges of bricks).
+#define FC_BRICK_OF(a, i) ((i) < (a).block_split ? (a).block_first + (i) : (a).block_first2 + ((i) - (a).block_split))
 
 // Brick geometry shared by the kernels that stage a brick.
 struct BrickGeom {
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(FC_MAX_BLOCK, 1) k_force_cells(CellArgs a)
     const int R = g.R;
 
     // ---- brick geometry ---------------------------------------------------------------------
-    const int bid = blockIdx.x + a.block_first;
+    const int bid = FC_BRICK_OF(a, (int)blockIdx.x);
     const BrickGeom bg = brick_geom(g, bid);
     const int nhx = bg.nhx, nhy = bg.nhy, nhz = bg.nhz;
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;

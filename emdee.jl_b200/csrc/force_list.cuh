@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NW = BLOCK / 32;
     const int R = g.R;
-    const int bid = blockIdx.x + a.block_first;
+    const int bid = FC_BRICK_OF(a, (int)blockIdx.x);
     const BrickGeom bg = brick_geom(g, bid);
     qguard[tid] = 0;
 

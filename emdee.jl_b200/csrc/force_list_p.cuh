@@ -88,8 +88,8 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
         const int R = g.R;
         int hdr_n1 = 0, hdr_nh = 0;
         if ((int)blockIdx.x < nbricks) {
-            hdr_n1 = a.brickhdr[2 * (blockIdx.x + a.block_first)];
-            hdr_nh = a.brickhdr[2 * (blockIdx.x + a.block_first) + 1];
+            hdr_n1 = a.brickhdr[2 * FC_BRICK_OF(a, (int)blockIdx.x)];
+            hdr_nh = a.brickhdr[2 * FC_BRICK_OF(a, (int)blockIdx.x) + 1];
         }
         for (int k = 0;; k++) {
             const int b = k % NBUF;
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 bar_arrive(1 + b, FLP_THREADS);
                 break;
             }
-            const int bid = brick + a.block_first;
+            const int bid = FC_BRICK_OF(a, brick);
             const BrickGeom bg = brick_geom(g, bid);
             // the recipe written by k_list_build at the last re-binning: slot and staged-cell coordinates of every staged
             // atom, so staging is one coalesced load, three gathers and ~30 instructions per atom, with no table or scan
@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 // at were written by k_vv just before this kernel and are L2 hits)
                 const int nb = brick + gridDim.x;
                 if (nb < nbricks) {
-                    const int nbid = nb + a.block_first;
+                    const int nbid = FC_BRICK_OF(a, nb);
                     hdr_n1 = a.brickhdr[2 * nbid];
                     hdr_nh = a.brickhdr[2 * nbid + 1];
                     const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
         bar_sync(1 + b, FLP_THREADS);                                 // full[b]
         const int brick = B.scal[4];
         if (brick < 0) break;
-        const int bid = brick + a.block_first;
+        const int bid = FC_BRICK_OF(a, brick);
         const double2 *pxy = B.pxy;
         const double *pz = B.pz;
         const uint2 *ph = B.ph;

@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = g.R;
-    const int bid = blockIdx.x + a.block_first;
+    const int bid = FC_BRICK_OF(a, (int)blockIdx.x);
     const BrickGeom bg = brick_geom(g, bid);
     const int nhx = bg.nhx, nhy = bg.nhy, nhz = bg.nhz;
     const int sxn = bg.sxn, syn = bg.syn, ncs = bg.ncs;

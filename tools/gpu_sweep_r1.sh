@@ -1,5 +1,11 @@
 cd /root/repo
-timeout 300 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -8
-timeout 200 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/s_e2e.json 2> gpurun_out/s_e2e.err; tail -3 gpurun_out/s_e2e.err
-python -c "
-import json; d=json.loads(open('gpurun_out/s_e2e.json').read().strip().splitlines()[-1]); print('ms/step %.3f e2e %.4g pairs/s, %.3f ms/call'%(d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_call']))"
+timeout 300 python -m pytest tests -m gpu -x -q --timeout 60 2>&1 | tail -3
+B="timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --e2e-iters 1"
+run() { # name, env..., extra args after --
+  name=$1; shift
+  env EMDEE_DEBUG=1 "$@" > gpurun_out/s_$name.json 2> gpurun_out/s_$name.err
+  echo "$name: $(grep 'bricks\|force kernel mode' gpurun_out/s_$name.err | head -3 | sed 's/.*mode//;s/.emdee. //' | tr '\n' ';') $(python -c "
+import json; d=json.loads(open('gpurun_out/s_$name.json').read().strip().splitlines()[-1]); print('ms/step %.3f e2e %.3f ms'%(d['ms_per_step'], d['e2e']['ms_per_call']))" 2>&1 | tail -1)"
+}
+run nd1 $B
+run nd2 $B --ndiv 2
