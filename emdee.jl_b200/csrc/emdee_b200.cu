@@ -140,6 +140,7 @@ struct emdee_system {
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
     int fl_nbuf = 2, want_nbuf = 3;                       // three when they fit
+    bool fl_fuse = true;                                  // walk and drain share a basic block
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
@@ -406,6 +407,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NBUF")) s->want_nbuf = atoi(e) >= 3 ? 3 : 2;
+    if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -1208,7 +1210,7 @@ static int launch_list_i(emdee_system *s, const CellArgs &a, int nblocks)
 template <bool MULTI, bool COUNT, bool EW>
 static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
 {
-    auto kern = k_force_list_p<MULTI, COUNT, 2, EW>;
+    auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
     const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<std::min(nblocks, s->ctx->sm_count), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks, store_f ? 1 : 0);

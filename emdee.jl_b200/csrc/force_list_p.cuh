@@ -64,7 +64,10 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 
 // EW: also per-atom energies and virials (half of every pair to each atom, src/nonbonded.jl:93-94) -- the single-point
 // evaluation behind emdee_compute_nonbonded(EMDEE_CUTOFF); store_f: write the forces (bitmask without FORCES: false).
-template <bool MULTI, bool COUNT, int NBUF, bool EW>
+// FUSE: from the second chunk on, every walk iteration also pops and evaluates ILP stack entries in the same basic
+// block, so the scheduler fills the FP64 dependency stalls of the drain with the FP16 tests and stack pushes of the
+// walk (ncu: `wait` was the top stall of the consumers with walk and drain as separate loops).
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE>
 __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = 4;
@@ -253,10 +256,8 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             unsigned tmin = 0xffffffffu;
             unsigned long long np = 0;
 
-            auto pair_eval = [&](int idx) {
-                const int j = queue[max(idx, -1) * FLP_QS + ctid];
-                const double2 j0 = pxy[j];
-                const double jz = pz[j];
+            // the arithmetic of one pair, given the partner's staged index and coordinates
+            auto pair_math = [&](int j, double2 j0, double jz) {
                 const double vx = pix - j0.x, vy = piy - j0.y, vz = piz - jz;
                 const double r2 = fma(vz, vz, fma(vy, vy, vx * vx));
                 const int t = __double2hiint(r2) - (a.rc2hi - 1);     // pair_in_range: t < 0 inside, t <= 2 borderline
@@ -269,6 +270,10 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
                 if (EW) { e += t < 0 ? Eg : 0.0; w += t < 0 ? Wg : 0.0; }
                 if (COUNT) np += t < 0 ? 1 : 0;
+            };
+            auto pair_eval = [&](int idx) {
+                const int j = queue[max(idx, -1) * FLP_QS + ctid];
+                pair_math(j, pxy[j], pz[j]);
             };
             auto drain = [&](int depth) {
                 for (int kk = 0; kk < depth; kk += ILP) {
@@ -291,8 +296,26 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 const unsigned j0 = e0.x & 0xffffu, j1 = e0.x >> 16, j2 = e0.y & 0xffffu, j3 = e0.y >> 16;
                 const unsigned j4 = e0.z & 0xffffu, j5 = e0.z >> 16, j6 = e0.w & 0xffffu, j7 = e0.w >> 16;
                 const uint2 h0 = ph[j0], h1 = ph[j1], h2 = ph[j2], h3 = ph[j3], h4 = ph[j4], h5 = ph[j5], h6 = ph[j6], h7 = ph[j7];
-                test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
-                test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
+                if (FUSE && c > 0) {
+                    // pop ILP entries (an empty stack yields the dummy atom) and fetch their coordinates before anything is
+                    // pushed; the tests/pushes of this chunk and the FP64 arithmetic of the popped pairs then share one block
+                    int pj[ILP];
+                    double2 pxyj[ILP];
+                    double pzj[ILP];
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) pj[u] = queue[max(cnt - 1 - u, -1) * FLP_QS + ctid];
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) { pxyj[u] = pxy[pj[u]]; pzj[u] = pz[pj[u]]; }
+                    cnt = max(cnt - ILP, 0);
+                    qp = queue + cnt * FLP_QS + ctid;
+                    test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
+                    test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
+#pragma unroll
+                    for (int u = 0; u < ILP; u++) pair_math(pj[u], pxyj[u], pzj[u]);
+                } else {
+                    test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
+                    test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
+                }
                 e0 = e1; e1 = e2;
                 const int over = __reduce_max_sync(0xffffffffu, cnt) - (QCAP - 8);
                 if (over > 0) drain((max(over, FL_MINPOP) + ILP - 1) & ~(ILP - 1));
