@@ -141,6 +141,7 @@ struct emdee_system {
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
     int fl_nbuf = 2, want_nbuf = 3;                       // three when they fit
     bool fl_fuse = true;                                  // walk and drain share a basic block
+    int reserve_sms = 0, nccl_sms = 0;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS; measured at 4 GPUs: what the exchange gains the interior launch loses)
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
@@ -174,6 +175,8 @@ struct emdee_system {
     std::vector<cudaEvent_t> prof_events;
     std::vector<int> prof_mode;               // launch mode of every event pair (0 scan, 1 list build, 2 list walk)
     size_t prof_used = 0;
+    std::vector<cudaEvent_t> prof_mid;        // slab runs: end of the interior launch, start of the boundary launch
+    std::vector<size_t> prof_mid_of;          // index of the event pair each mid pair belongs to
     double prof_ms[4] = {0, 0, 0, 0};         // per-kind totals of the last profile (emdee_profile_kind)
     int64_t prof_n[4] = {0, 0, 0, 0};
     // scratch for host transfers
@@ -408,6 +411,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NBUF")) s->want_nbuf = atoi(e) >= 3 ? 3 : 2;
     if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
     int st = EMDEE_OK;
@@ -1213,7 +1217,10 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
     const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<std::min(nblocks, s->ctx->sm_count), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks, store_f ? 1 : 0);
+    // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
+    // registers of its SM, so NCCL could not start before the first block retires otherwise)
+    const int sms = std::max(1, s->ctx->sm_count - s->reserve_sms);
+    kern<<<std::min(nblocks, sms), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks, store_f ? 1 : 0);
     s->ctx->launches++;
     return check_launch("k_force_list_p");
 }
@@ -1371,11 +1378,23 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         second_first = s->brick_hi_begin * layer; ranges[1][2] = s->fc_nblocks - s->brick_hi_begin * layer;
     }
     for (int k = 0; k < 2; k++) {
-        if (k == 1 && halo && c->nranks > 1) CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+        if (k == 1 && halo && c->nranks > 1) {
+            cudaEvent_t m0 = nullptr, m1 = nullptr;
+            if (pe0 && getenv("EMDEE_DEBUG")) {
+                CUDA_TRY(cudaEventCreate(&m0)); CUDA_TRY(cudaEventCreate(&m1));
+                s->prof_mid.push_back(m0); s->prof_mid.push_back(m1);
+                s->prof_mid_of.push_back(s->prof_used - 2);
+                CUDA_TRY(cudaEventRecord(m0, c->stream));
+            }
+            CUDA_TRY(cudaStreamWaitEvent(c->stream, c->ev_comm, 0));
+            if (m1) CUDA_TRY(cudaEventRecord(m1, c->stream));
+        }
         a.block_first = ranges[k][0];
         a.block_split = ranges[k][1];
         a.block_first2 = second_first;
+        s->reserve_sms = (k == 0 && halo && c->nranks > 1) ? s->nccl_sms : 0;
         EMDEE_TRY(launch_cells(s, a, ranges[k][1] + ranges[k][2], F, EW, s->has_excl, audit, mode));
+        s->reserve_sms = 0;
         if (getenv("EMDEE_DEBUG_SYNC")) {
             fprintf(stderr, "[emdee] force launch mode %d range %d (%d blocks) issued\n", mode, k, ranges[k][1] + ranges[k][2]);
             CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1756,6 +1775,21 @@ extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
         per_mode[m] += t; n_mode[m]++;
     }
     for (int m = 0; m < 4; m++) { s->prof_ms[m] = per_mode[m]; s->prof_n[m] = n_mode[m]; }
+    if (!s->prof_mid.empty()) {       // slab runs: interior launch / wait for the halo / boundary launch
+        double ti = 0, tw = 0, tb = 0;
+        for (size_t k = 0; k < s->prof_mid_of.size(); k++) {
+            float x = 0;
+            const size_t p = s->prof_mid_of[k];
+            CUDA_TRY(cudaEventElapsedTime(&x, s->prof_events[p], s->prof_mid[2 * k])); ti += x;
+            CUDA_TRY(cudaEventElapsedTime(&x, s->prof_mid[2 * k], s->prof_mid[2 * k + 1])); tw += x;
+            CUDA_TRY(cudaEventElapsedTime(&x, s->prof_mid[2 * k + 1], s->prof_events[p + 1])); tb += x;
+        }
+        const double n = (double)s->prof_mid_of.size();
+        fprintf(stderr, "[emdee] rank %d slab step: interior %.4f ms, waiting for the halo %.4f ms, boundary %.4f ms (%d steps)\n", c->rank,
+                ti / n, tw / n, tb / n, (int)n);
+        for (cudaEvent_t e : s->prof_mid) cudaEventDestroy(e);
+        s->prof_mid.clear(); s->prof_mid_of.clear();
+    }
     if (getenv("EMDEE_DEBUG"))
         for (int m = 0; m < 4; m++)
             if (n_mode[m]) fprintf(stderr, "[emdee] force kernel mode %d: %d launches, %.4f ms each\n", m, n_mode[m], per_mode[m] / n_mode[m]);

@@ -296,11 +296,19 @@ def test_velocity_verlet(em, oracle):
     s.close()
 
 
-def test_pair_list_stepping_audit(em, oracle):
-    """The stepping path (pair list built on the re-binning step, walked by k_force_list afterwards): after
+@pytest.mark.parametrize("variant", ["persistent", "block_per_brick", "ndiv2", "no_list"])
+def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
+    """The stepping path (pair list built on the re-binning step, walked by k_force_list_p afterwards): after
     steps that only walked the list, forces and the evaluated pair count equal the oracle's at the same
-    positions.  A pair the FP16/FP32 pre-culls dropped near rc would be invisible in the forces (g -> 0 there),
-    so the count is the sharp check."""
+    positions.  A pair the FP16 pre-culls dropped near rc would be invisible in the forces (g -> 0 there),
+    so the count is the sharp check.  Variants: the persistent kernel (default), the block-per-brick kernel
+    it falls back to when two staging buffers do not fit, cells of half the edge (ndiv = 2), and stepping
+    without a list (window scan on every step)."""
+    if variant == "block_per_brick":
+        monkeypatch.setenv("EMDEE_PERSIST", "0")
+    if variant == "no_list":
+        monkeypatch.setenv("EMDEE_LIST", "0")
+    ndiv = 2 if variant == "ndiv2" else 1
     pos, L = em.workloads.fcc_lattice(16)
     N = pos.shape[0]
     atoms = em.workloads.lj_fluid_atoms(N)
@@ -308,7 +316,7 @@ def test_pair_list_stepping_audit(em, oracle):
     s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
     s.set_masses(np.ones(N))
     s.set_skin(0.4)
-    s.bin(1)
+    s.bin(ndiv)
     s.compute(em.CUTOFF, em.FORCES)
     for nsteps in (1, 3):                       # 1: the build step itself; 3 more: list walks
         s.vv_step(0.005, nsteps, rebin_every=5)
@@ -316,7 +324,13 @@ def test_pair_list_stepping_audit(em, oracle):
         p = s.positions()
         ref = oracle.cutoff_cells(p, L, 2.5, 2.0, atoms, ndiv=1, fast=True)
         assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
-        assert s.list_pair_count() == ref["npairs"]
+        n = s.list_pair_count()
+        assert n == (-1 if variant == "no_list" else ref["npairs"])
+    # a single-point evaluation within the skin re-uses the list (energies and virials from the list kernel)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(s.positions(), L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
     s.close()
 
 
