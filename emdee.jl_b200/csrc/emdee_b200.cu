@@ -1303,18 +1303,26 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         a.fast.id2 = s->model.id2;
         a.fast.nrs2id2 = -s->model.rs2 * s->model.id2;
         a.fast.c60id2 = 60.0 * s->model.id2;
-        // FP16 pre-cull of k_force_list: coordinates within +-cmax of the brick centre are stored with an error of
-        // half an FP16 ulp (both atoms), the separation and the three squares/sums round once more each
-        const double hx = 0.5 * (s->g.bx + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
-        const double hy = 0.5 * (s->g.by + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
-        const double hz = 0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin;
-        const double cmax = std::max(hx, std::max(hy, hz));
-        const double ulp_c = std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(cmax))) - 10);   // FP16 ulp at cmax
-        const double u = std::ldexp(1.0, -11);                                                        // FP16 unit roundoff
-        const double dd = ulp_c + 4.0 * u * (s->cutoff + s->skin + 1.0);   // per-component error of a separation (2 x ulp/2 + rounding of d)
-        auto thr16 = [&](double rc) {      // threshold such that r <= rc implies r2_fp16 <= threshold
-            const double e2 = 2.0 * std::sqrt(3.0) * rc * dd + 3.0 * dd * dd + 8.0 * u * (rc * rc + 1.0);   // bound on |r2_fp16 - r2|
-            return (float)((rc * rc + 1.5 * e2) * (1.0 + 2.0 * u));
+        // FP16 pre-culls (k_force_list*, k_list_build): a pair with r <= rcut must pass r2_fp16 <= threshold.
+        //   stored coordinates: |c_k| <= h_k (half extent of the staged box + skin/2), rounded to FP16 (through FP32):
+        //     half an ulp16(h_k) per atom; the separation rounds once more: ulp16(rcut)/2   ->  delta_k
+        //   r2 of the stored separations <= rcut^2 + 2 rcut |delta| + |delta|^2            (Cauchy-Schwarz)
+        //   at most four FP16 roundings in the squares and sums: 4.2 u (rcut + |delta|)^2, u = 2^-11
+        // (5 % head-room on the error terms; the device rounds the threshold up to FP16.)
+        const double hext[3] = {0.5 * (s->g.bx + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin,
+                                0.5 * (s->g.by + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin,
+                                0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin};
+        auto ulp16 = [](double v) { return std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(v))) - 10); };
+        const double u = std::ldexp(1.0, -11);
+        auto thr16 = [&](double rcut) {
+            double d2 = 0;
+            for (int k = 0; k < 3; k++) {
+                const double dk = 1.001 * ulp16(hext[k]) + 0.5 * ulp16(rcut);
+                d2 += dk * dk;
+            }
+            const double dn = std::sqrt(d2);
+            const double err = 2.0 * rcut * dn + d2 + 4.2 * u * (rcut + dn) * (rcut + dn);
+            return (float)((rcut * rcut + 1.05 * err) * (1.0 + u));
         };
         a.rc2h = thr16(s->cutoff);
         a.rl2h = thr16(s->cutoff + s->skin);
