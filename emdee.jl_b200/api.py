@@ -238,6 +238,8 @@ class NonbondedSystem:
         call("emdee_compute_nonbonded", self._h, int(mode), int(bitmask))
 
     def vv_step(self, dt, nsteps, rebin_every=1):
+        """nsteps velocity-Verlet steps; rebin_every > 0: re-bin at that cadence, 0: never, < 0 (with a skin):
+        adaptively, when an atom has moved more than skin/2 since the last binning."""
         call("emdee_vv_step", self._h, float(dt), int(nsteps), int(rebin_every))
 
     def synchronize(self):

@@ -32,6 +32,7 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -48,7 +49,7 @@ static int nccl_load()
     if (!g_nccl.field) EMDEE_FAIL(EMDEE_ERR_NCCL, "libnccl.so.2 lacks %s", name);
     NCCL_SYM(GetUniqueId, "ncclGetUniqueId") NCCL_SYM(CommInitRank, "ncclCommInitRank") NCCL_SYM(CommDestroy, "ncclCommDestroy")
     NCCL_SYM(Send, "ncclSend") NCCL_SYM(Recv, "ncclRecv") NCCL_SYM(GroupStart, "ncclGroupStart") NCCL_SYM(GroupEnd, "ncclGroupEnd")
-    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString") NCCL_SYM(AllReduce, "ncclAllReduce")
 #undef NCCL_SYM
     g_nccl.handle = h;
     return EMDEE_OK;
@@ -124,6 +125,7 @@ struct emdee_system {
     int32_t *count = nullptr, *cell_start = nullptr, *fill = nullptr, *order = nullptr, *src_of_new = nullptr;
     int32_t *block_sum = nullptr, *maxpop = nullptr;
     int64_t steps_since_bin = 0;
+    unsigned *maxd2 = nullptr;                // device: max |r - r_bin|^2 since the last binning (float bits), adaptive re-binning
     // slab decomposition (nranks > 1)
     bool decomposed = false;
     int z0 = 0, nz = 0;                               // my global planes [z0, z0+nz)
@@ -426,6 +428,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->order, s->cap));
     A(dev_alloc(&s->src_of_new, s->cap));
     A(dev_alloc(&s->totals, 2));
+    A(dev_alloc(&s->maxd2, 2));
     A(dev_alloc(&s->digest, 4));
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
@@ -463,7 +466,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     for (int k = 0; k < 2; k++) { dev_free(s->gcell[k]); dev_free(s->lcell[k]); }
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
-    dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest);
+    dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest); dev_free(s->maxd2);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
@@ -838,7 +841,11 @@ static int choose_bricks(emdee_system *s)
             if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin) {
                 // persistent kernel (two staging buffers): the largest brick that fits, and among equal volumes the
                 // one that stages the fewest cells (least halo per home atom)
-                const double score = 1e6 + 1000.0 * (g.bx * g.by * g.bz) - ncs;
+                // ... weighted by how well its warp tasks fill the consumer warps: a brick period lasts ceil(groups / consumers)
+                // task times (measured: 13 groups on 12 consumer warps cost 1.55 ms per launch against 1.31 ms for 11)
+                const double groups = std::ceil(1.03 * home / 32.0);
+                const double fill = groups / (std::ceil(groups / FLP_NCONS) * FLP_NCONS);
+                const double score = 1e6 + 1000.0 * (g.bx * g.by * g.bz) * fill - ncs;
                 if (score > best_score) {
                     best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
@@ -955,6 +962,7 @@ static int do_bin(emdee_system *s, int ndiv)
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
+    CUDA_TRY(cudaMemsetAsync(s->maxd2, 0, sizeof(unsigned), c->stream));
     if (s->grid_ok) EMDEE_TRY(choose_bricks(s));
     return EMDEE_OK;
 }
@@ -1099,6 +1107,7 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
+    CUDA_TRY(cudaMemsetAsync(s->maxd2, 0, sizeof(unsigned), c->stream));
     EMDEE_TRY(choose_bricks(s));
     // brick layers whose halo reaches ghost planes (they must wait for the halo exchange)
     const int bz = s->g.bz, nbz = s->g.nbz;
@@ -1681,7 +1690,7 @@ extern "C" int emdee_list_pair_count(emdee_system *s, int64_t *npairs)
 // ------------------------------------------------------------------------------------------------
 // velocity-Verlet
 // ------------------------------------------------------------------------------------------------
-static int launch_vv(emdee_system *s, double dt, int drift, int check_skin)
+static int launch_vv(emdee_system *s, double dt, int drift, int check_skin, bool track = false)
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
@@ -1697,6 +1706,7 @@ static int launch_vv(emdee_system *s, double dt, int drift, int check_skin)
     a.drift = drift;
     a.check_skin = check_skin;
     a.err = s->err;
+    a.maxd2 = track ? s->maxd2 : nullptr;
     LAUNCH_1D(c, k_vv, a.n, a);
     return check_launch("k_vv");
 }
@@ -1709,12 +1719,25 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     if (!s->forces_valid) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: call emdee_compute_nonbonded(EMDEE_CUTOFF, FORCES|...) first");
     if (s->last_mode != EMDEE_CUTOFF) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: forces must come from EMDEE_CUTOFF mode");
     if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
+    const bool adaptive = rebin_every < 0 && s->skin > 0;      // rebin_every < 0: re-bin when the skin is used up
     for (int64_t st = 0; st < nsteps; st++) {
         // A pair list must be built at the positions the cells were binned at (both rely on "no atom moved
         // more than skin/2 since the binning"), so a missing list forces a re-binning on this step.
         const bool need_list = list_capable(s) && !s->list_valid;
-        const bool rebin = need_list || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
-        EMDEE_TRY(launch_vv(s, dt, 1, rebin ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
+        bool rebin = need_list || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
+        if (adaptive && !rebin) {
+            // re-bin exactly when an atom has moved more than skin/2 since the last binning: one 4-byte read-back per
+            // step (all ranks must take the same decision: max over ranks)
+            EMDEE_TRY(launch_vv(s, dt, 1, 0, true));
+            if (c->nranks > 1) NCCL_TRY(g_nccl.AllReduce(s->maxd2, s->maxd2, 1, ncclUint32, ncclMax, c->comm, c->stream));
+            unsigned bits = 0;
+            CUDA_TRY(cudaMemcpyAsync(&bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            float d2max;
+            memcpy(&d2max, &bits, 4);
+            rebin = (double)d2max > 0.25 * s->skin * s->skin;
+        } else
+            EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
         s->kick_pending = false;
         s->steps_since_bin++;
         if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));

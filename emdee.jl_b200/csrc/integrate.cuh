@@ -17,6 +17,7 @@ struct VVArgs {
     int drift;                 // 1: kick + drift (+ rescale s), 0: kick only
     int check_skin;
     int *err;
+    unsigned *maxd2;           // adaptive re-binning: max over atoms of |r - r_bin|^2 as float bits (atomicMax); may be null
 };
 
 // One kernel per step: [second half-kick of step n-1] + first half-kick + drift of step n.
@@ -44,6 +45,10 @@ __global__ void k_vv(VVArgs a)
         a.v[c][i] = v;
     }
     if (a.drift && a.check_skin && d2 > a.half_skin2) atomicCAS(a.err, 0, 3);
+    if (a.maxd2) {      // positive floats order like their bit patterns (rounded up: the decision must be conservative)
+        const unsigned m = __reduce_max_sync(__activemask(), __float_as_uint(__double2float_ru(d2)));
+        if ((threadIdx.x & 31) == 0 && m > *a.maxd2) atomicMax(a.maxd2, m);
+    }
 }
 
 // K = sum 1/2 m v^2 over owned slots; per-block partials, summed on the host in block order.

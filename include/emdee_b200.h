@@ -116,7 +116,8 @@ int emdee_list_pair_count(emdee_system *sys, int64_t *npairs);
 
 /* Velocity-Verlet (absent from the reference): nsteps of
  * v += dt/2m f ; r += dt v ; f = F(r) ; v += dt/2m f, re-binning every `rebin_every` steps
- * (<=0: never).  Needs model, atoms, masses, velocities, one emdee_bin and one emdee_compute_nonbonded. */
+ * (0: never; < 0 with a skin: adaptively, on the first step on which an atom has moved more than skin/2 since the
+ * last binning -- one 4-byte read-back per step, and a max over ranks in a slab decomposition).  Needs model, atoms, masses, velocities, one emdee_bin and one emdee_compute_nonbonded. */
 int emdee_vv_step(emdee_system *sys, double dt, int64_t nsteps, int rebin_every);
 int emdee_kinetic_energy(emdee_system *sys, double *K);
 int emdee_synchronize(emdee_system *sys);

@@ -282,12 +282,24 @@ def test_velocity_verlet(em, oracle):
     assert np.abs(s.positions() - p).max() <= 1e-10
     assert np.abs(s.velocities() - v).max() <= 1e-9
     assert np.abs(s.forces() - f).max() <= 1e-8 * frms(f)
+    # adaptive re-binning (rebin_every < 0): re-bin on the step on which an atom has used up skin/2
+    s.set_positions(pos)
+    s.set_velocities(vel)
+    s.set_skin(0.3)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(dt, nsteps, rebin_every=-1)
+    s.synchronize()
+    assert np.abs(s.positions() - p).max() <= 1e-10
+    assert np.abs(s.velocities() - v).max() <= 1e-9
+    assert np.abs(s.forces() - f).max() <= 1e-8 * frms(f)
     s.set_skin(0.0)
     # energy conservation over a longer run, with a skin and sparse re-binning
     s.set_skin(0.5)            # fastest atom ~6 sigma/tau -> 0.03 sigma per step: 5 steps stay below skin/2
     s.bin(1)
     s.compute(em.CUTOFF, em.FORCES)
-    s.vv_step(dt, 200, rebin_every=5)
+    s.vv_step(dt, 100, rebin_every=5)
+    s.vv_step(dt, 100, rebin_every=-1)
     s.compute(em.CUTOFF, em.FORCES | em.ENERGIES)
     E1 = s.totals(pairs=False)[0]
     K1 = s.kinetic_energy()
