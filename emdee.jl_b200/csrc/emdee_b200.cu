@@ -138,6 +138,8 @@ struct emdee_system {
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
     bool fc_typed = false;
     int fc_shape[3] = {0, 0, 0};
+    double fc_per_cell = 0;                   // atoms per cell and reach when the shape was chosen
+    int fc_R = 0;
     int fl_block = 192;                       // block size of k_force_list
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
@@ -752,7 +754,7 @@ static int choose_bricks(emdee_system *s)
     GridDesc &g = s->g;
     const int R = g.R;
     const bool typed = s->ntypes > 0;
-    const bool listed = list_capable(s);
+    const bool listed = s->use_list && s->ntypes > 0;    // the list kernels also serve single-point evaluations (any skin)
     const size_t per_sm = c->smem_optin + 1024;          // usable shared memory per SM (1 KB reserved per block)
     const int64_t ntot = s->nlo + s->nown + s->nhi;
     const double per_cell = (double)ntot / (double)std::max<int64_t>(1, (int64_t)g.M * g.M * g.nzt);
@@ -793,8 +795,9 @@ static int choose_bricks(emdee_system *s)
         }
         return EMDEE_OK;
     };
-    // keep the previous configuration while it fits (one tiny kernel + sync per re-binning)
-    if (s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK")) {
+    // keep the previous configuration while it fits and the cells hold about as many atoms as when it was chosen
+    // (one tiny kernel + sync per re-binning)
+    if (s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK") && std::fabs(per_cell - s->fc_per_cell) <= 0.08 * s->fc_per_cell && R == s->fc_R) {
         set_brick_shape(s, s->fc_shape);
         int cap = 0;
         EMDEE_TRY(brick_capacity(s, &cap));
@@ -804,7 +807,8 @@ static int choose_bricks(emdee_system *s)
             return finish(cap, s->fc_block, s->fl_block);
     }
     // shapes in units of ndiv cells (a cell edge is (rc + skin)/ndiv), so the candidates keep their physical size
-    static const int base_shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {8, 2, 1}, {4, 4, 1}, {4, 2, 2}, {3, 2, 2}, {4, 2, 1}, {2, 2, 2}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
+    static const int base_shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {7, 2, 2}, {5, 3, 2}, {6, 2, 2}, {4, 3, 2}, {5, 2, 2}, {3, 3, 2}, {8, 2, 1}, {4, 4, 1},
+                                         {4, 2, 2}, {3, 2, 2}, {4, 2, 1}, {2, 2, 2}, {8, 1, 1}, {4, 1, 1}, {2, 2, 1}, {2, 1, 1}, {1, 1, 1}};
     constexpr int NBASE = sizeof(base_shapes) / sizeof(base_shapes[0]);
     int shapes[2 * NBASE][3];
     int nshapes_all = 0;
@@ -839,13 +843,13 @@ static int choose_bricks(emdee_system *s)
             const int cblock = cells_block(cap, ncs, forced_block);
             if (!cblock) continue;
             if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin) {
-                // persistent kernel (two staging buffers): the largest brick that fits, and among equal volumes the
-                // one that stages the fewest cells (least halo per home atom)
-                // ... weighted by how well its warp tasks fill the consumer warps: a brick period lasts ceil(groups / consumers)
-                // task times (measured: 13 groups on 12 consumer warps cost 1.55 ms per launch against 1.31 ms for 11)
+                // persistent kernel (two staging buffers).  Cost model per home atom, fitted to B200 measurements
+                // (4x2x2 / 3x2x2 / 4x3x2 / 5x2x2 bricks at skins 0.35-0.5): the consumers' time is 1 / fill, where a brick period
+                // lasts ceil(groups / consumer warps) warp-task times (13 groups on 12 consumers: 1.55 ms per launch against
+                // 1.31 ms for 11-12), plus ~2.5 % per staged cell per home cell for the producers' staging
                 const double groups = std::ceil(1.03 * home / 32.0);
                 const double fill = groups / (std::ceil(groups / FLP_NCONS) * FLP_NCONS);
-                const double score = 1e6 + 1000.0 * (g.bx * g.by * g.bz) * fill - ncs;
+                const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
                 if (score > best_score) {
                     best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
@@ -902,6 +906,8 @@ static int choose_bricks(emdee_system *s)
         fprintf(stderr, "[emdee] bricks %dx%dx%d block %d list-block %d cap %d (full search, per_cell %.1f, maxpop %d, listed %d)\n", best_shape[0],
                 best_shape[1], best_shape[2], best_block, best_lblock, best_cap, per_cell, maxpop, (int)listed);
     for (int k = 0; k < 3; k++) s->fc_shape[k] = best_shape[k];
+    s->fc_per_cell = per_cell;
+    s->fc_R = R;
     s->fc_smem_budget = std::min(best_budget, c->smem_optin);
     return finish(best_cap, best_block, best_lblock);
 }
