@@ -155,7 +155,8 @@ struct emdee_system {
     int *brickhdr = nullptr;
     int64_t recipe_cap = 0, hdr_cap = 0;
     int64_t list_slots = 0;                   // allocated groups
-    int lcap8 = 24;                           // chunks per atom (192 entries)
+    int lcap8 = 24;                           // chunks per atom (192 entries; grown from the density, or EMDEE_LIST_CHUNKS)
+    bool lcap8_forced = false;
     bool list_valid = false, use_list = true;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
@@ -410,7 +411,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     s->N = N;
     s->L = L;
     if (const char *e = getenv("EMDEE_LIST")) s->use_list = atoi(e) != 0;
-    if (const char *e = getenv("EMDEE_LIST_CHUNKS")) s->lcap8 = std::max(4, atoi(e));
+    if (const char *e = getenv("EMDEE_LIST_CHUNKS")) { s->lcap8 = std::max(4, atoi(e)); s->lcap8_forced = true; }
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NBUF")) s->want_nbuf = atoi(e) >= 3 ? 3 : 2;
@@ -1346,6 +1347,15 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         if (audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list kernels do not audit");
         if (!(s->grid_ok && s->use_list && s->ntypes > 0)) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: pair list requested for a system that cannot use one");
         const int64_t slots = (int64_t)s->fc_nblocks * s->fc_gmax;
+        if (!s->lcap8_forced) {
+            // chunks per atom from the mean density: entries inside rc + skin (+ FP16 margin), 40 % head-room for
+            // density fluctuations, at least 24 chunks; a denser neighbourhood than that raises the overflow error
+            const double rl = s->cutoff + s->skin + 0.05;
+            const double mean = (double)s->N / (s->L * s->L * s->L) * 4.18879 * rl * rl * rl;
+            const int want = std::max(24, (int)std::ceil(1.4 * mean / 8.0) + 2);
+            if (want > s->lcap8) { s->lcap8 = want; s->list_slots = 0; }      // re-allocate below
+            a.lcap8 = s->lcap8;
+        }
         if (slots > s->list_slots) {
             dev_free(s->list8); dev_free(s->list_n); dev_free(s->homeidx);
             s->list_slots = slots + slots / 4;
