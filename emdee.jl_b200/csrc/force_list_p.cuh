@@ -98,8 +98,8 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
             const int brick = blockIdx.x + k * gridDim.x;
-            if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);                 // empty[b]: the consumers are done with this buffer
             if (brick >= nbricks) {
+                if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
                 bar_arrive(1 + b, FLP_THREADS);
@@ -112,54 +112,23 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const int2 *recipe = a.recipe + (size_t)bid * a.rcap;
             const int n1 = min(hdr_n1, cap1);                         // staged atoms + 1
             const int nh = hdr_nh;
-            {   // one brick ahead: header into registers, recipe into L2 (it streams from HBM; the coordinates it points
-                // at were written by k_vv just before this kernel and are L2 hits)
-                const int nb = brick + gridDim.x;
-                if (nb < nbricks) {
-                    const int nbid = FC_BRICK_OF(a, nb);
-                    hdr_n1 = a.brickhdr[2 * nbid];
-                    hdr_nh = a.brickhdr[2 * nbid + 1];
-                    const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
-                    for (int t = tid * 128; t < a.rcap * 8; t += PN * 128) prefetch_l2(nr + t);
-                }
-            }
-            if (tid == 0) {
-                B.pxy[0] = make_double2(1e30, 1e30);
-                B.pz[0] = 1e30;
-                const __half2 far = __floats2half2_rn(60000.0f, 60000.0f), farz = __floats2half2_rn(60000.0f, 0.0f);
-                B.ph[0] = make_uint2(*reinterpret_cast<const unsigned *>(&far), *reinterpret_cast<const unsigned *>(&farz));
-                if (MULTI) B.ptyp[0] = 0;
-                B.scal[0] = nh;
-                B.scal[1] = n1;
-                B.scal[3] = 0;              // task cursor
-                B.scal[4] = brick;
-            }
-            {   // the consumers claim this brick's tasks dynamically: bring every group's entry counts and first chunks into L2
-                const int ng = min((nh + 31) >> 5, a.gmax);
-                for (int t = tid; t < ng * 8; t += PN) {      // 2 chunks x 512 B = 8 lines of 128 B per group
-                    const size_t gs = (size_t)bid * a.gmax + (t >> 3);
-                    const int part = t & 7;
-                    if (part == 0) prefetch_l2(a.list_n + gs * 32);
-                    prefetch_l2(reinterpret_cast<const unsigned char *>(a.list8 + gs * a.lcap8 * 32) + part * 128);
-                }
-            }
             const double invM = 1.0 / g.M;
             const int ux0 = bg.hx0 - R, uy0 = bg.hy0 - R, uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0) - R;
             const double bcx = ((double)bg.hx0 + 0.5 * bg.nhx) * invM, bcy = ((double)bg.hy0 + 0.5 * bg.nhy) * invM,
                          bcz = ((double)(uz0 + R) + 0.5 * bg.nhz) * invM;
-            constexpr int U = 6;
-            for (int i0 = 1 + tid; i0 < n1; i0 += U * PN) {
-                int2 rc[U];
-                double sx[U], sy[U], sz[U];
+            constexpr int U = 9;                // atoms per thread in flight: ~2300 staged atoms / 128 threads = two batches
+            int2 rc[U];
+            double sx[U], sy[U], sz[U];
+            auto load_batch = [&](int i0) {
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const int i = i0 + u * PN;
                     rc[u] = i < n1 ? recipe[i] : make_int2(0, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x];
-                }
+                for (int u = 0; u < U; u++) { sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x]; }
+            };
+            auto store_batch = [&](int i0) {
 #pragma unroll
                 for (int u = 0; u < U; u++) {
                     const int i = i0 + u * PN;
@@ -176,6 +145,46 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                     B.ph[i] = make_uint2(*reinterpret_cast<const unsigned *>(&hxy), *reinterpret_cast<const unsigned *>(&hz0h));
                     if (MULTI) B.ptyp[i] = (uint8_t)a.type[rc[u].x];
                 }
+            };
+            // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
+            // time, and the staging latency that follows the hand-over is what the consumers then wait for
+            load_batch(1 + tid);
+            {   // one brick ahead: header into registers, recipe into L2 (it streams from HBM; the coordinates it points
+                // at were written by k_vv just before this kernel and are L2 hits)
+                const int nb = brick + gridDim.x;
+                if (nb < nbricks) {
+                    const int nbid = FC_BRICK_OF(a, nb);
+                    hdr_n1 = a.brickhdr[2 * nbid];
+                    hdr_nh = a.brickhdr[2 * nbid + 1];
+                    const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
+                    for (int t = tid * 128; t < a.rcap * 8; t += PN * 128) prefetch_l2(nr + t);
+                }
+            }
+            {   // the consumers claim this brick's tasks dynamically: bring every group's entry counts and first chunks into L2
+                const int ng = min((nh + 31) >> 5, a.gmax);
+                for (int t = tid; t < ng * 8; t += PN) {      // 2 chunks x 512 B = 8 lines of 128 B per group
+                    const size_t gs = (size_t)bid * a.gmax + (t >> 3);
+                    const int part = t & 7;
+                    if (part == 0) prefetch_l2(a.list_n + gs * 32);
+                    prefetch_l2(reinterpret_cast<const unsigned char *>(a.list8 + gs * a.lcap8 * 32) + part * 128);
+                }
+            }
+            if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);       // empty[b]: the consumers are done with this buffer
+            if (tid == 0) {
+                B.pxy[0] = make_double2(1e30, 1e30);
+                B.pz[0] = 1e30;
+                const __half2 far = __floats2half2_rn(60000.0f, 60000.0f), farz = __floats2half2_rn(60000.0f, 0.0f);
+                B.ph[0] = make_uint2(*reinterpret_cast<const unsigned *>(&far), *reinterpret_cast<const unsigned *>(&farz));
+                if (MULTI) B.ptyp[0] = 0;
+                B.scal[0] = nh;
+                B.scal[1] = n1;
+                B.scal[3] = 0;              // task cursor
+                B.scal[4] = brick;
+            }
+            store_batch(1 + tid);
+            for (int i0 = 1 + tid + U * PN; i0 < n1; i0 += U * PN) {
+                load_batch(i0);
+                store_batch(i0);
             }
             __threadfence_block();
             bar_arrive(1 + b, FLP_THREADS);                           // full[b]
