@@ -101,10 +101,11 @@ def load():
     """Load the shared library and declare every entry point of include/emdee_b200.h."""
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("EMDEE_B200_LIB", LIB_PATH)      # the same override the Julia shim reads
+        if not os.path.exists(path):
             raise ImportError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                              "(there is no CPU fallback for the nonbonded path)" % LIB_PATH)
-        lib = C.CDLL(LIB_PATH)
+                              "(there is no CPU fallback for the nonbonded path)" % path)
+        lib = C.CDLL(path)
         for name, args in SIGNATURES.items():
             fn = getattr(lib, name)
             fn.restype = _i

@@ -26,7 +26,9 @@
 #define FL_QCAP 48          // per-lane stack entries
 #define FL_MINPOP 8
 #define FL_MAX_BLOCK 256
+#ifndef FL_AHEAD
 #define FL_AHEAD 4          // list chunks requested into L2 ahead of the register loads
+#endif
 
 __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 

@@ -15,7 +15,9 @@
 #include "force_list.cuh"
 
 #define FLP_THREADS 512
+#ifndef FLP_NPROD
 #define FLP_NPROD 4
+#endif
 #define FLP_NCONS (FLP_THREADS / 32 - FLP_NPROD)
 #define FLP_QS (FLP_NCONS * 32)          // row stride of the consumers' stacks
 
