@@ -38,6 +38,7 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_PAIR = 71
 BYTES_FORCE_EVAL = 80          # B/atom: read x,y,z + LJ params, write f, e, w
+BYTES_LIST_STEP = 280          # B/atom-step of the pair-list stepping kernel: 176 list + 54 recipe + 24 positions + 24 forces
 BYTES_VV = 120                 # B/atom-step: read r,v,f, write r,v
 BYTES_REBIN = 72               # B/atom-rebin
 
@@ -280,7 +281,8 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     rebins = kinds[1][1] if kinds[1][1] > 0 else (args.steps / args.rebin_every if args.rebin_every > 0 else 0)
-    step_bytes = nloc * (BYTES_FORCE_EVAL - 16 + BYTES_VV) + nloc * BYTES_REBIN * rebins / args.steps   # forces only: no e,w
+    force_bytes = BYTES_LIST_STEP if dom == 2 else BYTES_FORCE_EVAL - 16                                # forces only: no e,w
+    step_bytes = nloc * (force_bytes + BYTES_VV) + nloc * BYTES_REBIN * rebins / args.steps
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
