@@ -143,7 +143,6 @@ struct emdee_system {
     int fl_block = 192;                       // block size of k_force_list
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
-    int fl_nbuf = 2, want_nbuf = 3;                       // three when they fit
     bool fl_fuse = true;                                  // walk and drain share a basic block
     int reserve_sms = 0, nccl_sms = 0;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS; measured at 4 GPUs: what the exchange gains the interior launch loses)
     size_t fl_smem = 0;
@@ -160,11 +159,8 @@ struct emdee_system {
     bool list_valid = false, use_list = true;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
-    double *partial = nullptr;
-    int64_t partial_cap = 0;
     double2 *ljtab = nullptr;                 // pair table of the LJ parameter classes
     int ntypes = 0;                           // 0: too many classes, kernels gather per-atom parameters
-    double *totals = nullptr;                 // device {E, W}
     unsigned long long *digest = nullptr;     // device {count, sum, xor} + pair counter at [3]
     int *err = nullptr;                       // device error flag
     int *brick_max = nullptr;
@@ -414,7 +410,6 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_LIST_CHUNKS")) { s->lcap8 = std::max(4, atoi(e)); s->lcap8_forced = true; }
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
-    if (const char *e = getenv("EMDEE_NBUF")) s->want_nbuf = atoi(e) >= 3 ? 3 : 2;
     if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
@@ -430,7 +425,6 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->slot_of_id, N));
     A(dev_alloc(&s->order, s->cap));
     A(dev_alloc(&s->src_of_new, s->cap));
-    A(dev_alloc(&s->totals, 2));
     A(dev_alloc(&s->maxd2, 2));
     A(dev_alloc(&s->digest, 4));
     A(dev_alloc(&s->err, 1));
@@ -469,7 +463,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     for (int k = 0; k < 2; k++) { dev_free(s->gcell[k]); dev_free(s->lcell[k]); }
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
-    dev_free(s->partial); dev_free(s->ljtab); dev_free(s->totals); dev_free(s->digest); dev_free(s->maxd2);
+    dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
@@ -785,15 +779,8 @@ static int choose_bricks(emdee_system *s)
         s->fl_block = lblock;
         s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
         s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin;
-        s->fl_nbuf = s->want_nbuf == 3 && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 3) <= c->smem_optin ? 3 : 2;
         s->fc_typed = typed;
         s->fc_nblocks = g.nbx * g.nby * g.nbz;
-        const int64_t nwarps = (int64_t)s->fc_nblocks * (block / 32);
-        if (nwarps > s->partial_cap) {
-            dev_free(s->partial);
-            s->partial_cap = nwarps;
-            EMDEE_TRY(dev_alloc(&s->partial, (size_t)2 * s->partial_cap));
-        }
         return EMDEE_OK;
     };
     // keep the previous configuration while it fits and the cells hold about as many atoms as when it was chosen
