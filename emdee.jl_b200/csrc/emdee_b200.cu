@@ -125,6 +125,7 @@ struct emdee_system {
     int32_t *count = nullptr, *cell_start = nullptr, *fill = nullptr, *order = nullptr, *src_of_new = nullptr;
     int32_t *block_sum = nullptr, *maxpop = nullptr;
     int64_t steps_since_bin = 0;
+    int *brick_counter = nullptr;             // device: brick cursor of the persistent kernel
     unsigned *maxd2 = nullptr;                // device: max |r - r_bin|^2 since the last binning (float bits), adaptive re-binning
     // slab decomposition (nranks > 1)
     bool decomposed = false;
@@ -426,6 +427,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->order, s->cap));
     A(dev_alloc(&s->src_of_new, s->cap));
     A(dev_alloc(&s->maxd2, 2));
+    A(dev_alloc(&s->brick_counter, 2));
     A(dev_alloc(&s->digest, 4));
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
@@ -463,7 +465,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     for (int k = 0; k < 2; k++) { dev_free(s->gcell[k]); dev_free(s->lcell[k]); }
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
-    dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2);
+    dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2); dev_free(s->brick_counter);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
@@ -1223,7 +1225,10 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
     // registers of its SM, so NCCL could not start before the first block retires otherwise)
     const int sms = std::max(1, s->ctx->sm_count - s->reserve_sms);
-    kern<<<std::min(nblocks, sms), FLP_THREADS, smem, s->ctx->stream>>>(a, nblocks, store_f ? 1 : 0);
+    CUDA_TRY(cudaMemsetAsync(s->brick_counter, 0, sizeof(int), s->ctx->stream));
+    CellArgs ac = a;
+    ac.brick_counter = s->brick_counter;
+    kern<<<std::min(nblocks, sms), FLP_THREADS, smem, s->ctx->stream>>>(ac, nblocks, store_f ? 1 : 0);
     s->ctx->launches++;
     return check_launch("k_force_list_p");
 }

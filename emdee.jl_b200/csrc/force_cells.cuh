@@ -81,6 +81,7 @@ struct CellArgs {
     uint16_t *homeidx;                // homeidx[(brick*gmax + h/32)*32 + h%32] = staged index + 1 of home atom h
     int *brickhdr;                    // brickhdr[2*brick] = staged atoms + 1, [2*brick+1] = home atoms
     int rcap;
+    int *brick_counter;               // persistent kernel: bricks beyond the first of each block are claimed here (zeroed per launch)
 };
 
 // Brick handled by launch index i (a launch covers one or two contiguous ranges of bricks).

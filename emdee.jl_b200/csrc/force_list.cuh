@@ -23,8 +23,12 @@
 
 #include "force_cells.cuh"
 
+#ifndef FL_QCAP
 #define FL_QCAP 48          // per-lane stack entries
-#define FL_MINPOP 8
+#endif
+#ifndef FL_MINPOP
+#define FL_MINPOP 8          // a partial drain pops at least this many entries per lane
+#endif
 #define FL_MAX_BLOCK 256
 #ifndef FL_AHEAD
 #define FL_AHEAD 4          // list chunks requested into L2 ahead of the register loads

@@ -3,7 +3,8 @@
 // ncu on k_force_list (profiles/): a third of all warp time went into staging a brick (three dependent global
 // round trips and two block barriers per block) during which the block's FP64 work stands still, and shared
 // memory allowed only two blocks per SM, so staging was overlapped by at most one other block.  Here one
-// 512-thread block per SM stays resident and walks over bricks (brick = blockIdx.x + k * gridDim.x):
+// 512-thread block per SM stays resident and walks over bricks (the first one is blockIdx.x, later ones are claimed
+// from a global counter, so the SMs finish within one brick of each other):
 //   * 4 producer warps stage brick k+1 into one of two shared-memory buffers (cell table, prefix scan, atoms in
 //     the brick's frame in FP64 + FP16) while
 //   * 12 consumer warps walk the pair list of brick k (same walk / drain as k_force_list, ILP 4).
@@ -81,6 +82,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
     double2 *ljt = reinterpret_cast<double2 *>(smem_raw + NBUF * bufsz);
     uint16_t *qguard = reinterpret_cast<uint16_t *>(ljt + a.ntypes * a.ntypes);
     uint16_t *queue = qguard + FLP_QS;
+    __shared__ int claimed[2];                 // the producers' next brick (double-buffered over the brick parity)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < a.ntypes * a.ntypes; t += FLP_THREADS) ljt[t] = a.ljtab[t];
@@ -96,10 +98,10 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             hdr_n1 = a.brickhdr[2 * FC_BRICK_OF(a, (int)blockIdx.x)];
             hdr_nh = a.brickhdr[2 * FC_BRICK_OF(a, (int)blockIdx.x) + 1];
         }
+        int brick = blockIdx.x;
         for (int k = 0;; k++) {
             const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
-            const int brick = blockIdx.x + k * gridDim.x;
             if (brick >= nbricks) {
                 if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);
                 if (tid == 0) B.scal[4] = -1;
@@ -151,9 +153,11 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
             // time, and the staging latency that follows the hand-over is what the consumers then wait for
             load_batch(1 + tid);
+            if (tid == 0) claimed[k & 1] = gridDim.x + atomicAdd(a.brick_counter, 1);
+            bar_sync(5, PN);
+            const int nb = claimed[k & 1];
             {   // one brick ahead: header into registers, recipe into L2 (it streams from HBM; the coordinates it points
                 // at were written by k_vv just before this kernel and are L2 hits)
-                const int nb = brick + gridDim.x;
                 if (nb < nbricks) {
                     const int nbid = FC_BRICK_OF(a, nb);
                     hdr_n1 = a.brickhdr[2 * nbid];
@@ -190,6 +194,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             }
             __threadfence_block();
             bar_arrive(1 + b, FLP_THREADS);                           // full[b]
+            brick = nb;
         }
         return;
     }

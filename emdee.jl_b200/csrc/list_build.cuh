@@ -24,6 +24,9 @@
 #include "force_cells.cuh"
 
 #define LB_MAX_BLOCK 256
+#ifndef LB_MIN_BLOCKS
+#define LB_MIN_BLOCKS 3
+#endif
 #define LB_ROW_ENTRIES 48                         // capacity of a lane's row
 #define LB_ROW_BYTES (LB_ROW_ENTRIES * 2 + 16)    // 112 B = 28 words: eight distinct banks over the lanes
 #define LB_FLUSH_AT 28                            // flush when a lane holds this many entries (up to 18 may arrive before the next check)
@@ -42,7 +45,7 @@ __host__ __device__ inline size_t lb_smem_bytes(int cap, int ncs_max, int block,
 }
 
 template <bool EXCL>
-__global__ void __launch_bounds__(LB_MAX_BLOCK, 3) k_list_build(CellArgs a)
+__global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(CellArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;

@@ -1,3 +1,4 @@
+# A/B of compile-time tuning variants (build/libemdee_<name>.so built with -D...; selected with EMDEE_B200_LIB).
 cd /root/repo
 B="timeout 300 python bench.py --no-cpu-baseline --e2e-iters 1"
 run() { # name, env..., extra args after --
@@ -7,6 +8,4 @@ run() { # name, env..., extra args after --
 import json; d=json.loads(open('gpurun_out/s_$name.json').read().strip().splitlines()[-1]); print('ms/step %.3f'%(d['ms_per_step']))" 2>&1 | tail -1)"
 }
 run base $B
-for v in np3 np2 np5 ah8; do run $v EMDEE_B200_LIB=/root/repo/build/libemdee_$v.so $B; done
-run np3_s40 EMDEE_B200_LIB=/root/repo/build/libemdee_np3.so $B --skin 0.4
-run np3_s50 EMDEE_B200_LIB=/root/repo/build/libemdee_np3.so $B --skin 0.5
+for v in "$@"; do run $v EMDEE_B200_LIB=/root/repo/build/libemdee_$v.so $B; done
