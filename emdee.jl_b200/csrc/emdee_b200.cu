@@ -126,6 +126,12 @@ struct emdee_system {
     int32_t *block_sum = nullptr, *maxpop = nullptr;
     int64_t steps_since_bin = 0;
     int *brick_counter = nullptr;             // device: brick cursor of the persistent kernel
+    // velocity-Verlet fused into the stepping kernel (EMDEE_FUSE_VV): second buffer of scaled positions, per-launch mode
+    bool fuse_vv = false;
+    double *s_alt[3] = {nullptr, nullptr, nullptr};
+    int vv_mode = 0, vv_check_skin = 0;
+    bool vv_track = false;
+    double vv_dt = 0;
     unsigned *maxd2 = nullptr;                // device: max |r - r_bin|^2 since the last binning (float bits), adaptive re-binning
     // slab decomposition (nranks > 1)
     bool decomposed = false;
@@ -412,6 +418,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_ILP8")) s->fl_ilp8 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_FUSE_VV")) s->fuse_vv = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -466,6 +473,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
     dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2); dev_free(s->brick_counter);
+    for (int k = 0; k < 3; k++) dev_free(s->s_alt[k]);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
@@ -1220,6 +1228,7 @@ template <bool MULTI, bool COUNT, bool EW>
 static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
 {
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
+    if (!COUNT && !EW && s->vv_mode != 0) kern = k_force_list_p<MULTI, false, 2, false, true, true>;
     const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
@@ -1228,6 +1237,15 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     CUDA_TRY(cudaMemsetAsync(s->brick_counter, 0, sizeof(int), s->ctx->stream));
     CellArgs ac = a;
     ac.brick_counter = s->brick_counter;
+    ac.vv_mode = 0;
+    if (!COUNT && !EW && s->vv_mode != 0) {
+        AtomArrays &A = s->A[s->cur];
+        ac.vv_mode = s->vv_mode; ac.vv_dt = s->vv_dt; ac.vv_half_skin2 = 0.25 * s->skin * s->skin;
+        for (int k = 0; k < 3; k++) { ac.vv_v[k] = A.v[k]; ac.vv_r[k] = A.r[k]; ac.vv_snew[k] = s->s_alt[k]; ac.vv_rb[k] = A.rb[k]; }
+        ac.vv_mass = A.mass;
+        ac.vv_maxd2 = s->vv_track ? s->maxd2 : nullptr;
+        ac.vv_check_skin = s->vv_check_skin;
+    }
     kern<<<std::min(nblocks, sms), FLP_THREADS, smem, s->ctx->stream>>>(ac, nblocks, store_f ? 1 : 0);
     s->ctx->launches++;
     return check_launch("k_force_list_p");
@@ -1728,6 +1746,52 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     if (s->last_mode != EMDEE_CUTOFF) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: forces must come from EMDEE_CUTOFF mode");
     if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
     const bool adaptive = rebin_every < 0 && s->skin > 0;      // rebin_every < 0: re-bin when the skin is used up
+    if (s->fuse_vv && c->nranks == 1 && list_capable(s) && s->fl_persistent && nsteps > 0) {
+        // One kernel per step: the stepping kernel's epilogue finishes step n (second half-kick) and starts step n+1
+        // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
+        // k_vv only starts the first step of the call.
+        for (int k = 0; k < 3; k++)
+            if (!s->s_alt[k]) EMDEE_TRY(dev_alloc(&s->s_alt[k], (size_t)s->cap));
+        bool drifted = false;
+        for (int64_t st = 0; st < nsteps; st++) {
+            bool rebin = !s->list_valid || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
+            if (!drifted) EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1, adaptive && !rebin));
+            if (adaptive && !rebin) {
+                unsigned bits = 0;
+                CUDA_TRY(cudaMemcpyAsync(&bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                float d2max;
+                memcpy(&d2max, &bits, 4);
+                rebin = (double)d2max > 0.25 * s->skin * s->skin;
+            }
+            s->kick_pending = false;
+            s->steps_since_bin++;
+            if (rebin) EMDEE_TRY(do_bin(s, s->ndiv));
+            if (!(list_capable(s) && s->fl_persistent)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: the re-binning left the fused path unusable (EMDEE_FUSE_VV=0)");
+            if (!s->list_valid) {
+                EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1));
+                s->list_valid = true;
+            }
+            const bool last = st == nsteps - 1;
+            const bool next_rebin = rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every;
+            s->vv_mode = last ? 1 : 2;
+            s->vv_dt = dt;
+            s->vv_check_skin = (!adaptive && !next_rebin) ? 1 : 0;
+            s->vv_track = adaptive;
+            const int rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 2);
+            s->vv_mode = 0;
+            EMDEE_TRY(rc_);
+            if (!last) {
+                AtomArrays &Ac = s->A[s->cur];
+                for (int k = 0; k < 3; k++) std::swap(Ac.s[k], s->s_alt[k]);      // the drifted positions become current
+                drifted = true;
+            }
+        }
+        s->kick_pending = false;
+        s->last_bitmask = EMDEE_FORCES;
+        s->forces_valid = true;
+        return EMDEE_OK;
+    }
     for (int64_t st = 0; st < nsteps; st++) {
         // A pair list must be built at the positions the cells were binned at (both rely on "no atom moved
         // more than skin/2 since the binning"), so a missing list forces a re-binning on this step.

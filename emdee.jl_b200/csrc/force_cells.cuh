@@ -81,6 +81,15 @@ struct CellArgs {
     uint16_t *homeidx;                // homeidx[(brick*gmax + h/32)*32 + h%32] = staged index + 1 of home atom h
     int *brickhdr;                    // brickhdr[2*brick] = staged atoms + 1, [2*brick+1] = home atoms
     int rcap;
+    // velocity-Verlet fused into the stepping kernel's epilogue (VV variant of k_force_list_p): the atom's own thread
+    // completes step n (second half-kick) and starts step n+1 (first half-kick, drift) as soon as its force is known;
+    // the new scaled positions go to a second buffer because other bricks still stage the old ones
+    int vv_mode;                      // 1: second half-kick only (last step), 2: + first half-kick and drift of the next step
+    double vv_dt, vv_half_skin2;
+    double *vv_v[3], *vv_r[3], *vv_snew[3];
+    const double *vv_rb[3], *vv_mass;
+    unsigned *vv_maxd2;               // adaptive re-binning (may be null)
+    int vv_check_skin;
     int *brick_counter;               // persistent kernel: bricks beyond the first of each block are claimed here (zeroed per launch)
 };
 

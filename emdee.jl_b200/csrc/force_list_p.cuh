@@ -70,7 +70,9 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // FUSE: from the second chunk on, every walk iteration also pops and evaluates ILP stack entries in the same basic
 // block, so the scheduler fills the FP64 dependency stalls of the drain with the FP16 tests and stack pushes of the
 // walk (ncu: `wait` was the top stall of the consumers with walk and drain as separate loops).
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE>
+// VV: the epilogue also advances the atom (k_vv's arithmetic, one fma per line, same rounding): v += h f [step n done];
+// v += h f; r += dt v; s' = r/L [step n+1 started], so a step is ONE kernel instead of k_vv + force kernel.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false>
 __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = 4;
@@ -247,6 +249,13 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const int hh = active ? h : (grp << 5);
             const int me = a.homeidx[((size_t)bid * a.gmax + grp) * 32 + (hh & 31)];
             const int slot_i = recipe[me].x;
+            if (VV && active) {      // what the epilogue will read: into L2 now, so that it is not an HBM round trip then
+#pragma unroll
+                for (int c3 = 0; c3 < 3; c3++) {
+                    prefetch_l2(a.vv_v[c3] + slot_i); prefetch_l2(a.vv_r[c3] + slot_i); prefetch_l2(a.vv_rb[c3] + slot_i);
+                }
+                prefetch_l2(a.vv_mass + slot_i);
+            }
             const double2 q0 = pxy[me];
             const double pix = q0.x, piy = q0.y, piz = pz[me];
             const uint2 hme = ph[me];
@@ -353,6 +362,31 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             if (active) {
                 if (store_f) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
                 if (EW) { a.en[slot_i] = 0.5 * e; a.vir[slot_i] = 0.5 * w; }
+            }
+            if (VV) {
+                double d2 = 0;
+                if (active) {
+                    const double hk = __ddiv_rn(0.5 * a.vv_dt, a.vv_mass[slot_i]);
+                    const double f3[3] = {fx, fy, fz};
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; c3++) {
+                        double v = __fma_rn(hk, f3[c3], a.vv_v[c3][slot_i]);          // second half-kick of this step
+                        if (a.vv_mode == 2) {
+                            v = __fma_rn(hk, f3[c3], v);                              // first half-kick of the next step
+                            const double r = __fma_rn(a.vv_dt, v, a.vv_r[c3][slot_i]);   // drift
+                            a.vv_r[c3][slot_i] = r;
+                            a.vv_snew[c3][slot_i] = __ddiv_rn(r, a.L);
+                            const double d = r - a.vv_rb[c3][slot_i];
+                            d2 = fma(d, d, d2);
+                        }
+                        a.vv_v[c3][slot_i] = v;
+                    }
+                    if (a.vv_mode == 2 && a.vv_check_skin && d2 > a.vv_half_skin2) atomicCAS(a.err, 0, 3);
+                }
+                if (a.vv_mode == 2 && a.vv_maxd2) {
+                    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(__double2float_ru(d2)));
+                    if (lane == 0 && m > *a.vv_maxd2) atomicMax(a.vv_maxd2, m);
+                }
             }
             grp = ngrp;
         }

@@ -250,7 +250,10 @@ def test_exclusions_molecular(em, oracle, dioxin_water):
     s.close()
 
 
-def test_velocity_verlet(em, oracle):
+@pytest.mark.parametrize("fuse_vv", [0, 1])
+def test_velocity_verlet(em, oracle, fuse_vv, monkeypatch):
+    """fuse_vv = 1: kick and drift run in the stepping kernel's epilogue (one kernel per step) instead of k_vv."""
+    monkeypatch.setenv("EMDEE_FUSE_VV", str(fuse_vv))
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
     atoms = em.workloads.lj_fluid_atoms(N)
@@ -308,7 +311,7 @@ def test_velocity_verlet(em, oracle):
     s.close()
 
 
-@pytest.mark.parametrize("variant", ["persistent", "block_per_brick", "ndiv2", "no_list"])
+@pytest.mark.parametrize("variant", ["persistent", "fused_vv", "block_per_brick", "ndiv2", "no_list"])
 def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     """The stepping path (pair list built on the re-binning step, walked by k_force_list_p afterwards): after
     steps that only walked the list, forces and the evaluated pair count equal the oracle's at the same
@@ -316,6 +319,7 @@ def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     so the count is the sharp check.  Variants: the persistent kernel (default), the block-per-brick kernel
     it falls back to when two staging buffers do not fit, cells of half the edge (ndiv = 2), and stepping
     without a list (window scan on every step)."""
+    monkeypatch.setenv("EMDEE_FUSE_VV", "1" if variant == "fused_vv" else "0")
     if variant == "block_per_brick":
         monkeypatch.setenv("EMDEE_PERSIST", "0")
     if variant == "no_list":
