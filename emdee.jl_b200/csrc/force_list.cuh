@@ -1,7 +1,8 @@
 // force_list.cuh -- the stepping kernel: Lennard-Jones forces from the stored pair list, FP64.
 //
-// Runs on every velocity-Verlet step between two re-binnings (k_force_cells MODE 1 builds the list on the
-// re-binning step).  Same decomposition as k_force_cells -- one block per home brick, the brick and its
+// Block-per-brick form; the default is the persistent form in force_list_p.cuh (same walk / drain), this one runs
+// when two staging buffers do not fit in shared memory (EMDEE_PERSIST=0 forces it).  k_list_build (list_build.cuh)
+// builds the list on a re-binning step.  Same decomposition as k_force_cells -- one block per home brick, the brick and its
 // halo staged in shared memory in the same order, so a list entry (staged index + 1) means the same atom --
 // but organised around what ncu showed to bound the kernel (profiles/): the FP64 pipe, the shared-memory
 // crossbar (a random 16-byte gather costs ~10 wavefronts per warp) and the issue slots, in that order.

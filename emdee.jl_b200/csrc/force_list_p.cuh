@@ -5,8 +5,10 @@
 // memory allowed only two blocks per SM, so staging was overlapped by at most one other block.  Here one
 // 512-thread block per SM stays resident and walks over bricks (the first one is blockIdx.x, later ones are claimed
 // from a global counter, so the SMs finish within one brick of each other):
-//   * 4 producer warps stage brick k+1 into one of two shared-memory buffers (cell table, prefix scan, atoms in
-//     the brick's frame in FP64 + FP16) while
+//   * 4 producer warps stage brick k+1 into one of two shared-memory buffers from the per-brick staging recipe that
+//     k_list_build wrote at the last re-binning (slot and staged-cell coordinates of every staged atom: one coalesced
+//     load, three gathers and ~30 instructions per atom, no cell table / prefix scan / search on the step path; the
+//     first batch of loads is issued before the buffer is handed over), while
 //   * 12 consumer warps walk the pair list of brick k (same walk / drain as k_force_list, ILP 4).
 // Hand-over by named barriers (bar.arrive / bar.sync): full[b] producers -> consumers, empty[b] consumers ->
 // producers; no block-wide barrier after the prologue.  A consumer warp that runs out of tasks in brick k moves
