@@ -25,7 +25,7 @@
 
 #define LB_MAX_BLOCK 256
 #ifndef LB_MIN_BLOCKS
-#define LB_MIN_BLOCKS 3
+#define LB_MIN_BLOCKS 4
 #endif
 #define LB_ROW_ENTRIES 48                         // capacity of a lane's row
 #define LB_ROW_BYTES (LB_ROW_ENTRIES * 2 + 16)    // 112 B = 28 words: eight distinct banks over the lanes
