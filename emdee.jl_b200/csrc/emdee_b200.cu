@@ -151,7 +151,9 @@ struct emdee_system {
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
     bool fl_fuse = true;                                  // walk and drain share a basic block
-    int reserve_sms = 0, nccl_sms = 0;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS; measured at 4 GPUs: what the exchange gains the interior launch loses)
+    int reserve_sms = 0, nccl_sms = 4;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS).
+                                                          // With bricks claimed dynamically every SM is busy until the launch ends, so NCCL's kernel would
+                                                          // only start then; measured at 2 GPUs: halo wait 85 -> 3 us, interior +14 us, step 1.136 -> 1.083 ms
     size_t fl_smem = 0;
     int fc_gmax = 0;                          // 32-atom groups per brick (pair-list addressing)
     uint4 *list8 = nullptr;                   // pair list: chunks of 8 x uint16 (staged index + 1) per home atom
