@@ -80,6 +80,7 @@ SIGNATURES = {
     "emdee_pair_set_digest": [_p, _p],
     "emdee_list_pair_count": [_p, _p],
     "emdee_profile_kind": [_p, _i, _p, _p],
+    "emdee_fp16_threshold": [_p, _d, _p],
     "emdee_vv_step": [_p, _d, _i64, _i],
     "emdee_kinetic_energy": [_p, C.POINTER(_d)],
     "emdee_synchronize": [_p],

@@ -1287,6 +1287,33 @@ static int launch_cells(emdee_system *s, const CellArgs &a, int nb, bool F, bool
     return s->ntypes > 0 ? launch_cells_ty<true>(s, a, nb, F, EW, EXCL, AUDIT) : launch_cells_ty<false>(s, a, nb, F, EW, EXCL, AUDIT);
 }
 
+// FP16 pre-culls (k_force_list*, k_list_build): a pair with r <= rcut must pass r2_fp16 <= threshold.
+//   stored coordinates: |c_k| <= h_k (half extent of the staged box + skin/2), rounded to FP16 (through FP32):
+//     half an ulp16(h_k) per atom; the separation rounds once more: ulp16(rcut)/2   ->  delta_k
+//   r2 of the stored separations <= rcut^2 + 2 rcut |delta| + |delta|^2            (Cauchy-Schwarz)
+//   at most four FP16 roundings in the squares and sums: 4.2 u (rcut + |delta|)^2, u = 2^-11
+// (5 % head-room on the error terms; the device rounds the threshold up to FP16.)
+static float fp16_threshold(const double hext[3], double rcut)
+{
+    auto ulp16 = [](double v) { return std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(v))) - 10); };
+    const double u = std::ldexp(1.0, -11);
+    double d2 = 0;
+    for (int k = 0; k < 3; k++) {
+        const double dk = 1.001 * ulp16(hext[k]) + 0.5 * ulp16(rcut);
+        d2 += dk * dk;
+    }
+    const double dn = std::sqrt(d2);
+    const double err = 2.0 * rcut * dn + d2 + 4.2 * u * (rcut + dn) * (rcut + dn);
+    return (float)((rcut * rcut + 1.05 * err) * (1.0 + u));
+}
+// host-only helper behind the CPU test of that bound (no GPU involved)
+extern "C" int emdee_fp16_threshold(const double half_extent[3], double rcut, float *threshold)
+{
+    if (!half_extent || !threshold || !(rcut > 0)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_fp16_threshold: bad arguments");
+    *threshold = fp16_threshold(half_extent, rcut);
+    return EMDEE_OK;
+}
+
 // halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
 // communication stream while the interior brick layers compute; the boundary layers wait for them.
 static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false, int mode = 0)
@@ -1331,27 +1358,10 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         a.fast.id2 = s->model.id2;
         a.fast.nrs2id2 = -s->model.rs2 * s->model.id2;
         a.fast.c60id2 = 60.0 * s->model.id2;
-        // FP16 pre-culls (k_force_list*, k_list_build): a pair with r <= rcut must pass r2_fp16 <= threshold.
-        //   stored coordinates: |c_k| <= h_k (half extent of the staged box + skin/2), rounded to FP16 (through FP32):
-        //     half an ulp16(h_k) per atom; the separation rounds once more: ulp16(rcut)/2   ->  delta_k
-        //   r2 of the stored separations <= rcut^2 + 2 rcut |delta| + |delta|^2            (Cauchy-Schwarz)
-        //   at most four FP16 roundings in the squares and sums: 4.2 u (rcut + |delta|)^2, u = 2^-11
-        // (5 % head-room on the error terms; the device rounds the threshold up to FP16.)
         const double hext[3] = {0.5 * (s->g.bx + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin,
                                 0.5 * (s->g.by + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin,
                                 0.5 * (s->g.bz + 2 * s->g.R) * a.cell_edge + 0.5 * s->skin};
-        auto ulp16 = [](double v) { return std::ldexp(1.0, std::max(-14, (int)std::floor(std::log2(v))) - 10); };
-        const double u = std::ldexp(1.0, -11);
-        auto thr16 = [&](double rcut) {
-            double d2 = 0;
-            for (int k = 0; k < 3; k++) {
-                const double dk = 1.001 * ulp16(hext[k]) + 0.5 * ulp16(rcut);
-                d2 += dk * dk;
-            }
-            const double dn = std::sqrt(d2);
-            const double err = 2.0 * rcut * dn + d2 + 4.2 * u * (rcut + dn) * (rcut + dn);
-            return (float)((rcut * rcut + 1.05 * err) * (1.0 + u));
-        };
+        auto thr16 = [&](double rcut) { return fp16_threshold(hext, rcut); };
         a.rc2h = thr16(s->cutoff);
         a.rl2h = thr16(s->cutoff + s->skin);
     }

@@ -113,6 +113,9 @@ int emdee_pair_set_digest(emdee_system *sys, uint64_t out[3]);
  * conservative, the final decision is the oracle's).  Needs a valid list, i.e. a preceding emdee_vv_step.
  * Returns -1 in *npairs when the system steps without a list (no skin, EMDEE_LIST=0, > 16 LJ classes). */
 int emdee_list_pair_count(emdee_system *sys, int64_t *npairs);
+/* Host-only: the conservative FP16 threshold the list kernels pre-cull with, for coordinates within +-half_extent[k]
+ * of a brick centre: every pair with r <= rcut satisfies r2_fp16 <= *threshold (tests/test_host_logic.py checks it). */
+int emdee_fp16_threshold(const double half_extent[3], double rcut, float *threshold);
 
 /* Velocity-Verlet (absent from the reference): nsteps of
  * v += dt/2m f ; r += dt v ; f = F(r) ; v += dt/2m f, re-binning every `rebin_every` steps
