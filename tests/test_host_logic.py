@@ -46,3 +46,24 @@ def test_fp16_precull_never_drops_a_pair(em, hext, rcut):
     # ... and it is tight enough to be useful: pairs 4 % beyond rcut are rejected more often than not
     cj2 = ci + 1.04 * (cj - ci)
     assert (_r2_fp16(ci, cj2) > thr).mean() > 0.5
+
+
+def test_cutoff_band_classification():
+    """pair_in_range (lj_pair.cuh): t = hi(r2) - (hi(rc2) - 1); t < 0 inside, t > 2 outside, else the exact path.
+    A decided pair must stay decided under any perturbation of r2 far larger than the ~1e-13 relative difference
+    between the brick-frame r2 and the oracle's rounding sequence."""
+    def hi(x):
+        return (np.asarray(x, dtype=np.float64).view(np.int64) >> 32).astype(np.int64)
+
+    rng = np.random.default_rng(3)
+    for rc in (2.5, 3.0, 10.0, 1.0, 2.0 ** 0.5):
+        rc2 = rc * rc
+        r2 = rc2 * (1.0 + (rng.random(200000) - 0.5) * 2e-5)
+        r2 = np.concatenate([r2, rc2 * (1.0 + (rng.random(200000) - 0.5) * 2.0)])
+        t = hi(r2) - (hi(rc2) - 1)
+        inside, outside = t < 0, t > 2
+        eps = 1e-9
+        assert (r2[inside] * (1 + eps) < rc2).all()
+        assert (r2[outside] * (1 - eps) > rc2).all()
+        band = ~inside & ~outside
+        assert (np.abs(r2[band] / rc2 - 1.0) < 4e-6).all()      # the exact path is taken only within ~3 * 2^-20 of rc2
