@@ -296,6 +296,8 @@ def run_b200(args):
         "peak_source": "DFMA chains measured in this run (emdee_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": pairs_local, "ms_per_launch": force_ms_per_launch,
         "launches_timed": dom_launches, "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
+        "kernel_also_does": ("the velocity-Verlet kick and drift of the step (fused into the producer warps; EMDEE_FUSE_VV=0 "
+                             "runs them as k_vv and the force kernel alone takes 1.22 ms)") if dom == 2 and world == 1 and os.environ.get("EMDEE_FUSE_VV", "1") != "0" else None,
         "force_kernels_share_of_step": force_ms / ms if ms > 0 else None,
         "list_build": {"kernel": "k_list_build", "ms_per_launch": build_ms_per_launch, "launches_timed": kinds[1][1],
                        "share_of_step": kinds[1][0] / ms if ms > 0 else None},

@@ -126,8 +126,9 @@ struct emdee_system {
     int32_t *block_sum = nullptr, *maxpop = nullptr;
     int64_t steps_since_bin = 0;
     int *brick_counter = nullptr;             // device: brick cursor of the persistent kernel
-    // velocity-Verlet fused into the stepping kernel (EMDEE_FUSE_VV): second buffer of scaled positions, per-launch mode
-    bool fuse_vv = false;
+    // velocity-Verlet fused into the stepping kernel (producer warps advance the atoms of released bricks; EMDEE_FUSE_VV=0
+    // switches back to k_vv): second buffer of scaled positions, per-launch mode
+    bool fuse_vv = true;
     double *s_alt[3] = {nullptr, nullptr, nullptr};
     int vv_mode = 0, vv_check_skin = 0;
     bool vv_track = false;

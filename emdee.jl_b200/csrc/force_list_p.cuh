@@ -103,6 +103,62 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             hdr_nh = a.brickhdr[2 * FC_BRICK_OF(a, (int)blockIdx.x) + 1];
         }
         int brick = blockIdx.x;
+        // VV: once the consumers have released a buffer, the forces of that brick's home atoms are final; the producers
+        // (idle ~40 % of the time) then complete the step for those atoms (second half-kick) and start the next one
+        // (first half-kick, drift, s = r/L into the second position buffer) -- k_vv's arithmetic, one fma per line.
+        int held_bid[NBUF], held_nh[NBUF];           // brick in each buffer whose atoms still have to be advanced
+#pragma unroll
+        for (int q = 0; q < NBUF; q++) { held_bid[q] = -1; held_nh[q] = 0; }
+        auto advance_atoms = [&](int vbid, int vnh) {
+            const int2 *vrecipe = a.recipe + (size_t)vbid * a.rcap;
+            unsigned dmax = 0;
+            constexpr int W = 3;                 // atoms per thread in flight: the chain home index -> slot -> data is pure latency
+            for (int h00 = 0; h00 < vnh; h00 += W * PN) {
+                int slot[W];
+                bool ok[W];
+                double mass[W], f3[W][3], v3[W][3], r3[W][3], rb3[W][3];
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    const int h = h00 + u * PN + tid;
+                    ok[u] = h < vnh && (h >> 5) < a.gmax;
+                    slot[u] = ok[u] ? (int)a.homeidx[((size_t)vbid * a.gmax + (h >> 5)) * 32 + (h & 31)] : 1;
+                }
+#pragma unroll
+                for (int u = 0; u < W; u++) slot[u] = vrecipe[slot[u]].x;
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    mass[u] = a.vv_mass[slot[u]];
+                    f3[u][0] = a.fx[slot[u]]; f3[u][1] = a.fy[slot[u]]; f3[u][2] = a.fz[slot[u]];
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; c3++) { v3[u][c3] = a.vv_v[c3][slot[u]]; r3[u][c3] = a.vv_r[c3][slot[u]]; rb3[u][c3] = a.vv_rb[c3][slot[u]]; }
+                }
+#pragma unroll
+                for (int u = 0; u < W; u++) {
+                    if (!ok[u]) continue;
+                    const double hk = __ddiv_rn(0.5 * a.vv_dt, mass[u]);
+                    double d2 = 0;
+#pragma unroll
+                    for (int c3 = 0; c3 < 3; c3++) {
+                        double v = __fma_rn(hk, f3[u][c3], v3[u][c3]);                // second half-kick of this step
+                        if (a.vv_mode == 2) {
+                            v = __fma_rn(hk, f3[u][c3], v);                           // first half-kick of the next step
+                            const double r = __fma_rn(a.vv_dt, v, r3[u][c3]);         // drift
+                            a.vv_r[c3][slot[u]] = r;
+                            a.vv_snew[c3][slot[u]] = __ddiv_rn(r, a.L);
+                            const double d = r - rb3[u][c3];
+                            d2 = fma(d, d, d2);
+                        }
+                        a.vv_v[c3][slot[u]] = v;
+                    }
+                    if (a.vv_mode == 2 && a.vv_check_skin && d2 > a.vv_half_skin2) atomicCAS(a.err, 0, 3);
+                    dmax = max(dmax, __float_as_uint(__double2float_ru(d2)));
+                }
+            }
+            if (a.vv_mode == 2 && a.vv_maxd2) {
+                dmax = __reduce_max_sync(0xffffffffu, dmax);
+                if (lane == 0 && dmax > *a.vv_maxd2) atomicMax(a.vv_maxd2, dmax);
+            }
+        };
         for (int k = 0;; k++) {
             const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
@@ -111,6 +167,18 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
                 bar_arrive(1 + b, FLP_THREADS);
+                if (VV) {
+                    // the atoms of the brick just released, then (after its release) those of the brick in the other buffer
+                    if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);
+#pragma unroll
+                    for (int q = 1; q < NBUF; q++) {
+                        const int ob = (k + q) % NBUF;
+                        if (held_bid[ob] >= 0) {
+                            bar_sync(1 + NBUF + ob, FLP_THREADS);
+                            advance_atoms(held_bid[ob], held_nh[ob]);
+                        }
+                    }
+                }
                 break;
             }
             const int bid = FC_BRICK_OF(a, brick);
@@ -198,6 +266,10 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             }
             __threadfence_block();
             bar_arrive(1 + b, FLP_THREADS);                           // full[b]
+            if (VV) {
+                if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);     // released before this staging started
+                held_bid[b] = bid; held_nh[b] = nh;
+            }
             brick = nb;
         }
         return;
@@ -251,13 +323,6 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const int hh = active ? h : (grp << 5);
             const int me = a.homeidx[((size_t)bid * a.gmax + grp) * 32 + (hh & 31)];
             const int slot_i = recipe[me].x;
-            if (VV && active) {      // what the epilogue will read: into L2 now, so that it is not an HBM round trip then
-#pragma unroll
-                for (int c3 = 0; c3 < 3; c3++) {
-                    prefetch_l2(a.vv_v[c3] + slot_i); prefetch_l2(a.vv_r[c3] + slot_i); prefetch_l2(a.vv_rb[c3] + slot_i);
-                }
-                prefetch_l2(a.vv_mass + slot_i);
-            }
             const double2 q0 = pxy[me];
             const double pix = q0.x, piy = q0.y, piz = pz[me];
             const uint2 hme = ph[me];
@@ -365,33 +430,9 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
                 if (store_f) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
                 if (EW) { a.en[slot_i] = 0.5 * e; a.vir[slot_i] = 0.5 * w; }
             }
-            if (VV) {
-                double d2 = 0;
-                if (active) {
-                    const double hk = __ddiv_rn(0.5 * a.vv_dt, a.vv_mass[slot_i]);
-                    const double f3[3] = {fx, fy, fz};
-#pragma unroll
-                    for (int c3 = 0; c3 < 3; c3++) {
-                        double v = __fma_rn(hk, f3[c3], a.vv_v[c3][slot_i]);          // second half-kick of this step
-                        if (a.vv_mode == 2) {
-                            v = __fma_rn(hk, f3[c3], v);                              // first half-kick of the next step
-                            const double r = __fma_rn(a.vv_dt, v, a.vv_r[c3][slot_i]);   // drift
-                            a.vv_r[c3][slot_i] = r;
-                            a.vv_snew[c3][slot_i] = __ddiv_rn(r, a.L);
-                            const double d = r - a.vv_rb[c3][slot_i];
-                            d2 = fma(d, d, d2);
-                        }
-                        a.vv_v[c3][slot_i] = v;
-                    }
-                    if (a.vv_mode == 2 && a.vv_check_skin && d2 > a.vv_half_skin2) atomicCAS(a.err, 0, 3);
-                }
-                if (a.vv_mode == 2 && a.vv_maxd2) {
-                    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(__double2float_ru(d2)));
-                    if (lane == 0 && m > *a.vv_maxd2) atomicMax(a.vv_maxd2, m);
-                }
-            }
             grp = ngrp;
         }
+        if (VV) __threadfence_block();                                // the producers read this brick's forces after empty[b]
         bar_arrive(1 + NBUF + b, FLP_THREADS);                        // empty[b]
     }
     if (COUNT) {
