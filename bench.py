@@ -38,7 +38,8 @@ sys.path.insert(0, ROOT)
 
 FLOPS_PER_PAIR = 71
 BYTES_FORCE_EVAL = 80          # B/atom: read x,y,z + LJ params, write f, e, w
-BYTES_LIST_STEP = 280          # B/atom-step of the pair-list stepping kernel: 176 list + 54 recipe + 24 positions + 24 forces
+BYTES_LIST_STEP = 280          # B/atom-step of the pair-list stepping kernel: 176 list + 54 recipe + 24 positions + 24 forces;
+                               # the fused velocity-Verlet update adds BYTES_VV (+ r_bin, mass) to the same kernel
 BYTES_VV = 120                 # B/atom-step: read r,v,f, write r,v
 BYTES_REBIN = 72               # B/atom-rebin
 
