@@ -143,7 +143,8 @@ function list_pair_count(s::NonbondedSystem)
     return n[]
 end
 
-# velocity-Verlet (additive; the reference has no integrator)
+# velocity-Verlet (additive; the reference has no integrator).  rebin_every > 0: re-bin at that cadence; 0: never;
+# < 0 (with a skin, set_skin!): adaptively, on the step on which an atom has moved more than skin/2 since the last binning
 step!(s::NonbondedSystem, nsteps::Integer; dt::Real=0.005, rebin_every::Integer=1) =
     check(ccall((:emdee_vv_step, libemdee), Cint, (Ptr{Cvoid}, Cdouble, Int64, Cint), s.handle, dt, nsteps, rebin_every))
 
