@@ -49,7 +49,11 @@ WORKLOADS = {
     "c2": (40, 2.5, 2.0, "LJ fluid N=256000 (fcc 40^3), rc=2.5, rho*=0.8442"),
     "c3": (100, 2.5, 2.0, "LJ fluid N=4000000 (fcc 100^3), rc=2.5, rho*=0.8442"),
     "c5": (200, 3.0, 2.5, "LJ fluid N=32000000 (fcc 200^3), rc=3.0, rho*=0.8442"),
+    # config 4: n = replications per dimension of the reference's molecular test system (lengths in A, energies in kJ/mol)
+    "c4": (9, 10.0, 9.0, "dibenzo-p-dioxin in water (test/data, 1519 atoms) replicated 9^3 = 1107351 atoms, rc=10 A, 1-2/1-3 exclusions"),
 }
+MOLECULAR = {"c4"}
+GOLDEN_C4 = os.path.join(ROOT, "tests", "golden", "dioxin_water.npz")
 
 
 def parse():
@@ -60,25 +64,57 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--ndiv", type=int, default=1)
-    ap.add_argument("--skin", type=float, default=0.45)
+    ap.add_argument("--skin", type=float, default=None, help="pair-list skin (default 0.45 sigma; 1.0 A for c4)")
     ap.add_argument("--rebin-every", type=int, default=-1,
                     help="steps between re-binnings; -1: adaptive (re-bin when an atom has moved more than skin/2)")
-    ap.add_argument("--dt", type=float, default=0.005)
-    ap.add_argument("--temperature", type=float, default=1.44)
+    ap.add_argument("--dt", type=float, default=None, help="time step (default 0.005 tau; 0.01 = 1 fs for c4)")
+    ap.add_argument("--temperature", type=float, default=None, help="kT of the initial velocities (default 1.44 eps; 2.494 kJ/mol for c4)")
     ap.add_argument("--e2e-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    a = ap.parse_args()
+    mol = a.workload in MOLECULAR
+    if a.skin is None:
+        a.skin = 1.0 if mol else 0.45
+    if a.dt is None:
+        a.dt = 0.01 if mol else 0.005           # c4: A, amu, kJ/mol -> time unit 0.1 ps
+    if a.temperature is None:
+        a.temperature = 2.494 if mol else 1.44   # c4: kT at 300 K in kJ/mol
+    return a
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled from a
+    thread of this process every millisecond (a timed region of 20 steps lasts ~30 ms, which the 20 ms cadence of an
+    `nvidia-smi -lms` child process would sample once at best); `mark()` brackets the timed region, and only samples
+    taken inside it are reported (all samples, i.e. warm-up + timed region, if the region held fewer than 3).
+    Falls back to the nvidia-smi child when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.samples, self.marks, self.nvml, self.handle, self.stop_flag, self.max_mhz = [], [], None, None, False, None
 
     def start(self):
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.device
+            if vis:
+                ids = [x.strip() for x in vis.split(",") if x.strip()]
+                if self.device < len(ids) and ids[self.device].isdigit():
+                    index = int(ids[self.device])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            pynvml.nvmlDeviceGetClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "20"],
@@ -88,13 +124,55 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
+    def mark(self):
+        """Call at the start and at the end of the timed region."""
+        self.marks.append(time.perf_counter())
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                why = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                self.samples.append((time.perf_counter(), mhz, why))
+            except Exception:
+                pass
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
+    def _stop_nvml(self):
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        n = self.nvml
+        names = (("hw_slowdown", 0x8), ("sw_power_cap", 0x4), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40),
+                 ("hw_power_brake_slowdown", 0x80))        # nvmlClocksEventReason* bits
+        inside = self.samples
+        region = "warm-up + timed steps"
+        if len(self.marks) >= 2:
+            sel = [x for x in self.samples if self.marks[0] <= x[0] <= self.marks[-1]]
+            if len(sel) >= 3:
+                inside, region = sel, "timed steps"
+        bits = 0
+        for _, _, why in inside:
+            bits |= why
+        try:
+            n.nvmlShutdown()
+        except Exception:
+            pass
+        sm = [x[1] for x in inside]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": min(sm) if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(name for name, bit in names if bits & bit), "samples": len(sm), "sampled_over": region,
+                "source": "NVML polled in-process every ms"}
+
     def stop(self):
+        if self.nvml is not None:
+            return self._stop_nvml()
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
@@ -110,53 +188,64 @@ class ClockSampler:
                 if val.lower() == "active":
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 20"}
 
 
 def workload(args):
     import emdee_jl_b200 as em
 
     n, rc, rs, desc = WORKLOADS[args.workload]
+    return sample(args, n, rc, rs, desc)
+
+
+def sample(args, n, rc, rs, desc=""):
+    """The workload at size parameter n (fcc cells per dimension, or replications of the molecular fixture)."""
+    import emdee_jl_b200 as em
+
+    if args.workload in MOLECULAR:
+        m = em.workloads.molecular_system(dict(np.load(GOLDEN_C4)), reps=n)
+        pos, L, N = m["positions"], m["L"], m["positions"].shape[0]
+        return dict(n=n, rc=rc, rs=rs, desc=desc, pos=pos, L=L, N=N, atoms=m["atoms"], mass=m["masses"], excl=m["excl"],
+                    vel=em.workloads.maxwell_velocities(N, args.temperature, m["masses"]))
     pos, L = em.workloads.fcc_lattice(n)
     N = pos.shape[0]
-    return dict(n=n, rc=rc, rs=rs, desc=desc, pos=pos, L=L, N=N, atoms=em.workloads.lj_fluid_atoms(N),
+    return dict(n=n, rc=rc, rs=rs, desc=desc, pos=pos, L=L, N=N, atoms=em.workloads.lj_fluid_atoms(N), mass=np.ones(N), excl=None,
                 vel=em.workloads.maxwell_velocities(N, args.temperature))
 
 
 def cpu_leg(args, w, budget_s, steps, warmup):
     """Times the CPU oracle (OpenMP, all host cores) on a bounded sample of the workload: velocity-Verlet
-    steps of a same-density, same-cutoff FCC fluid small enough to finish in `budget_s`."""
-    import emdee_jl_b200 as em
+    steps of the same kind of system (same density, cutoff, LJ classes, exclusions) small enough to finish
+    in `budget_s`."""
     from oracle import oracle_c
 
     oracle_c.build()
     cores = oracle_c.num_threads(fast=True)
-    # probe the evaluation rate on config 2's size, then pick the largest sample that fits the budget
-    pos, L = em.workloads.fcc_lattice(16)
-    at = em.workloads.lj_fluid_atoms(pos.shape[0])
-    oracle_c.cutoff_cells(pos, L, w["rc"], w["rs"], at, ndiv=args.ndiv, bitmask=1, fast=True)
+    mol = args.workload in MOLECULAR
+    # probe the evaluation rate on a small sample, then pick the largest sample that fits the budget
+    p0 = sample(args, 2 if mol else 16, w["rc"], w["rs"])
+    oracle_c.cutoff_cells(p0["pos"], p0["L"], w["rc"], w["rs"], p0["atoms"], ndiv=args.ndiv, excl=p0["excl"], bitmask=1, fast=True)
     t0 = time.perf_counter()
-    r = oracle_c.cutoff_cells(pos, L, w["rc"], w["rs"], at, ndiv=args.ndiv, bitmask=1, fast=True)
-    rate = pos.shape[0] / (time.perf_counter() - t0)          # atom-evaluations/s, O(N)
-    n = w["n"]
-    while n > 8 and 4 * n ** 3 * (steps + warmup + 1) / rate > budget_s:
-        n = max(8, int(n * 0.8))
-    pos, L = em.workloads.fcc_lattice(n)
-    N = pos.shape[0]
-    at = em.workloads.lj_fluid_atoms(N)
-    vel = em.workloads.maxwell_velocities(N, args.temperature)
-    mass = np.ones(N)
-    r = oracle_c.cutoff_cells(pos, L, w["rc"], w["rs"], at, ndiv=args.ndiv, bitmask=1, fast=True)
-    p, v, f = pos, vel, r["forces"]
+    oracle_c.cutoff_cells(p0["pos"], p0["L"], w["rc"], w["rs"], p0["atoms"], ndiv=args.ndiv, excl=p0["excl"], bitmask=1, fast=True)
+    rate = p0["N"] / (time.perf_counter() - t0)          # atom-evaluations/s, O(N)
+    per_n3 = p0["N"] / p0["n"] ** 3                       # atoms per unit of n^3
+    n, nmin = w["n"], (2 if mol else 8)
+    while n > nmin and per_n3 * n ** 3 * (steps + warmup + 1) / rate > budget_s:
+        n = max(nmin, int(n * 0.8))
+    q = sample(args, n, w["rc"], w["rs"])
+    N, L, at, mass, excl = q["N"], q["L"], q["atoms"], q["mass"], q["excl"]
+    r = oracle_c.cutoff_cells(q["pos"], L, w["rc"], w["rs"], at, ndiv=args.ndiv, excl=excl, bitmask=1, fast=True)
+    p, v, f = q["pos"], q["vel"], r["forces"]
     if warmup:
-        p, v, f = oracle_c.vv_steps(p, v, f, mass, L, w["rc"], w["rs"], at, args.dt, warmup, ndiv=args.ndiv, fast=True)
+        p, v, f = oracle_c.vv_steps(p, v, f, mass, L, w["rc"], w["rs"], at, args.dt, warmup, ndiv=args.ndiv, excl=excl, fast=True)
     t0 = time.perf_counter()
-    p, v, f = oracle_c.vv_steps(p, v, f, mass, L, w["rc"], w["rs"], at, args.dt, steps, ndiv=args.ndiv, fast=True)
+    p, v, f = oracle_c.vv_steps(p, v, f, mass, L, w["rc"], w["rs"], at, args.dt, steps, ndiv=args.ndiv, excl=excl, fast=True)
     dt = time.perf_counter() - t0
-    npairs = oracle_c.cutoff_cells(p, L, w["rc"], w["rs"], at, ndiv=args.ndiv, bitmask=1, fast=True)["npairs"]
+    npairs = oracle_c.cutoff_cells(p, L, w["rc"], w["rs"], at, ndiv=args.ndiv, excl=excl, bitmask=1, fast=True)["npairs"]
+    kind = ("the molecular fixture replicated %d^3" % n) if mol else "an fcc LJ fluid"
     return dict(value=npairs * steps / dt, unit="pair-interactions/s", cores=cores, kind="port",
-                sample="%d velocity-Verlet steps of an N=%d fcc LJ fluid (same rho*, rc, rs, dt; full-neighbour "
-                       "OpenMP cell-list oracle, -O3 AVX2+FMA)" % (steps, N),
+                sample="%d velocity-Verlet steps of N=%d atoms of %s (same density, rc, rs, dt%s; full-neighbour "
+                       "OpenMP cell-list oracle, -O3 AVX2+FMA)" % (steps, N, kind, ", exclusions" if mol else ""),
                 atom_steps_per_s=N * steps / dt, ms_per_step=dt / steps * 1e3, N=N)
 
 
@@ -212,7 +301,9 @@ def run_b200(args):
     s.set_atoms(w["atoms"])
     s.set_positions(w["pos"])
     s.set_velocities(w["vel"])
-    s.set_masses(np.ones(N))
+    s.set_masses(w["mass"])
+    if w["excl"] is not None:
+        s.set_exclusions(*w["excl"])
     s.set_skin(args.skin)
     s.bin(args.ndiv)
     s.compute(em.CUTOFF, em.FORCES)
@@ -238,6 +329,8 @@ def run_b200(args):
         return float(t.item())
 
     fp64_peak = ctx.measure_fp64_peak()
+    cfg = s.step_config()
+    step_kernel = ("k_force_list_p" if cfg["persistent"] else "k_force_list") if cfg["pair_list"] else "k_force_cells"
 
     # ---- warm-up, then exactly K timed steps -----------------------------------------------------
     sampler = ClockSampler(local)
@@ -250,12 +343,14 @@ def run_b200(args):
     barrier()
     launches0 = ctx.launch_count()
     s.profile_begin()
+    sampler.mark()
     wall0 = time.perf_counter()
     ctx.timer_start()
     s.vv_step(args.dt, args.steps, args.rebin_every)
     ms = ctx.timer_stop()
     barrier()
     wall = time.perf_counter() - wall0
+    sampler.mark()
     force_ms, force_launches = s.profile_end()
     kinds = [s.profile_kind(k) for k in range(3)]          # (ms, launches): window scan, list build, list walk
     dom = 2 if kinds[2][1] > 0 else 0                       # the stepping kernel; systems that cannot use a list scan windows
@@ -282,7 +377,9 @@ def run_b200(args):
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     rebins = kinds[1][1] if kinds[1][1] > 0 else (args.steps / args.rebin_every if args.rebin_every > 0 else 0)
-    force_bytes = BYTES_LIST_STEP if dom == 2 else BYTES_FORCE_EVAL - 16                                # forces only: no e,w
+    # list walk: 2 B per entry inside rc + skin (the mean over atoms) + 54 B recipe + 24 B positions + 24 B forces
+    list_bytes = 2.0 * N / L ** 3 * 4.18879 * (w["rc"] + args.skin) ** 3 + (BYTES_LIST_STEP - 176)
+    force_bytes = list_bytes if dom == 2 else BYTES_FORCE_EVAL - 16                                # forces only: no e,w
     step_bytes = nloc * (force_bytes + BYTES_VV) + nloc * BYTES_REBIN * rebins / args.steps
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
@@ -292,13 +389,13 @@ def run_b200(args):
     except (OSError, ValueError, KeyError):
         pass
     roofline = {
-        "bound": "fp64", "kernel": "k_force_list_p" if dom == 2 else "k_force_cells", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
+        "bound": "fp64", "kernel": step_kernel if dom == 2 else "k_force_cells", "achieved": achieved, "peak": fp64_peak / 1e12, "unit": "TFLOP/s",
         "frac": achieved / (fp64_peak / 1e12), "traffic": traffic,
         "peak_source": "DFMA chains measured in this run (emdee_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry; nominal 37 TFLOP/s",
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": pairs_local, "ms_per_launch": force_ms_per_launch,
         "launches_timed": dom_launches, "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
         "kernel_also_does": ("the velocity-Verlet kick and drift of the step (fused into the producer warps; EMDEE_FUSE_VV=0 "
-                             "runs them as k_vv and the force kernel alone takes 1.22 ms)") if dom == 2 and world == 1 and os.environ.get("EMDEE_FUSE_VV", "1") != "0" else None,
+                             "runs them as k_vv and the force kernel alone takes 1.22 ms)") if dom == 2 and cfg["fused_vv"] else None,
         "force_kernels_share_of_step": force_ms / ms if ms > 0 else None,
         "list_build": {"kernel": "k_list_build", "ms_per_launch": build_ms_per_launch, "launches_timed": kinds[1][1],
                        "share_of_step": kinds[1][0] / ms if ms > 0 else None},
@@ -348,7 +445,7 @@ def run_b200(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["desc"], "N": N, "L": L, "cutoff": w["rc"], "switch": w["rs"], "dt": args.dt,
-                       "ndiv": args.ndiv, "skin": args.skin,
+                       "ndiv": args.ndiv, "skin": args.skin, "brick_cells": list(cfg["brick"]), "brick_capacity": cfg["brick_capacity"],
                        "rebin_every": args.rebin_every if args.rebin_every >= 0 else "adaptive (skin/2 criterion)",
                        "rebins_in_timed_steps": int(rebins),
                        "decomposition": "z-slabs x%d" % world if world > 1 else "single GPU",

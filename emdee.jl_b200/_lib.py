@@ -89,6 +89,7 @@ SIGNATURES = {
     "emdee_timer_stop": [_p, C.POINTER(_d)],
     "emdee_profile_begin": [_p],
     "emdee_profile_end": [_p, C.POINTER(_d), C.POINTER(_i64)],
+    "emdee_get_step_config": [_p, _p],
     "emdee_get_local_count": [_p, C.POINTER(_i64), C.POINTER(_i64)],
     "emdee_get_local_ids": [_p, _p],
     "emdee_compute_nonbonded_host": [_i64, _p, _d, _d, _d, _p, _p, _i64, _i, _i, _i, _p, _p, _p],

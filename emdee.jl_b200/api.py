@@ -296,6 +296,13 @@ class NonbondedSystem:
         call("emdee_kinetic_energy", self._h, C.byref(K))
         return K.value
 
+    def step_config(self):
+        """How the stepping path is configured after the last bin(): brick shape, kernel variant (host-only query)."""
+        o = np.zeros(8, dtype=np.int32)
+        call("emdee_get_step_config", self._h, _ptr(o))
+        return dict(brick=(int(o[0]), int(o[1]), int(o[2])), brick_capacity=int(o[3]), pair_list=bool(o[4]),
+                    persistent=bool(o[5]), fused_vv=bool(o[6]), list_chunks=int(o[7]))
+
     def cells_per_dimension(self):
         M = C.c_int32()
         call("emdee_get_cells_per_dimension", self._h, C.byref(M))

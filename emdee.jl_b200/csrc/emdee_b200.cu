@@ -1852,6 +1852,23 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     return EMDEE_OK;
 }
 
+extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
+{
+    SYS_ENTER(s, "emdee_get_step_config");
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_step_config: null output");
+    if (!s->binned) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_step_config: call emdee_bin first");
+    const bool listed = list_capable(s);
+    out[0] = s->grid_ok ? s->g.bx : 0;
+    out[1] = s->grid_ok ? s->g.by : 0;
+    out[2] = s->grid_ok ? s->g.bz : 0;
+    out[3] = s->grid_ok ? s->fc_cap : 0;
+    out[4] = listed ? 1 : 0;
+    out[5] = listed && s->fl_persistent ? 1 : 0;
+    out[6] = listed && s->fl_persistent && s->fuse_vv && c->nranks == 1 ? 1 : 0;
+    out[7] = s->lcap8;
+    return EMDEE_OK;
+}
+
 extern "C" int emdee_kinetic_energy(emdee_system *s, double *K)
 {
     SYS_ENTER(s, "emdee_kinetic_energy");

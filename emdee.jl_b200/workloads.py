@@ -128,3 +128,28 @@ def replicate_molecular(pos, box, bonds, per_atom, reps, jitter=0.01, seed=SEED)
     allbonds = (np.asarray(bonds, dtype=np.int64)[None, :, :] + (k * N0)[:, None, None]).reshape(-1, 2)
     out = {name: np.tile(arr, (ncopy,) + (1,) * (arr.ndim - 1)) for name, arr in per_atom.items()}
     return np.ascontiguousarray(allpos), reps * box, allbonds, out
+
+
+def molecular_system(fixture, reps=9, jitter=0.01, seed=SEED):
+    """BASELINE config 4: the reference's molecular test system
+    (test/data/dibenzo-p-dioxin-in-water.{pdb,xml}: 1519 atoms, 500 residues, cubic box 24.56 A) replicated
+    reps^3 times -- reps = 9 gives 1,107,351 atoms in a box of 221.04 A.  `fixture` is the parsed form of
+    those two files (tests/golden/dioxin_water.npz, or modelling.System(...).fixture()).  Lengths in A
+    (sigma converted nm -> A), per-type LJ parameters, 1-2/1-3 exclusions from the bond graph as bitmasks;
+    cutoff 10 A, switch 9 A.  Returns a dict: positions, L, atoms (N,2), masses, excl = (base, mask), bonds,
+    cutoff, switch."""
+    pos0 = np.asarray(fixture["positions"], dtype=np.float64)
+    box = float(fixture["box"])
+    tidx = np.asarray(fixture["type_index"])
+    N0 = pos0.shape[0]
+    sig = np.asarray(fixture["type_sigma_nm"])[tidx] * 10.0
+    eps = np.asarray(fixture["type_epsilon"])[tidx]
+    atoms0 = np.stack([0.5 * sig, 2.0 * np.sqrt(eps)], axis=1)
+    mass0 = np.asarray(fixture["type_mass"])[tidx]
+    base0, mask0 = exclusion_masks(N0, fixture["bonds"])
+    pos, L, bonds, per = replicate_molecular(pos0, box, fixture["bonds"], {"atoms": atoms0, "mass": mass0, "mask": mask0},
+                                            reps, jitter, seed)
+    # the exclusion window of copy k is the window of copy 0 shifted by k*N0 atom ids
+    base = (base0.astype(np.int64)[None, :] + (np.arange(reps ** 3, dtype=np.int64) * N0)[:, None]).reshape(-1)
+    return dict(positions=pos, L=L, atoms=np.ascontiguousarray(per["atoms"]), masses=np.ascontiguousarray(per["mass"]),
+                excl=(base.astype(np.int32), np.ascontiguousarray(per["mask"])), bonds=bonds, cutoff=10.0, switch=9.0)

@@ -140,6 +140,12 @@ int emdee_profile_end(emdee_system *sys, double *force_kernel_ms, int64_t *force
  * evaluations), 1 = k_list_build (pair-list build on a re-binning step), 2 = k_force_list(_p) (the stepping kernel). */
 int emdee_profile_kind(emdee_system *sys, int kind, double *ms, int64_t *launches);
 
+/* Host-only: how the stepping path is configured after the last emdee_bin (what bench.py names as the dominant
+ * kernel): out = {brick cells x, y, z, staged-atom capacity of a brick, list-capable (1: k_list_build + list walk,
+ * 0: window scan on every step), persistent (1: k_force_list_p, 0: k_force_list, one block per brick),
+ * velocity-Verlet fused into the stepping kernel (1/0), list chunks of 8 entries per atom}. */
+int emdee_get_step_config(emdee_system *sys, int32_t out[8]);
+
 /* Slab decomposition info (valid after emdee_bin): atoms owned by this rank and their ids */
 int emdee_get_local_count(emdee_system *sys, int64_t *nlocal, int64_t *nghost);
 int emdee_get_local_ids(emdee_system *sys, int32_t *ids_nlocal);

@@ -405,6 +405,79 @@ def test_pair_list_molecular(em, oracle, dioxin_water):
     s.close()
 
 
+def _c4_system(em, w):
+    s = make_system(em, w["positions"], w["L"], w["cutoff"], w["switch"], w["atoms"])
+    s.set_exclusions(*w["excl"])
+    s.set_masses(w["masses"])
+    return s
+
+
+@pytest.mark.parametrize("ndiv", [1, 2])
+def test_config4_replicated_cell_grid(em, oracle, dioxin_water, ndiv):
+    """BASELINE config 4 at 3x3x3 replications (41,013 atoms, L = 73.68 A, M = 7 / 14): the single fixture box is too
+    small for a cell grid (M = 2: it runs on tiles), so this is where several LJ classes and exclusion bitmasks meet
+    the cell-list kernels at molecular density (~130 atoms per 11 A cell): single point (pair set bit-exact, E/W/F),
+    then the stepping path (list build with exclusions removed at the flush, list walk), audited by the pair count."""
+    w = em.workloads.molecular_system(dioxin_water, reps=3)
+    pos, L, atoms, excl = w["positions"], w["L"], w["atoms"], w["excl"]
+    N = pos.shape[0]
+    s = _c4_system(em, w)
+    s.bin(ndiv)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=ndiv, excl=excl)
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    E, W, npairs = s.totals()
+    assert npairs == ref["npairs"]
+    # stepping: thermal velocities (kT = 2.494 kJ/mol; A, amu, kJ/mol -> time unit 0.1 ps), 1 fs steps, skin 1 A
+    s.set_velocities(em.workloads.maxwell_velocities(N, 2.494, w["masses"]))
+    s.set_skin(1.0)
+    s.bin(ndiv)
+    s.compute(em.CUTOFF, em.FORCES)
+    cfg = s.step_config()
+    assert cfg["pair_list"], cfg
+    for nsteps in (1, 3):
+        s.vv_step(0.01, nsteps, rebin_every=5)
+        s.synchronize()
+        ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=excl, fast=True)
+        assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+        assert s.list_pair_count() == ref["npairs"]
+    s.compute(em.CUTOFF, 7)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    s.close()
+
+
+def test_config4_full_size(em, oracle, dioxin_water):
+    """BASELINE config 4 at full size: 9x9x9 replications = 1,107,351 atoms, L = 221.04 A, rc = 10 A, 2.4e8 pairs.
+    Pair-set digest, pair count, E, W and per-atom forces against the OpenMP oracle; Newton's third law over the
+    whole system; a few steps on the pair list audited by the evaluated pair count."""
+    w = em.workloads.molecular_system(dioxin_water, reps=9)
+    pos, L, atoms, excl = w["positions"], w["L"], w["atoms"], w["excl"]
+    N = pos.shape[0]
+    assert N == 1107351
+    s = _c4_system(em, w)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1, excl=excl, fast=True)
+    E, W, npairs = s.totals()
+    f = s.forces()
+    assert np.array_equal(s.pair_set_digest(), ref["digest"]) and npairs == ref["npairs"]
+    assert abs(E - ref["E"]) <= E_TOL * abs(ref["E"]) and abs(W - ref["W"]) <= E_TOL * abs(ref["W"])
+    assert np.abs(f - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    assert np.abs(f.sum(axis=0)).max() <= 1e-12 * np.abs(f).sum()
+    s.set_velocities(em.workloads.maxwell_velocities(N, 2.494, w["masses"]))
+    s.set_skin(1.0)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.01, 4, rebin_every=5)
+    s.synchronize()
+    ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=excl, fast=True)
+    assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    assert s.list_pair_count() == ref["npairs"]
+    s.close()
+
+
 def test_skin_violation_is_reported(em):
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
