@@ -15,6 +15,7 @@ from .api import (  # noqa: F401
     VIRIALS,
     WARPSIZE,
     Cells,
+    berendsen_,
     Context,
     LennardJonesAtom,
     LennardJonesModel,

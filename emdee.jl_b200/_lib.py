@@ -83,6 +83,7 @@ SIGNATURES = {
     "emdee_fp16_threshold": [_p, _d, _p],
     "emdee_vv_step": [_p, _d, _i64, _i],
     "emdee_kinetic_energy": [_p, C.POINTER(_d)],
+    "emdee_scale_velocities": [_p, _d],
     "emdee_synchronize": [_p],
     "emdee_launch_count": [_p, C.POINTER(_i64)],
     "emdee_timer_start": [_p],

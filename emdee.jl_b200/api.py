@@ -303,6 +303,21 @@ class NonbondedSystem:
         return dict(brick=(int(o[0]), int(o[1]), int(o[2])), brick_capacity=int(o[3]), pair_list=bool(o[4]),
                     persistent=bool(o[5]), fused_vv=bool(o[6]), list_chunks=int(o[7]))
 
+    def scale_velocities(self, factor):
+        call("emdee_scale_velocities", self._h, float(factor))
+
+    def checkpoint(self):
+        """Host copy of everything a restart needs, in atom-id order (additive)."""
+        return dict(N=self.N, L=self.L, positions=self.positions(), velocities=self.velocities())
+
+    def restore(self, ckpt):
+        """Positions and velocities from checkpoint(); the caller re-bins and re-evaluates the forces
+        (bin(); compute(CUTOFF, FORCES)) before stepping on."""
+        if int(ckpt["N"]) != self.N or float(ckpt["L"]) != self.L:
+            raise ValueError("checkpoint belongs to a different system (N or L differ)")
+        self.set_positions(ckpt["positions"])
+        self.set_velocities(ckpt["velocities"])
+
     def cells_per_dimension(self):
         M = C.c_int32()
         call("emdee_get_cells_per_dimension", self._h, C.byref(M))
@@ -462,6 +477,18 @@ def update_cells_(cells, r, L):
         raise ValueError("update_cells!: L differs from the box the cells were built for")
     cells._refresh(_as_3xN(r, "r"))
     return None
+
+
+def berendsen_(system, kT, tau, elapsed, ndof=None):
+    """Additive: one Berendsen velocity rescaling towards temperature kT (energy units) with coupling time tau after
+    `elapsed` time of dynamics: lambda = sqrt(1 + elapsed/tau (kT/kT_now - 1)), kT_now = 2K/ndof (ndof = 3N - 3).
+    K comes from the device (emdee_kinetic_energy), the scaling runs on the device (emdee_scale_velocities).
+    Returns (kT_now, lambda)."""
+    ndof = 3 * system.N - 3 if ndof is None else ndof
+    now = 2.0 * system.kinetic_energy() / ndof
+    lam = math.sqrt(max(0.0, 1.0 + elapsed / tau * (kT / now - 1.0))) if now > 0 else 1.0
+    system.scale_velocities(lam)
+    return now, lam
 
 
 def step_(system, nsteps, dt, rebin_every=1):

@@ -1852,6 +1852,16 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     return EMDEE_OK;
 }
 
+extern "C" int emdee_scale_velocities(emdee_system *s, double factor)
+{
+    SYS_ENTER(s, "emdee_scale_velocities");
+    if (!s->has_vel) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_scale_velocities: velocities were never set");
+    if (!std::isfinite(factor)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_scale_velocities: factor=%g", factor);
+    if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_scale_velocities: a half-kick is pending (call between emdee_vv_step calls)");
+    LAUNCH_1D(c, k_scale3, s->nown, s->nlo, s->nown, factor, A.v[0], A.v[1], A.v[2]);
+    return check_launch("k_scale3");
+}
+
 extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
 {
     SYS_ENTER(s, "emdee_get_step_config");

@@ -70,6 +70,17 @@ __global__ void k_kinetic(int64_t first, int64_t n, const double *__restrict__ v
     if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
+// v *= factor over owned slots (velocity-rescaling thermostats, driven from the host between emdee_vv_step calls)
+__global__ void k_scale3(int64_t first, int64_t n, double factor, double *__restrict__ vx, double *__restrict__ vy, double *__restrict__ vz)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int64_t i = first + k;
+    vx[i] *= factor;
+    vy[i] *= factor;
+    vz[i] *= factor;
+}
+
 // host layout (3xN column-major, id order) <-> slot order
 __global__ void k_set3(int64_t first, int64_t n, const int32_t *__restrict__ id, const double *__restrict__ in,
                        double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2)

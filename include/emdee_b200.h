@@ -123,6 +123,9 @@ int emdee_fp16_threshold(const double half_extent[3], double rcut, float *thresh
  * last binning -- one 4-byte read-back per step, and a max over ranks in a slab decomposition).  Needs model, atoms, masses, velocities, one emdee_bin and one emdee_compute_nonbonded. */
 int emdee_vv_step(emdee_system *sys, double dt, int64_t nsteps, int rebin_every);
 int emdee_kinetic_energy(emdee_system *sys, double *K);
+/* v *= factor for every atom this rank owns: the device half of a velocity-rescaling thermostat (the reference has
+ * none); the host computes the factor from emdee_kinetic_energy between emdee_vv_step calls. */
+int emdee_scale_velocities(emdee_system *sys, double factor);
 int emdee_synchronize(emdee_system *sys);
 /* number of kernels this library has launched on the context since creation */
 int emdee_launch_count(emdee_ctx *ctx, int64_t *n);

@@ -148,6 +148,28 @@ end
 step!(s::NonbondedSystem, nsteps::Integer; dt::Real=0.005, rebin_every::Integer=1) =
     check(ccall((:emdee_vv_step, libemdee), Cint, (Ptr{Cvoid}, Cdouble, Int64, Cint), s.handle, dt, nsteps, rebin_every))
 
+# thermostat pieces (additive): kinetic energy from the device, velocity rescaling on the device
+function kinetic_energy(s::NonbondedSystem)
+    K = Ref{Cdouble}(0)
+    check(ccall((:emdee_kinetic_energy, libemdee), Cint, (Ptr{Cvoid}, Ref{Cdouble}), s.handle, K))
+    return K[]
+end
+scale_velocities!(s::NonbondedSystem, factor::Real) =
+    check(ccall((:emdee_scale_velocities, libemdee), Cint, (Ptr{Cvoid}, Cdouble), s.handle, factor))
+# one Berendsen rescaling towards kT with coupling time tau after `elapsed` time of dynamics
+function berendsen!(s::NonbondedSystem, kT::Real, tau::Real, elapsed::Real; ndof::Integer=3*s.N-3)
+    now = 2*kinetic_energy(s)/ndof
+    lambda = now > 0 ? sqrt(max(0.0, 1 + elapsed/tau*(kT/now - 1))) : 1.0
+    scale_velocities!(s, lambda)
+    return now, lambda
+end
+# how the stepping path is configured after bin!: (brick cells x,y,z, brick capacity, pair list?, persistent?, fused VV?, list chunks)
+function step_config(s::NonbondedSystem)
+    o = zeros(Int32, 8)
+    check(ccall((:emdee_get_step_config, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}), s.handle, o))
+    return o
+end
+
 # ---- compute_nonbonded!, src/nonbonded.jl:109-120 ----------------------------------------------------
 function compute_nonbonded!(forces::Matrix{Float64}, energies::Vector{Float64}, virials::Vector{Float64},
                             positions::Matrix{Float64}, L, tiles, model::LennardJonesModel,

@@ -478,6 +478,56 @@ def test_config4_full_size(em, oracle, dioxin_water):
     s.close()
 
 
+def test_thermostat_and_checkpoint(em, oracle):
+    """SURVEY section 8f-4 (after the path): velocity rescaling on the device (Berendsen driven from the host) and a
+    host checkpoint.  Scaling: K -> lambda^2 K exactly to rounding.  Restart: a run continued from a checkpoint in a
+    NEW system follows the uninterrupted run (summation order differs after the restart's re-binning: 1e-10)."""
+    pos, L = em.workloads.fcc_lattice(12)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+
+    def fresh(p, v):
+        s = make_system(em, p, L, 2.5, 2.0, atoms)
+        s.set_velocities(v)
+        s.set_masses(np.ones(N))
+        s.set_skin(0.4)
+        s.bin(1)
+        s.compute(em.CUTOFF, em.FORCES)
+        return s
+
+    a = fresh(pos, em.workloads.maxwell_velocities(N, 1.44))
+    K0 = a.kinetic_energy()
+    a.scale_velocities(0.5)
+    assert abs(a.kinetic_energy() - 0.25 * K0) <= 1e-12 * K0
+    a.scale_velocities(2.0)
+    assert abs(a.kinetic_energy() - K0) <= 1e-12 * K0
+    # Berendsen towards kT = 1.0 with tau = 10 dt, applied every 5 steps: the temperature moves towards the target
+    kT = [2.0 * a.kinetic_energy() / (3 * N - 3)]
+    for _ in range(6):
+        a.vv_step(0.005, 5, rebin_every=5)
+        now, lam = em.berendsen_(a, 1.0, 0.05, 0.025)
+        assert lam < 1.0 or now < 1.0
+        kT.append(now)
+    assert abs(2.0 * a.kinetic_energy() / (3 * N - 3) - 1.0) < abs(kT[0] - 1.0)
+    # checkpoint / restart
+    a.vv_step(0.005, 5, rebin_every=5)
+    ck = a.checkpoint()
+    a.vv_step(0.005, 10, rebin_every=5)
+    b = fresh(ck["positions"], ck["velocities"])
+    b.restore(ck)
+    b.bin(1)
+    b.compute(em.CUTOFF, em.FORCES)
+    b.vv_step(0.005, 10, rebin_every=5)
+    d = a.positions() - b.positions()
+    d -= L * np.rint(d / L)
+    assert np.abs(d).max() <= 1e-10
+    assert np.abs(a.velocities() - b.velocities()).max() <= 1e-9
+    with pytest.raises(ValueError):
+        b.restore(dict(ck, N=N + 1))
+    a.close()
+    b.close()
+
+
 def test_skin_violation_is_reported(em):
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
