@@ -17,7 +17,15 @@
 #pragma once
 #include "force_list.cuh"
 
+#ifndef FLP_THREADS
 #define FLP_THREADS 512
+#endif
+#ifndef FLP_ILP
+#define FLP_ILP 4            // stack entries evaluated per drain iteration (independent FP64 chains per lane)
+#endif
+#ifndef FLP_STAGE_U
+#define FLP_STAGE_U 9        // atoms per producer thread in flight: ~2300 staged atoms / 128 threads = two batches
+#endif
 #ifndef FLP_NPROD
 #define FLP_NPROD 4
 #endif
@@ -74,10 +82,15 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // walk (ncu: `wait` was the top stall of the consumers with walk and drain as separate loops).
 // VV: the epilogue also advances the atom (k_vv's arithmetic, one fma per line, same rounding): v += h f [step n done];
 // v += h f; r += dt v; s' = r/L [step n+1 started], so a step is ONE kernel instead of k_vv + force kernel.
+#ifdef FLP_MAXNREG      // block sizes that are not a multiple of 128: ptxas rounds the launch bound up, this states the budget
+#define FLP_BOUNDS __maxnreg__(FLP_MAXNREG)
+#else
+#define FLP_BOUNDS __launch_bounds__(FLP_THREADS, 1)
+#endif
 template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false>
-__global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int nbricks, int store_f)
+__global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
-    constexpr int ILP = 4;
+    constexpr int ILP = FLP_ILP;
     constexpr int QCAP = NBUF >= 3 ? 24 : FL_QCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(FLP_THREADS, 1) k_force_list_p(CellArgs a, int
             const int ux0 = bg.hx0 - R, uy0 = bg.hy0 - R, uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0) - R;
             const double bcx = ((double)bg.hx0 + 0.5 * bg.nhx) * invM, bcy = ((double)bg.hy0 + 0.5 * bg.nhy) * invM,
                          bcz = ((double)(uz0 + R) + 0.5 * bg.nhz) * invM;
-            constexpr int U = 9;                // atoms per thread in flight: ~2300 staged atoms / 128 threads = two batches
+            constexpr int U = FLP_STAGE_U;
             int2 rc[U];
             double sx[U], sy[U], sz[U];
             auto load_batch = [&](int i0) {

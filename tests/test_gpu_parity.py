@@ -429,15 +429,22 @@ def test_config4_replicated_cell_grid(em, oracle, dioxin_water, ndiv):
     check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
     E, W, npairs = s.totals()
     assert npairs == ref["npairs"]
-    # stepping: thermal velocities (kT = 2.494 kJ/mol; A, amu, kJ/mol -> time unit 0.1 ps), 1 fs steps, skin 1 A
+    # stepping: thermal velocities (kT = 2.494 kJ/mol; A, amu, kJ/mol -> time unit 0.1 ps), 0.5 fs steps.  Skin 0.5 A:
+    # with 1 A this box would get M = 6 cells of 12.3 A, whose 27-cell neighbourhood (~5100 atoms) does not fit
+    # shared memory at ndiv = 1 -- the library reports that as a capacity error, checked below
     s.set_velocities(em.workloads.maxwell_velocities(N, 2.494, w["masses"]))
-    s.set_skin(1.0)
+    if ndiv == 1:
+        s.set_skin(1.0)
+        with pytest.raises(em.EmDeeError) as ei:
+            s.bin(1)
+        assert ei.value.status == 5 and "larger ndiv" in str(ei.value)
+    s.set_skin(0.5)
     s.bin(ndiv)
     s.compute(em.CUTOFF, em.FORCES)
     cfg = s.step_config()
     assert cfg["pair_list"], cfg
     for nsteps in (1, 3):
-        s.vv_step(0.01, nsteps, rebin_every=5)
+        s.vv_step(0.005, nsteps, rebin_every=5)
         s.synchronize()
         ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=excl, fast=True)
         assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
