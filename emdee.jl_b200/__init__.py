@@ -16,6 +16,7 @@ from .api import (  # noqa: F401
     WARPSIZE,
     Cells,
     berendsen_,
+    cells_per_dimension,
     Context,
     LennardJonesAtom,
     LennardJonesModel,
@@ -23,9 +24,12 @@ from .api import (  # noqa: F401
     comm_unique_id,
     compute_nonbonded_,
     default_context,
+    index2voxel,
     naively_compute_nonbonded_,
     nonbonded_computation_tiles,
     step_,
+    stencil_vectors,
+    surrounding_cells,
     update_cells_,
 )
 from . import workloads  # noqa: F401

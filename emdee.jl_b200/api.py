@@ -415,6 +415,49 @@ def naively_compute_nonbonded_(forces, energies, virials, positions, L, model, a
                        FORCES | ENERGIES | VIRIALS, mode=ALLPAIRS_REFERENCE)
 
 
+def index2voxel(index, M):
+    """index2voxel(index, M) -- src/cells.jl:22-26: 1-based linear cell index -> 0-based voxel [i, j, k], x fastest."""
+    k, l = divmod(int(index) - 1, M * M)
+    j, i = divmod(l, M)
+    return np.array([i, j, k], dtype=np.int64)
+
+
+def stencil_vectors(rc, action):
+    """stencil_vectors(rc, action) -- src/cells.jl:28-34, restated literally (integer work, identical output and order):
+    the (2*ceil(rc)+1)^3 block around a cell is split by linear order into the first half (`action`) and the second
+    half (reaction), the centre excluded, and filtered by sum((|d|-1)^2) < rc^2 with rc in cell units.  Note that a
+    zero component contributes (0-1)^2 = 1 to that sum, as in the reference (it drops needed cells
+    for rc* < sqrt(3); the kernels here do not use these tables)."""
+    nmax = int(math.ceil(rc))
+    M = 1 + 2 * nmax
+    half = M ** 3 // 2
+    rng = range(1, half + 1) if action else range(half + 2, M ** 3 + 1)
+    out = []
+    for i in rng:
+        v = index2voxel(i, M) - nmax
+        if int(((np.abs(v) - 1) ** 2).sum()) < rc * rc:
+            out.append(v)
+    return np.array(out, dtype=np.int64).reshape(-1, 3)
+
+
+def cells_per_dimension(L, cutoff, ndiv):
+    """cells_per_dimension(L, cutoff, ndiv) = floor(Int32, ndiv*L/cutoff) -- src/cells.jl:36."""
+    return int(np.int32(math.floor(ndiv * L / cutoff)))
+
+
+def surrounding_cells(L, cutoff, M, action):
+    """surrounding_cells(L, cutoff, M, action) -- src/cells.jl:38-44: (n_vec, M^3) Int32 table of the 1-based cells
+    reached from every cell by the stencil vectors, one periodic image (:39).  Host table for small grids only:
+    62 x M^3 x 4 B is 597 MB at 4 M atoms, which is why the kernels derive neighbours from cell coordinates instead."""
+    M = int(M)
+    vectors = stencil_vectors(M * cutoff / L, action)
+    idx = np.arange(M ** 3, dtype=np.int64)
+    vox = np.stack([idx % M, (idx // M) % M, idx // (M * M)], axis=1)                  # index2voxel of every cell
+    t = vox[None, :, :] + vectors[:, None, :]
+    t = np.where(t < 0, t + M, np.where(t >= M, t - M, t))                              # pbc(x), one image only
+    return (1 + t[..., 0] + M * t[..., 1] + M * M * t[..., 2]).astype(np.int32)
+
+
 class Cells:
     """Cells(r, L, cutoff; ndiv=2, num_threads=256) -- src/cells.jl:6-20,176-194.
 
@@ -458,6 +501,15 @@ class Cells:
             nxt[ids1 - 1] = prev
             self._lists = (head, nxt)
         return self._lists
+
+    @property
+    def action_cells(self):
+        """The reference's stencil table (src/cells.jl:185), built on the host on demand (small grids only)."""
+        return surrounding_cells(self._sys.L, self.cutoff, self.M, True)
+
+    @property
+    def reaction_cells(self):
+        return surrounding_cells(self._sys.L, self.cutoff, self.M, False)
 
     @property
     def head(self):

@@ -168,3 +168,37 @@ def pair_digest(ij):
         s = np.add.reduce(h, dtype=np.uint64) if h.size else np.uint64(0)
     x = np.bitwise_xor.reduce(h) if h.size else np.uint64(0)
     return np.array([h.size, s, x], dtype=np.uint64)
+
+
+def stencil_vectors_loops(rc, action):
+    """src/cells.jl:22-34 as plain loops (test infrastructure: checks the vectorised host mirror in api.py)."""
+    import math
+    nmax = math.ceil(rc)
+    M = 1 + 2 * nmax
+    lo, hi = (1, M ** 3 // 2) if action else (M ** 3 // 2 + 2, M ** 3)
+    out = []
+    for index in range(lo, hi + 1):
+        k, l = divmod(index - 1, M * M)
+        j, i = divmod(l, M)
+        v = (i - nmax, j - nmax, k - nmax)
+        if sum((abs(c) - 1) ** 2 for c in v) < rc * rc:
+            out.append(v)
+    return out
+
+
+def surrounding_cells_loops(L, cutoff, M, action):
+    """src/cells.jl:38-44 as plain loops: table[v][cell-1] = 1-based neighbour cell."""
+    vectors = stencil_vectors_loops(M * cutoff / L, action)
+
+    def pbc(x):
+        return x + M if x < 0 else (x - M if x >= M else x)
+
+    table = []
+    for v in vectors:
+        row = []
+        for index in range(1, M ** 3 + 1):
+            k, l = divmod(index - 1, M * M)
+            j, i = divmod(l, M)
+            row.append(1 + pbc(i + v[0]) + M * pbc(j + v[1]) + M * M * pbc(k + v[2]))
+        table.append(row)
+    return table

@@ -67,3 +67,24 @@ def test_cutoff_band_classification():
         assert (r2[outside] * (1 - eps) > rc2).all()
         band = ~inside & ~outside
         assert (np.abs(r2[band] / rc2 - 1.0) < 4e-6).all()      # the exact path is taken only within ~3 * 2^-20 of rc2
+
+
+def test_stencil_tables_mirror(em):
+    """index2voxel / stencil_vectors / surrounding_cells (src/cells.jl:22-44): the vectorised host mirror against a
+    literal loop restatement; 62 + 62 vectors for rc* in [1.74, 2]; action and reaction stencils are
+    point reflections of each other, so every cell pair is visited once."""
+    from oracle import oracle_np as on
+
+    assert em.index2voxel(1, 5).tolist() == [0, 0, 0] and em.index2voxel(5 * 5 * 2 + 5 * 3 + 4 + 1, 5).tolist() == [4, 3, 2]
+    assert em.cells_per_dimension(10.0, 3.0, 2) == 6 and em.cells_per_dimension(167.96, 2.5, 1) == 67
+    for rc in (1.0, 1.5, 1.74, 1.9, 2.0, 2.3, 3.0):
+        for action in (True, False):
+            v = em.stencil_vectors(rc, action)
+            assert [tuple(x) for x in v.tolist()] == on.stencil_vectors_loops(rc, action), (rc, action)
+        a, r = em.stencil_vectors(rc, True), em.stencil_vectors(rc, False)
+        assert sorted(map(tuple, (-a).tolist())) == sorted(map(tuple, r.tolist()))
+    assert len(em.stencil_vectors(1.9, True)) == 62 and len(em.stencil_vectors(2.0, False)) == 62
+    for L, cutoff, M in ((10.0, 3.0, 6), (10.0, 2.0, 10), (7.0, 2.5, 5)):
+        for action in (True, False):
+            t = em.surrounding_cells(L, cutoff, M, action)
+            assert t.dtype == np.int32 and t.tolist() == on.surrounding_cells_loops(L, cutoff, M, action)
