@@ -249,6 +249,51 @@ def cpu_leg(args, w, budget_s, steps, warmup):
                 atom_steps_per_s=N * steps / dt, ms_per_step=dt / steps * 1e3, N=N)
 
 
+def reference_case(em, ctx):
+    """BASELINE configs[0] beside the headline: N = 4000 (fcc 10^3), rc = 2.5, single-point energies / forces / virials
+    with the REFERENCE'S OWN semantics and call shape -- `compute_nonbonded!(f, e, w, positions, L, tiles, model, atoms,
+    Val(7))` over all N(N-1)/2 minimum-image pairs (src/nonbonded.jl:109-120) -- through the C ABI with host arrays
+    (upload, k_force_tiles, download), next to the reference's own CPU path, the serial loop of
+    `naively_compute_nonbonded!` (src/nonbonded.jl:122-155), restated in oracle/ and timed on one host thread."""
+    from oracle import oracle_c
+
+    pos, L = em.workloads.fcc_lattice(10)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    model = em.LennardJonesModel(2.5, 2.0)
+    tiles = em.nonbonded_computation_tiles(N)
+    f = np.zeros((N, 3)); e = np.zeros(N); w = np.zeros(N)
+    s = em.NonbondedSystem(N, L, ctx)
+    s.set_model(model)
+    s.set_atoms(atoms)
+    s.set_tiles(tiles)
+
+    def once():
+        s.set_positions(pos)
+        s.compute(em.ALLPAIRS_REFERENCE, 7)
+        s.forces(f); s.energies(e); s.virials(w)
+
+    once()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        once()
+    gpu_ms = (time.perf_counter() - t0) / 5 * 1e3
+    s.close()
+    om = oracle_c.lj_model(2.5, 2.0)
+    oracle_c.naive_allpairs(pos, L, om, atoms)
+    t0 = time.perf_counter()
+    fr, er, wr = oracle_c.naive_allpairs(pos, L, om, atoms)
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    npairs = N * (N - 1) // 2
+    frms = float(np.sqrt((fr ** 2).sum(axis=1).mean()))
+    return {"workload": "LJ fluid N=4000 (fcc 10^3), rc=2.5: compute_nonbonded!(..., Val(7)) over all %d pairs, host arrays in and out" % npairs,
+            "b200_ms_per_call": gpu_ms, "b200_pairs_per_s": npairs / (gpu_ms * 1e-3),
+            "cpu_ms_per_call": cpu_ms, "cpu_pairs_per_s": npairs / (cpu_ms * 1e-3), "cpu_threads": 1,
+            "cpu_kind": "port of naively_compute_nonbonded! (serial loop, FP64)",
+            "max_force_diff_over_frms": float(np.abs(f - fr).max() / frms),
+            "energy_rel_diff": float(abs(e.sum() - er.sum()) / abs(er.sum()))}
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia
     (not installed; nothing under /root/reference compiles with gcc), so oracle/_ref does not exist and
@@ -437,6 +482,10 @@ def run_b200(args):
         r = cpu_leg(args, w, budget_s=25.0, steps=3, warmup=1)
         cpu = {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": "port", "sample": r["sample"],
                "atom_steps_per_s": r["atom_steps_per_s"]}
+        try:
+            cpu["reference_case"] = reference_case(em, ctx)
+        except Exception as ex:                      # never lose the headline line over the side measurement
+            cpu["reference_case"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

@@ -405,6 +405,38 @@ def test_pair_list_molecular(em, oracle, dioxin_water):
     s.close()
 
 
+def test_config3_full_size(em, oracle):
+    """BASELINE config 3 at full size (N = 4,000,000, the bench workload): pair-set digest, pair count, E, W and
+    per-atom forces against the OpenMP oracle; momentum conservation; then the bench's own stepping configuration
+    (skin 0.45, adaptive re-binning, fused velocity-Verlet) audited after 12 steps by the evaluated pair count."""
+    pos, L = em.workloads.fcc_lattice(100)
+    N = pos.shape[0]
+    assert N == 4000000
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+    E, W, npairs = s.totals()
+    f = s.forces()
+    assert np.array_equal(s.pair_set_digest(), ref["digest"]) and npairs == ref["npairs"]
+    assert abs(E - ref["E"]) <= E_TOL * abs(ref["E"]) and abs(W - ref["W"]) <= E_TOL * abs(ref["W"])
+    assert np.abs(f - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    assert np.abs(f.sum(axis=0)).max() <= 1e-12 * np.abs(f).sum()
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_masses(np.ones(N))
+    s.set_skin(0.45)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.005, 12, rebin_every=-1)
+    s.synchronize()
+    ref = oracle.cutoff_cells(s.positions(), L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+    assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    assert s.list_pair_count() == ref["npairs"]
+    assert np.abs(s.velocities().sum(axis=0)).max() < 1e-7
+    s.close()
+
+
 def _c4_system(em, w):
     s = make_system(em, w["positions"], w["L"], w["cutoff"], w["switch"], w["atoms"])
     s.set_exclusions(*w["excl"])
