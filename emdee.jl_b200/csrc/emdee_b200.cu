@@ -1760,6 +1760,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     if (s->last_mode != EMDEE_CUTOFF) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: forces must come from EMDEE_CUTOFF mode");
     if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
     const bool adaptive = rebin_every < 0 && s->skin > 0;      // rebin_every < 0: re-bin when the skin is used up
+    int64_t resume_at = -1;          // >= 0: the fused loop handed this step over after its kick, drift and re-binning
     if (s->fuse_vv && c->nranks == 1 && list_capable(s) && s->fl_persistent && nsteps > 0) {
         // One kernel per step: the stepping kernel's epilogue finishes step n (second half-kick) and starts step n+1
         // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
@@ -1767,6 +1768,8 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         for (int k = 0; k < 3; k++)
             if (!s->s_alt[k]) EMDEE_TRY(dev_alloc(&s->s_alt[k], (size_t)s->cap));
         bool drifted = false;
+        const char *ue = getenv("EMDEE_DEBUG_UNFUSE_AT");
+        const int64_t unfuse_at = ue ? atoll(ue) : -1;
         for (int64_t st = 0; st < nsteps; st++) {
             bool rebin = !s->list_valid || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
             if (!drifted) EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1, adaptive && !rebin));
@@ -1781,7 +1784,13 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
             s->kick_pending = false;
             s->steps_since_bin++;
             if (rebin) EMDEE_TRY(do_bin(s, s->ndiv));
-            if (!(list_capable(s) && s->fl_persistent)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_vv_step: the re-binning left the fused path unusable (EMDEE_FUSE_VV=0)");
+            if (!(list_capable(s) && s->fl_persistent) || (rebin && st > 0 && st == unfuse_at)) {
+                // the re-binning chose bricks whose two staging buffers no longer fit (denser cells): this step's atoms are
+                // already kicked, drifted and re-binned, so evaluate its forces with the generic path and carry on there
+                if (st == unfuse_at) s->fl_persistent = false;      // EMDEE_DEBUG_UNFUSE_AT=<step>: exercise this branch (tests)
+                resume_at = st;
+                break;
+            }
             if (!s->list_valid) {
                 EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1));
                 s->list_valid = true;
@@ -1801,17 +1810,21 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 drifted = true;
             }
         }
-        s->kick_pending = false;
-        s->last_bitmask = EMDEE_FORCES;
-        s->forces_valid = true;
-        return EMDEE_OK;
+        if (resume_at < 0) {
+            s->kick_pending = false;
+            s->last_bitmask = EMDEE_FORCES;
+            s->forces_valid = true;
+            return EMDEE_OK;
+        }
     }
-    for (int64_t st = 0; st < nsteps; st++) {
+    for (int64_t st = std::max<int64_t>(resume_at, 0); st < nsteps; st++) {
         // A pair list must be built at the positions the cells were binned at (both rely on "no atom moved
         // more than skin/2 since the binning"), so a missing list forces a re-binning on this step.
         const bool need_list = list_capable(s) && !s->list_valid;
         bool rebin = need_list || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
-        if (adaptive && !rebin) {
+        if (st == resume_at) {
+            rebin = true;            // taken over from the fused loop: kicked, drifted and re-binned already
+        } else if (adaptive && !rebin) {
             // re-bin exactly when an atom has moved more than skin/2 since the last binning: one 4-byte read-back per
             // step (all ranks must take the same decision: max over ranks)
             EMDEE_TRY(launch_vv(s, dt, 1, 0, true));
@@ -1824,9 +1837,11 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
             rebin = (double)d2max > 0.25 * s->skin * s->skin;
         } else
             EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1));     // [kick2 of the previous step] + kick1 + drift
-        s->kick_pending = false;
-        s->steps_since_bin++;
-        if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));
+        if (st != resume_at) {
+            s->kick_pending = false;
+            s->steps_since_bin++;
+            if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));
+        }
         if (s->grid_ok) {
             // pair list: built (k_list_build, a filter) right after a (re-)binning, walked (k_force_list) on every step
             if (list_capable(s)) {

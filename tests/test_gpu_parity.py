@@ -250,10 +250,14 @@ def test_exclusions_molecular(em, oracle, dioxin_water):
     s.close()
 
 
-@pytest.mark.parametrize("fuse_vv", [0, 1])
+@pytest.mark.parametrize("fuse_vv", [0, 1, 2])
 def test_velocity_verlet(em, oracle, fuse_vv, monkeypatch):
-    """fuse_vv = 1: kick and drift run in the stepping kernel's epilogue (one kernel per step) instead of k_vv."""
-    monkeypatch.setenv("EMDEE_FUSE_VV", str(fuse_vv))
+    """fuse_vv = 1: kick and drift run in the stepping kernel (one kernel per step) instead of k_vv; 2: the fused loop
+    hands over to the generic loop in the middle of a call (what happens when a re-binning picks bricks whose two
+    staging buffers no longer fit; forced here at the re-binning of step 5 by EMDEE_DEBUG_UNFUSE_AT)."""
+    monkeypatch.setenv("EMDEE_FUSE_VV", str(min(fuse_vv, 1)))
+    if fuse_vv == 2:
+        monkeypatch.setenv("EMDEE_DEBUG_UNFUSE_AT", "5")
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
     atoms = em.workloads.lj_fluid_atoms(N)
