@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the nonbonded hot path on synthetic FCC Lennard-Jones fluids.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c3|c2|c1|c4|c5]
 
 A "step" is one velocity-Verlet step of the whole fluid: [second half-kick + first half-kick + drift]
 kernel, re-binning when an atom has moved more than skin/2 since the last binning (or at a fixed cadence,
@@ -21,6 +21,12 @@ roofline: dominant kernel k_force_list_p (the pair-list stepping kernel, one lau
           stream, emdee_profile_begin/end/kind); peak = DFMA throughput measured on this GPU in the same run
           (MEASURED_PEAKS.json holds no FP64 number).  The pair-list build kernel (one launch per re-binning)
           is reported beside it; "traffic" is the DRAM bytes per launch of the ncu capture under profiles/.
+cpu_baseline: the OpenMP cell-list oracle on all host cores on a bounded sample of the same workload, plus
+          "reference_case": BASELINE configs[0] (N=4000, all pairs) through the C ABI with host arrays next to the
+          reference's own CPU path (the serial loop of naively_compute_nonbonded!, one thread).
+clocks  : SM clock and throttle reasons sampled through NVML every millisecond inside the timed region.
+Other workloads (parity-test configurations, not bench lines of the driver): c1, c2, c5 (FCC fluids) and c4 (the
+reference's molecular test system replicated to 1,107,351 atoms, exclusions, 5 LJ classes; lengths in Angstrom).
 The oracle (oracle/) is used here only for the cpu_baseline leg and for --impl reference.
 """
 import argparse
