@@ -32,4 +32,4 @@ from .api import (  # noqa: F401
     surrounding_cells,
     update_cells_,
 )
-from . import workloads  # noqa: F401
+from . import modelling, trajectory, workloads  # noqa: F401
