@@ -80,11 +80,29 @@ def dioxin_water():
     lj = {a.get("type"): (float(a.get("sigma")), float(a.get("epsilon"))) for a in nb.findall("Atom")}
     types = sorted(tmass)
     tidx = np.array([types.index(tname[(rn, an)]) for rn, an in zip(resn, names)], dtype=np.int32)
+    # the product's own readers (emdee.jl_b200/modelling.py) must arrive at the same arrays as this inline parser
+    from emdee_jl_b200 import modelling as md
+    from emdee_jl_b200 import workloads as wl
+    ff = md.ForceField(os.path.join(REF, "dibenzo-p-dioxin-in-water.xml"))
+    fx = md.System(os.path.join(REF, "dibenzo-p-dioxin-in-water.pdb"), ff).fixture(ff)
+    assert np.array_equal(fx["positions"], pos) and np.array_equal(fx["bonds"], bonds) and np.array_equal(fx["type_index"], tidx)
+    # CUTOFF evaluation of the single box (rc = 10 A, rs = 9 A, sigma nm -> A, 1-2/1-3 exclusions): C oracle, cross-checked
+    # against the numpy twin (exact pair set, forces / energies to rounding) before it is stored
+    sig = np.array([lj[t][0] for t in types])[tidx] * 10.0
+    eps = np.array([lj[t][1] for t in types])[tidx]
+    atoms = np.stack([0.5 * sig, 2.0 * np.sqrt(eps)], axis=1)
+    base, mask = wl.exclusion_masks(len(names), bonds)
+    cut = oc.cutoff_cells(pos, box, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
+    f2, e2, w2, ij = on.cutoff_compute(pos, box, 10.0, 9.0, atoms, base, mask)
+    assert np.array_equal(on.pair_digest(ij), cut["digest"]) and ij.shape[0] == cut["npairs"]
+    assert np.abs(f2 - cut["forces"]).max() < 1e-11 and np.abs(e2 - cut["energies"]).max() < 1e-12
     np.savez_compressed(
         os.path.join(HERE, "dioxin_water.npz"), positions=pos, box=box, bonds=bonds, residue=resi.astype(np.int32),
         type_index=tidx, type_names=np.array(types), type_sigma_nm=np.array([lj[t][0] for t in types]),
         type_epsilon=np.array([lj[t][1] for t in types]), type_mass=np.array([tmass[t] for t in types]),
-        lj14scale=float(nb.get("lj14scale")))
+        lj14scale=float(nb.get("lj14scale")),
+        cutoff_forces=cut["forces"], cutoff_E=cut["E"], cutoff_W=cut["W"], cutoff_npairs=np.int64(cut["npairs"]),
+        cutoff_digest=cut["digest"], excl_base=base, excl_mask=mask)
     print("dioxin_water: %d atoms, %d bonds, box %.3f, types %s" % (len(names), len(bonds), box, types))
 
 

@@ -247,6 +247,12 @@ def test_exclusions_molecular(em, oracle, dioxin_water):
         assert np.array_equal(s.pair_set_digest(), ref["digest"])
     noex = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1)
     assert noex["npairs"] - ref["npairs"] == sum(bin(int(m)).count("1") for m in mask) // 2
+    # ... and against the committed golden answers of this fixture (tests/golden/make_golden.py)
+    assert np.array_equal(s.pair_set_digest(), g["cutoff_digest"])
+    E, W, npairs = s.totals()
+    assert npairs == int(g["cutoff_npairs"])
+    assert abs(E - float(g["cutoff_E"])) <= E_TOL * abs(float(g["cutoff_E"])) and abs(W - float(g["cutoff_W"])) <= E_TOL * abs(float(g["cutoff_W"]))
+    assert np.abs(s.forces() - g["cutoff_forces"]).max() <= F_TOL * frms(g["cutoff_forces"])
     s.close()
 
 

@@ -178,6 +178,37 @@ def test_exclusions(oracle, em, dioxin_water):
     assert len(dropped) == nexcl        # bonded neighbours are all well inside 10 A
 
 
+def _molecular_inputs(em, g):
+    sig = g["type_sigma_nm"][g["type_index"]] * 10.0
+    eps = g["type_epsilon"][g["type_index"]]
+    atoms = np.stack([0.5 * sig, 2.0 * np.sqrt(eps)], axis=1)
+    base, mask = em.workloads.exclusion_masks(g["positions"].shape[0], g["bonds"])
+    return atoms, base, mask
+
+
+def test_molecular_golden(oracle, em, dioxin_water):
+    """Config 4's single box (1519 atoms, 5 LJ classes, 1-2/1-3 exclusions, rc = 10 A): stored pair digest, pair count,
+    E, W and forces; the exclusion masks themselves are part of the fixture."""
+    g = dioxin_water
+    atoms, base, mask = _molecular_inputs(em, g)
+    assert np.array_equal(base, g["excl_base"]) and np.array_equal(mask, g["excl_mask"])
+    r = oracle.cutoff_cells(g["positions"], float(g["box"]), 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
+    assert r["npairs"] == int(g["cutoff_npairs"]) == 323944 and np.array_equal(r["digest"], g["cutoff_digest"])
+    assert r["E"] == pytest.approx(float(g["cutoff_E"]), rel=1e-13) and r["W"] == pytest.approx(float(g["cutoff_W"]), rel=1e-13)
+    assert np.abs(r["forces"] - g["cutoff_forces"]).max() <= 1e-12 * np.abs(g["cutoff_forces"]).max()
+    fast = oracle.cutoff_cells(g["positions"], float(g["box"]), 10.0, 9.0, atoms, ndiv=1, excl=(base, mask), fast=True)
+    assert np.array_equal(fast["digest"], r["digest"]) and abs(fast["E"] - r["E"]) <= 1e-11 * abs(r["E"])
+
+
+def test_molecular_numpy_twin(oracle, em, dioxin_water):
+    """The same evaluation by the independent numpy restatement: identical pair set, forces and energies to rounding."""
+    g = dioxin_water
+    atoms, base, mask = _molecular_inputs(em, g)
+    f, e, w, ij = on.cutoff_compute(g["positions"], float(g["box"]), 10.0, 9.0, atoms, base, mask)
+    assert ij.shape[0] == int(g["cutoff_npairs"]) and np.array_equal(on.pair_digest(ij), g["cutoff_digest"])
+    assert np.abs(f - g["cutoff_forces"]).max() < 1e-11 and abs(e.sum() - float(g["cutoff_E"])) <= 1e-12 * abs(float(g["cutoff_E"]))
+
+
 def test_vv_energy_conservation(oracle, em):
     pos, L = em.workloads.fcc_lattice(5)
     N = pos.shape[0]
