@@ -43,3 +43,25 @@ def halo_plan(rank, nranks, M, R):
         "recv_upper_ghosts": [(z1 + k) % M for k in range(R)],
         "order": ("send_to_lower", "send_to_upper", "recv_upper_ghosts", "recv_lower_ghosts"),
     }
+
+
+def migration_targets(zplane, rank, nranks, M):
+    """Where the atoms a rank owns go at a re-binning, from the global z plane of their new cell -- the rule of
+    k_cell_index_slab (csrc/slab.cuh): with dz = (z - z0) mod M, an atom stays if dz < nz, moves up if it is nearer
+    to the top of the slab (dz - nz < M - dz) and down otherwise.  0 = stays, +1 = to the upper neighbour, -1 = to
+    the lower one.  An atom that lands beyond the neighbour's slab is an error (between re-binnings an atom moves at
+    most skin/2, less than one plane)."""
+    z0, z1 = plane_range(rank, nranks, M)
+    nz = z1 - z0
+    out = []
+    for z in zplane:
+        dz = (int(z) - z0) % M
+        if dz < nz:
+            out.append(0)
+            continue
+        step = 1 if dz - nz < M - dz else -1
+        t0, t1 = plane_range((rank + step) % nranks, nranks, M)
+        if not t0 <= int(z) % M < t1:
+            raise ValueError("an atom moved to plane %d, beyond the neighbours of rank %d" % (int(z) % M, rank))
+        out.append(step)
+    return out

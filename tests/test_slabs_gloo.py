@@ -75,18 +75,38 @@ def _worker(rank, world, port, ndiv, q):
     nown = torch.tensor([own.size], dtype=torch.int64)
     dist.all_reduce(nown)
     ok &= int(tot) == pairs.shape[0] and int(nown) == N
+    # ---- migration at a re-binning: the atoms drift (a fraction of a plane), leavers go to the ring neighbours ----
+    rng = np.random.default_rng(5)
+    moved = pos + rng.normal(scale=0.25, size=pos.shape)        # same numbers on every rank
+    znew = (oc.cell_index(moved, L, M) - 1) // (M * M)
+    tgt = np.array(slabs.migration_targets(znew[own], rank, world, M))
+    go_lo, go_hi = own[tgt == -1].astype(np.int64), own[tgt == 1].astype(np.int64)
+    n_hi, n_lo = torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64)
+    ops = [dist.P2POp(dist.isend, torch.tensor([go_lo.size]), lower), dist.P2POp(dist.isend, torch.tensor([go_hi.size]), upper),
+           dist.P2POp(dist.irecv, n_hi, upper), dist.P2POp(dist.irecv, n_lo, lower)]
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    in_hi, in_lo = torch.zeros(int(n_hi), dtype=torch.int64), torch.zeros(int(n_lo), dtype=torch.int64)
+    ops = [dist.P2POp(dist.isend, torch.from_numpy(go_lo), lower), dist.P2POp(dist.isend, torch.from_numpy(go_hi), upper),
+           dist.P2POp(dist.irecv, in_hi, upper), dist.P2POp(dist.irecv, in_lo, lower)]
+    for r in dist.batch_isend_irecv(ops):
+        r.wait()
+    new_own = np.sort(np.concatenate([own[tgt == 0], in_lo.numpy(), in_hi.numpy()]))
+    expect = np.nonzero((znew >= z0) & (znew < z1))[0]
+    ok &= np.array_equal(new_own, expect) and (go_lo.size + go_hi.size) > 0
     q.put((rank, bool(ok), int(tot), pairs.shape[0]))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ndiv", [1, 2])
-def test_slab_plan_world2(ndiv):
+@pytest.mark.parametrize("world,ndiv", [(2, 1), (2, 2), (3, 1)])
+def test_slab_plan_world2(world, ndiv):
+    """world 2: both ring neighbours are the same peer (message order matters); world 3: distinct neighbours."""
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, ndiv, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, ndiv, q)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
