@@ -202,3 +202,34 @@ def surrounding_cells_loops(L, cutoff, M, action):
             row.append(1 + pbc(i + v[0]) + M * pbc(j + v[1]) + M * M * pbc(k + v[2]))
         table.append(row)
     return table
+
+
+def naive_allpairs_loops(pos, L, model, atoms):
+    """naively_compute_nonbonded! (src/nonbonded.jl:122-155) as a literal scalar loop with the reference's mixed
+    precision: pair math in pos.dtype (Float32 in the reference), i-side accumulators in Float64 (:132-134), j-side
+    accumulated straight into the arrays (:141,143,145), i-side folded in after the j loop (:147-149).  Pure-Python
+    loops -- small N only; third, independent restatement that the C oracle's f32 and f64 instantiations must match
+    bit for bit."""
+    T = pos.dtype.type
+    N = pos.shape[0]
+    Lt = T(L)
+    sp = pos / Lt                                                         # :124
+    f = np.zeros((N, 3), dtype=T); e = np.zeros(N, dtype=T); w = np.zeros(N, dtype=T)
+    half = T(2)
+    for i in range(N - 1):
+        ei, wi, fi = np.float64(0), np.float64(0), np.zeros(3)             # :132-134
+        for j in range(i + 1, N):
+            d = sp[i] - sp[j]
+            rv = Lt * (d - np.rint(d))                                    # :136
+            r2 = (rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]           # :137  sum(x.*y) is a left fold
+            E, W = interaction(np.array([r2], dtype=T), model, atoms[i, 0], atoms[i, 1], atoms[j, 0], atoms[j, 1])
+            E, W = E[0], W[0]
+            fij = (W / r2) * rv                                           # :139
+            fi += fij.astype(np.float64)                                  # :140
+            f[j] -= fij                                                   # :141
+            ei += np.float64(E / half); e[j] += E / half                  # :142-143
+            wi += np.float64(W / half); w[j] += W / half                  # :144-145
+        f[i] = (f[i].astype(np.float64) + fi).astype(T)                   # :147
+        e[i] = T(np.float64(e[i]) + ei)                                   # :148
+        w[i] = T(np.float64(w[i]) + wi)                                   # :149
+    return f, e, w

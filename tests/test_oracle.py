@@ -76,6 +76,20 @@ def test_allpairs_numpy_twin_bitwise(oracle, lj_sample):
     assert np.array_equal(f, f2) and np.array_equal(e, e2) and np.array_equal(w, w2)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_allpairs_scalar_loop_bitwise(oracle, lj_sample, dtype):
+    """The C oracle (both instantiations) against a literal scalar-loop restatement of naively_compute_nonbonded!
+    with the reference's mixed-precision accumulators: bit for bit, N = 60 atoms of the fixture."""
+    n = 60
+    pos = np.ascontiguousarray(lj_sample["positions"][:n]).astype(dtype)
+    model = oracle.lj_model(3.0, 2.5, dtype)
+    atoms = np.tile(oracle.lj_atom(1, 1, dtype), (n, 1))
+    f, e, w = oracle.naive_allpairs(pos, 10.0, model, atoms)
+    f2, e2, w2 = on.naive_allpairs_loops(pos, 10.0, model, atoms)
+    assert f.dtype == dtype and f2.dtype == dtype
+    assert np.array_equal(f, f2) and np.array_equal(e, e2) and np.array_equal(w, w2)
+
+
 def test_float32_reference_criterion(oracle, lj_sample):
     """The reference's own test (test/runtests.jl:39-41): tile kernel vs naive loop < 1e-4, Float32."""
     g = lj_sample
