@@ -233,3 +233,58 @@ def naive_allpairs_loops(pos, L, model, atoms):
         e[i] = T(np.float64(e[i]) + ei)                                   # :148
         w[i] = T(np.float64(w[i]) + wi)                                   # :149
     return f, e, w
+
+
+def tiles_allpairs_loops(pos, L, tiles, model, atoms, bitmask=7):
+    """compute_tile! + compute_nonbonded! (src/nonbonded.jl:44-120) lane by lane in plain loops: 1-based lane ids,
+    partner lane j = (tid+m-1)%32+1 (:68), returning lane k = (tid+32-m-1)%32+1 (:69), shuffles modelled by reading
+    the other lane's value of the same iteration, atomics applied in tile order / lane order, I side before J side.
+    Lanes beyond N are masked (the reference would read out of bounds).  Small N only."""
+    T = pos.dtype.type
+    N = pos.shape[0]
+    Lt = T(L)
+    f = np.zeros((N, 3), dtype=T); e = np.zeros(N, dtype=T); w = np.zeros(N, dtype=T)
+    for bI, bJ in np.asarray(tiles).reshape(-1, 2).tolist():
+        diag = bI == bJ
+        I = [(bI - 1) * 32 + tid for tid in range(1, 33)]                # 1-based atom ids, lane tid at index tid-1
+        J = [(bJ - 1) * 32 + tid for tid in range(1, 33)]
+        zero3 = np.zeros(3, dtype=T)
+        si = [pos[a - 1] / Lt if a <= N else zero3 for a in I]           # :60
+        sj = [pos[a - 1] / Lt if a <= N else zero3 for a in J]           # :61
+        fi = [zero3.copy() for _ in range(32)]; fj = [zero3.copy() for _ in range(32)]
+        ei = [T(0)] * 32; ej = [T(0)] * 32; wi = [T(0)] * 32; wj = [T(0)] * 32
+        for m in range(1, 32 - int(diag) + 1):                           # :67
+            fij, Eij, Wij = [zero3] * 32, [T(0)] * 32, [T(0)] * 32
+            for tid in range(1, 33):
+                j = (tid + m - 1) % 32 + 1                               # :68
+                if I[tid - 1] > N or J[j - 1] > N:
+                    continue
+                d = si[tid - 1] - sj[j - 1]
+                rv = Lt * (d - np.rint(d))                               # :70
+                r2 = (rv[0] * rv[0] + rv[1] * rv[1]) + rv[2] * rv[2]      # :71
+                ai, aj = atoms[I[tid - 1] - 1], atoms[J[j - 1] - 1]
+                E, W = interaction(np.array([r2], dtype=T), model, ai[0], ai[1], aj[0], aj[1])   # :72
+                Eij[tid - 1], Wij[tid - 1] = E[0], W[0]
+                fij[tid - 1] = (W[0] / r2) * rv                          # :74
+            for tid in range(1, 33):
+                k = (tid + 32 - m - 1) % 32 + 1                          # :69
+                fi[tid - 1] = fi[tid - 1] + fij[tid - 1]                 # :75
+                fj[tid - 1] = fj[tid - 1] - fij[k - 1]                   # :76
+                ei[tid - 1] = ei[tid - 1] + Eij[tid - 1]; ej[tid - 1] = ej[tid - 1] + Eij[k - 1]   # :79-80
+                wi[tid - 1] = wi[tid - 1] + Wij[tid - 1]; wj[tid - 1] = wj[tid - 1] + Wij[k - 1]   # :83-84
+        for tid in range(1, 33):                                         # :88-94
+            a = I[tid - 1]
+            if a > N:
+                continue
+            if bitmask & 1: f[a - 1] += fi[tid - 1]
+            if bitmask & 2: e[a - 1] += T(0.5) * ei[tid - 1]
+            if bitmask & 4: w[a - 1] += T(0.5) * wi[tid - 1]
+        if not diag:                                                     # :96-104
+            for tid in range(1, 33):
+                a = J[tid - 1]
+                if a > N:
+                    continue
+                if bitmask & 1: f[a - 1] += fj[tid - 1]
+                if bitmask & 2: e[a - 1] += T(0.5) * ej[tid - 1]
+                if bitmask & 4: w[a - 1] += T(0.5) * wj[tid - 1]
+    return f, e, w

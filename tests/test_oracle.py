@@ -90,6 +90,24 @@ def test_allpairs_scalar_loop_bitwise(oracle, lj_sample, dtype):
     assert np.array_equal(f, f2) and np.array_equal(e, e2) and np.array_equal(w, w2)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [64, 50])
+def test_tile_schedule_scalar_loop_bitwise(oracle, lj_sample, dtype, n):
+    """compute_tile!'s lane schedule (partner lane, returning lane, epilogue order) restated a second time in plain
+    loops: the C oracle's tile simulation matches it bit for bit (n = 64: full tiles; n = 50: masked tail lanes)."""
+    pos = np.ascontiguousarray(lj_sample["positions"][:n]).astype(dtype)
+    model = oracle.lj_model(3.0, 2.5, dtype)
+    atoms = np.tile(oracle.lj_atom(1, 1, dtype), (n, 1))
+    tiles = oracle.tiles(n)
+    f, e, w = oracle.tiles_allpairs(pos, 10.0, tiles, model, atoms)
+    f2, e2, w2 = on.tiles_allpairs_loops(pos, 10.0, tiles, model, atoms)
+    assert np.array_equal(f, f2) and np.array_equal(e, e2) and np.array_equal(w, w2)
+    # and the schedule visits every ordered (lane, partner) exactly once: tile order == naive order up to summation order
+    fn, en, wn = oracle.naive_allpairs(pos, 10.0, model, atoms)
+    tol = 2e-4 if dtype == np.float32 else 1e-11
+    assert np.abs(f - fn).max() < tol * max(1.0, np.abs(fn).max()) and abs(e.sum() - en.sum()) < tol * abs(en.sum())
+
+
 def test_float32_reference_criterion(oracle, lj_sample):
     """The reference's own test (test/runtests.jl:39-41): tile kernel vs naive loop < 1e-4, Float32."""
     g = lj_sample
