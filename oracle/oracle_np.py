@@ -288,3 +288,16 @@ def tiles_allpairs_loops(pos, L, tiles, model, atoms, bitmask=7):
                 if bitmask & 2: e[a - 1] += T(0.5) * ej[tid - 1]
                 if bitmask & 4: w[a - 1] += T(0.5) * wj[tid - 1]
     return f, e, w
+
+
+def vv_steps_twin(pos, vel, forces, mass, L, cutoff, switch, atoms, dt, nsteps, excl_base=None, excl_mask=None):
+    """Velocity-Verlet as the oracle defines it (v += dt/2m f; r += dt v; f = F(r); v += dt/2m f) on the numpy twin's
+    force evaluation.  No fused multiply-adds here, so agreement with the C oracle is to rounding, not bitwise."""
+    pos, vel, forces = pos.copy(), vel.copy(), forces.copy()
+    h = (0.5 * dt / mass)[:, None]
+    for _ in range(nsteps):
+        vel = vel + h * forces
+        pos = pos + dt * vel
+        forces = cutoff_compute(pos, L, cutoff, switch, atoms, excl_base, excl_mask)[0]
+        vel = vel + h * forces
+    return pos, vel, forces

@@ -260,6 +260,20 @@ def test_vv_energy_conservation(oracle, em):
     assert np.abs(v.sum(axis=0)).max() < 1e-9          # momentum conserved
 
 
+def test_vv_numpy_twin(oracle, em):
+    """The oracle's velocity-Verlet against the numpy twin (independent force evaluation, unfused updates), unequal
+    masses, five steps: positions and velocities to rounding."""
+    pos, L = em.workloads.fcc_lattice(4)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    vel = em.workloads.maxwell_velocities(N, 1.2)
+    mass = 1.0 + 0.5 * em.workloads.uniform01(np.arange(1, N + 1) + (1 << 50))
+    f0 = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1)["forces"]
+    p, v, f = oracle.vv_steps(pos, vel, f0, mass, L, 2.5, 2.0, atoms, 0.004, 5)
+    p2, v2, f2 = on.vv_steps_twin(pos, vel, f0, mass, L, 2.5, 2.0, atoms, 0.004, 5)
+    assert np.abs(p - p2).max() < 1e-13 and np.abs(v - v2).max() < 1e-12 and np.abs(f - f2).max() < 1e-10
+
+
 def test_workload_generator(em):
     pos, L = em.workloads.fcc_lattice(10)
     assert pos.shape == (4000, 3) and L == pytest.approx(16.79596, abs=1e-5)
