@@ -26,6 +26,9 @@
 #ifndef FLP_STAGE_U
 #define FLP_STAGE_U 9        // atoms per producer thread in flight: ~2300 staged atoms / 128 threads = two batches
 #endif
+#ifndef FLP_PRELOAD2
+#define FLP_PRELOAD2 0       // 1: the recipes of the SECOND staging batch are also loaded before the buffer is handed over
+#endif                       // (opt-in experiment of DESIGN section 9 item 2; written after round 1's GPU budget was spent: unmeasured)
 #ifndef FLP_NPROD
 #define FLP_NPROD 4
 #endif
@@ -238,6 +241,14 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
             // time, and the staging latency that follows the hand-over is what the consumers then wait for
             load_batch(1 + tid);
+#if FLP_PRELOAD2
+            int2 rc2[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = 1 + tid + (U + u) * PN;
+                rc2[u] = i < n1 ? recipe[i] : make_int2(0, 0);
+            }
+#endif
             if (tid == 0) claimed[k & 1] = gridDim.x + atomicAdd(a.brick_counter, 1);
             bar_sync(5, PN);
             const int nb = claimed[k & 1];
@@ -273,7 +284,18 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 B.scal[4] = brick;
             }
             store_batch(1 + tid);
+#if FLP_PRELOAD2
+            {                                       // second batch: its recipes are already in registers, one round trip less
+#pragma unroll
+                for (int u = 0; u < U; u++) rc[u] = rc2[u];
+#pragma unroll
+                for (int u = 0; u < U; u++) { sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x]; }
+                store_batch(1 + tid + U * PN);
+            }
+            for (int i0 = 1 + tid + 2 * U * PN; i0 < n1; i0 += U * PN) {
+#else
             for (int i0 = 1 + tid + U * PN; i0 < n1; i0 += U * PN) {
+#endif
                 load_batch(i0);
                 store_batch(i0);
             }
