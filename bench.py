@@ -226,6 +226,12 @@ def cpu_leg(args, w, budget_s, steps, warmup):
     from oracle import oracle_c
 
     oracle_c.build()
+    if os.environ.get("WORLD_SIZE", "1") != "1" or "OMP_NUM_THREADS" not in os.environ:
+        # under torchrun every rank gets OMP_NUM_THREADS=1; this leg runs on rank 0 alone and uses the whole host
+        try:
+            oracle_c.set_num_threads(len(os.sched_getaffinity(0)), fast=True)
+        except AttributeError:
+            oracle_c.set_num_threads(os.cpu_count() or 1, fast=True)
     cores = oracle_c.num_threads(fast=True)
     mol = args.workload in MOLECULAR
     # probe the evaluation rate on a small sample, then pick the largest sample that fits the budget

@@ -46,6 +46,17 @@
 #undef RINT
 #undef FLOOR
 
+/* bench.py --impl reference under torchrun: the launcher exports OMP_NUM_THREADS=1 for every rank, but the reference
+ * arm runs on rank 0 alone and must use all the host threads it can (n <= 0: leave the runtime's default alone). */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

@@ -7,6 +7,7 @@ extern "C" {
 #endif
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 uint64_t oracle_mix64(uint64_t z);
 
 /* src/lennard_jones.jl:6-18,25-42 */

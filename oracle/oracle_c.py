@@ -36,6 +36,8 @@ def lib(fast=False):
             build()
         L = C.CDLL(path)
         L.oracle_num_threads.restype = C.c_int
+        L.oracle_set_num_threads.restype = None
+        L.oracle_set_num_threads.argtypes = [C.c_int]
         L.oracle_mix64.restype = _u64
         L.oracle_mix64.argtypes = [_u64]
         L.oracle_tiles.restype = _i64
@@ -71,6 +73,11 @@ def _arr(a, dtype):
 
 def num_threads(fast=False):
     return lib(fast).oracle_num_threads()
+
+
+def set_num_threads(n, fast=False):
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1 to every rank; the CPU arm wants the host)."""
+    lib(fast).oracle_set_num_threads(int(n))
 
 
 def lj_model(cutoff, switch, dtype=np.float64):
