@@ -122,6 +122,42 @@ def test_color_ranks_and_isomorphism(em):
     assert p == [1, 0, 2] or p == [1, 2, 0]
 
 
+def test_isomorphism_against_brute_force(em):
+    """Random small coloured graphs: the backtracking matcher finds a colour-preserving isomorphism exactly when a
+    brute-force search over all permutations does, and what it returns is one."""
+    import itertools
+
+    from emdee_jl_b200 import modelling as md
+
+    rng = np.random.default_rng(4)
+    found = missed = 0
+    for trial in range(300):
+        n = int(rng.integers(2, 7))
+        a = np.triu(rng.random((n, n)) < 0.45, 1)
+        a = a | a.T
+        ca = rng.integers(0, 2, n).tolist()
+        if trial % 2:                                        # an isomorphic copy: relabel a
+            perm = rng.permutation(n)
+            b = a[np.ix_(perm, perm)]
+            cb = [ca[k] for k in perm]
+        else:                                                # an unrelated graph with the same colour multiset
+            b = np.triu(rng.random((n, n)) < 0.45, 1)
+            b = b | b.T
+            cb = list(rng.permutation(ca))
+        brute = any(all(ca[i] == cb[p[i]] for i in range(n)) and all(a[i, j] == b[p[i], p[j]] for i in range(n) for j in range(n))
+                    for p in itertools.permutations(range(n)))
+        got = md.isomorphism(a, ca, b, cb)
+        assert (got is not None) == brute, (trial, a, b, ca, cb)
+        if got is not None:
+            found += 1
+            assert sorted(got) == list(range(n))
+            assert all(ca[i] == cb[got[i]] for i in range(n))
+            assert all(a[i, j] == b[got[i], got[j]] for i in range(n) for j in range(n))
+        else:
+            missed += 1
+    assert found > 100 and missed > 50
+
+
 def test_system_matching_and_order(em, files):
     from emdee_jl_b200 import modelling as md
 
