@@ -70,3 +70,27 @@ def test_julia_shim_binds_declared_symbols():
     text = open(path).read()
     called = set(re.findall(r"ccall\(\(:(emdee_[a-z0-9_]+),", text))
     assert called and called <= set(declared_symbols())
+
+
+def test_header_is_plain_c_and_links(em, tmp_path):
+    """include/emdee_b200.h compiles as strict C11 (what cgo / ccall / ctypes see), examples/abi_example.c links against
+    the shared library, runs, and -- on a box without a B200 -- reports EMDEE_ERR_CUDA instead of computing on the CPU."""
+    import shutil
+    import subprocess
+
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if not gcc:
+        pytest.skip("no C compiler")
+    em.build_library()
+    exe = str(tmp_path / "abi_example")
+    libdir = os.path.dirname(em.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "abi_example.c"), "-o", exe, "-L", libdir, "-lemdee_b200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    import torch
+
+    if torch.cuda.is_available():
+        assert out.returncode == 0 and "cutoff: E" in out.stdout, out.stdout + out.stderr
+    else:
+        assert out.returncode == 3 and "status 2" in out.stderr and "libemdee_b200 version" in out.stdout, out.stdout + out.stderr
