@@ -250,7 +250,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             }
 #endif
             if (tid == 0) claimed[k & 1] = gridDim.x + atomicAdd(a.brick_counter, 1);
-            bar_sync(5, PN);
+            bar_sync(1 + 2 * NBUF, PN);        // producers only; ids 1..NBUF are full[], NBUF+1..2*NBUF empty[]
             const int nb = claimed[k & 1];
             {   // one brick ahead: header into registers, recipe into L2 (it streams from HBM; the coordinates it points
                 // at were written by k_vv just before this kernel and are L2 hits)
