@@ -6,8 +6,10 @@
 A "step" is one velocity-Verlet step of the whole fluid: [second half-kick + first half-kick + drift]
 kernel, re-binning when an atom has moved more than skin/2 since the last binning (or at a fixed cadence,
 --rebin-every), one LJ force evaluation from the pair list.  The timed region holds
-exactly K steps issued as ONE emdee_vv_step call (no host synchronisation inside), bracketed by a
-barrier and a device synchronisation, timed with CUDA events on the library's stream, max over ranks.
+exactly K steps issued as ONE emdee_vv_step call, bracketed by a barrier and a device synchronisation, timed
+with CUDA events on the library's stream, max over ranks.  Host synchronisations INSIDE that call (they are part
+of the measured time): the adaptive re-binning criterion reads one 4-byte word back per step, and every
+re-binning reads the brick capacity (and, in a slab decomposition, the slab's atom counts) back once.
 
 metric  : LJ pair-interactions/s = (unique pairs i<j with r2 <= rc2, counted by the audit kernel) x K / t
           ("atom_steps_per_s" is printed beside it: N x K / t) -- BASELINE.json's two headline numbers.
@@ -77,6 +79,7 @@ def parse():
     ap.add_argument("--temperature", type=float, default=None, help="kT of the initial velocities (default 1.44 eps; 2.494 kJ/mol for c4)")
     ap.add_argument("--e2e-iters", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the final state (the `parity` block of the line)")
     a = ap.parse_args()
     mol = a.workload in MOLECULAR
     if a.skin is None:
@@ -306,6 +309,67 @@ def reference_case(em, ctx):
             "energy_rel_diff": float(abs(e.sum() - er.sum()) / abs(er.sum()))}
 
 
+def common_config(args, w, N, L):
+    """The keys both arms print under `config` (identical for the same command line): the workload and how the timed
+    steps relate to the 126 MB L2."""
+    return {"workload": w["desc"], "N": int(N), "L": float(L), "cutoff": w["rc"], "switch": w["rs"], "dt": args.dt, "ndiv": args.ndiv,
+            "l2": "per-step working set %.0f MB exceeds the 126 MB L2" % (N * (BYTES_VV + 48) / 1e6)
+            if N * (BYTES_VV + 48) > 126e6 else "working set fits L2 (consecutive MD steps reuse it by design)"}
+
+
+def parity_block(args, em, s, w, world, rank, allsum_arr):
+    """Parity of THIS run's final state against the CPU oracle, printed in the bench line so that the driver's own
+    1/2/4/8-GPU runs carry it ("parity under decomposition"): positions after the timed steps are gathered
+    in id order, and (i) the forces the stepping path left behind, (ii) a single-point F/E/W evaluation, (iii) the pair-set
+    digest (count, sum and xor of the pair hashes over all ranks) are compared with the oracle's on those positions.  The
+    oracle is the checker only; nothing here is timed."""
+    N, L = w["N"], w["L"]
+    s.synchronize()
+    pos = allsum_arr(s.positions())
+    f_step = allsum_arr(s.forces())
+    s.compute(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS)
+    f_sp = allsum_arr(s.forces())
+    e_sp = allsum_arr(s.energies())
+    w_sp = allsum_arr(s.virials())
+    dig = np.asarray(s.pair_set_digest(), dtype=np.uint64)
+    halves = np.array([int(dig[0]), int(dig[1]) & 0xFFFFFFFF, int(dig[1]) >> 32], dtype=np.int64)     # wrap-around sum in two halves
+    halves = allsum_arr(halves)
+    xor = int(dig[2])
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+
+        parts = [torch.zeros(2, dtype=torch.int64, device="cuda") for _ in range(world)]
+        dist.all_gather(parts, torch.tensor([xor & 0xFFFFFFFF, xor >> 32], dtype=torch.int64, device="cuda"))
+        xor = 0
+        for t in parts:
+            lo, hi = (int(x) for x in t.cpu())
+            xor ^= lo | (hi << 32)
+    s.compute(em.CUTOFF, em.FORCES)          # leave the system as the stepping path expects it
+    if rank != 0:
+        return None
+    from oracle import oracle_c
+
+    oracle_c.build()
+    try:
+        oracle_c.set_num_threads(len(os.sched_getaffinity(0)), fast=True)
+    except AttributeError:
+        oracle_c.set_num_threads(os.cpu_count() or 1, fast=True)
+    ref = oracle_c.cutoff_cells(pos, L, w["rc"], w["rs"], w["atoms"], ndiv=args.ndiv, excl=w["excl"], fast=True)
+    frms = float(np.sqrt((ref["forces"] ** 2).sum(axis=1).mean()))
+    got = [int(halves[0]), (int(halves[1]) + (int(halves[2]) << 32)) % (1 << 64), xor]
+    want = [int(x) for x in ref["digest"]]
+    out = {"checked_against": "CPU oracle (oracle/, OpenMP) on this run's final positions, N=%d, %d rank(s)" % (N, world),
+           "pair_digest_equal": got == want, "pairs": [got[0], int(ref["npairs"])],
+           "force_err_over_frms_stepping": float(np.abs(f_step - ref["forces"]).max() / frms),
+           "force_err_over_frms_single_point": float(np.abs(f_sp - ref["forces"]).max() / frms),
+           "E_rel_err": float(abs(e_sp.sum() - ref["E"]) / abs(ref["E"])), "W_rel_err": float(abs(w_sp.sum() - ref["W"]) / abs(ref["W"])),
+           "tolerances": {"pairs": "bit-exact", "E,W": 1e-10, "forces": "1e-9 F_rms"}}
+    out["ok"] = bool(out["pair_digest_equal"] and out["force_err_over_frms_stepping"] <= 1e-9 and out["force_err_over_frms_single_point"] <= 1e-9
+                     and out["E_rel_err"] <= 1e-10 and out["W_rel_err"] <= 1e-10)
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The reference is Julia
     (not installed; nothing under /root/reference compiles with gcc), so oracle/_ref does not exist and
@@ -315,12 +379,20 @@ def run_reference(args):
         return
     w = dict(zip(("n", "rc", "rs", "desc"), WORKLOADS[args.workload]))
     r = cpu_leg(args, w, budget_s=150.0, steps=args.steps, warmup=args.warmup)
+    import emdee_jl_b200 as em
+
+    if args.workload in MOLECULAR:
+        fx = np.load(GOLDEN_C4)
+        Nfull, Lfull = int(fx["positions"].shape[0]) * w["n"] ** 3, float(fx["box"]) * w["n"]
+    else:
+        Nfull, Lfull = 4 * w["n"] ** 3, em.workloads.fcc_box(w["n"])[1]
     line = {
         "impl": "reference", "metric": "LJ pair-interactions/s", "value": r["value"], "unit": "pair-interactions/s",
         "atom_steps_per_s": r["atom_steps_per_s"], "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["desc"], "sample": r["sample"], "ndiv": args.ndiv, "dt": args.dt},
+        "config": common_config(args, w, Nfull, Lfull),
+        "run": {"sample": r["sample"], "sample_N": r["N"]},
         "cpu_baseline": {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": r["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -377,6 +449,13 @@ def run_b200(args):
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t)
         return float(t.item())
+
+    def allsum_arr(a):
+        if world == 1:
+            return a
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        dist.all_reduce(t)
+        return t.cpu().numpy()
 
     def allmax(x):
         if world == 1:
@@ -462,6 +541,14 @@ def run_b200(args):
                 "bytes_per_atom_step": step_bytes / max(nloc, 1)},
     }
 
+    # ---- parity of this run's final state against the CPU oracle (outside every timed region) ------
+    parity = None
+    if not args.no_parity:
+        try:
+            parity = parity_block(args, em, s, w, world, rank, allsum_arr)
+        except Exception as ex:                      # never lose the headline line over the check; a failure is visible in the line
+            parity = {"ok": False, "error": repr(ex)}
+
     # ---- e2e: host buffers in, host buffers out, through the C ABI ---------------------------------
     pos_h = torch.from_numpy(w["pos"].copy()).pin_memory().numpy()
     f_h = torch.empty((N, 3), dtype=torch.float64).pin_memory().numpy()
@@ -505,14 +592,13 @@ def run_b200(args):
             "atom_steps_per_s": atom_steps, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["desc"], "N": N, "L": L, "cutoff": w["rc"], "switch": w["rs"], "dt": args.dt,
-                       "ndiv": args.ndiv, "skin": args.skin, "brick_cells": list(cfg["brick"]), "brick_capacity": cfg["brick_capacity"],
-                       "rebin_every": args.rebin_every if args.rebin_every >= 0 else "adaptive (skin/2 criterion)",
-                       "rebins_in_timed_steps": int(rebins),
-                       "decomposition": "z-slabs x%d" % world if world > 1 else "single GPU",
-                       "l2": "per-step working set %.0f MB exceeds the 126 MB L2" % (N * (BYTES_VV + 48) / 1e6)
-                       if N * (BYTES_VV + 48) > 126e6 else "working set fits L2 (consecutive MD steps reuse it by design)",
-                       "pairs": pairs, "wall_ms_per_step": wall / args.steps * 1e3},
+            "config": common_config(args, w, N, L),
+            "run": {"skin": args.skin, "brick_cells": list(cfg["brick"]), "brick_capacity": cfg["brick_capacity"],
+                    "rebin_every": args.rebin_every if args.rebin_every >= 0 else "adaptive (skin/2 criterion)",
+                    "rebins_in_timed_steps": int(rebins),
+                    "decomposition": "z-slabs x%d" % world if world > 1 else "single GPU",
+                    "pairs": pairs, "wall_ms_per_step": wall / args.steps * 1e3},
+            "parity": parity,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -308,6 +308,7 @@ class NonbondedSystem:
 
     def checkpoint(self):
         """Host copy of everything a restart needs, in atom-id order (additive)."""
+        self.synchronize()      # raises if a device-side check failed during the steps (skin violated, list overflow): never checkpoint such a state
         return dict(N=self.N, L=self.L, positions=self.positions(), velocities=self.velocities())
 
     def restore(self, ckpt):

@@ -190,6 +190,10 @@ struct emdee_system {
     std::vector<size_t> prof_mid_of;          // index of the event pair each mid pair belongs to
     double prof_ms[4] = {0, 0, 0, 0};         // per-kind totals of the last profile (emdee_profile_kind)
     int64_t prof_n[4] = {0, 0, 0, 0};
+    // outputs of the audit passes (pair digest / pair set): the audit re-evaluates the pairs, its forces, energies and virials go
+    // here so that the results of the last compute (and the bits of the next half-kick) are left alone
+    double *aud[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t aud_cap = 0;
     // scratch for host transfers
     double *tmp = nullptr;
     size_t tmp_bytes = 0;
@@ -225,6 +229,17 @@ static void dev_free(T *&p)
     p = nullptr;
 }
 
+static int ensure_audit_scratch(emdee_system *s)
+{
+    if (s->aud_cap >= s->cap) return EMDEE_OK;
+    for (int k = 0; k < 5; k++) {
+        if (s->aud[k]) cudaFree(s->aud[k]);
+        s->aud[k] = nullptr;
+        CUDA_TRY(cudaMalloc((void **)&s->aud[k], sizeof(double) * (size_t)s->cap));
+    }
+    s->aud_cap = s->cap;
+    return EMDEE_OK;
+}
 static int ensure_tmp(emdee_system *s, size_t bytes)
 {
     if (bytes <= s->tmp_bytes) return EMDEE_OK;
@@ -478,6 +493,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2); dev_free(s->brick_counter);
     for (int k = 0; k < 3; k++) dev_free(s->s_alt[k]);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
+    for (int k = 0; k < 5; k++) dev_free(s->aud[k]);
     for (cudaEvent_t e : s->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : s->prof_mid) cudaEventDestroy(e);
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
@@ -504,6 +520,10 @@ extern "C" int emdee_set_model(emdee_system *s, double cutoff, double sw)
     if (cutoff > 0.5 * s->L)
         EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_model: cutoff %g exceeds L/2 = %g (minimum image invalid)", cutoff, 0.5 * s->L);
     // LennardJonesModel(cutoff, switch) = new(cutoff^2, switch^2, 1/(cutoff^2 - switch^2)), src/lennard_jones.jl:10
+    if (cutoff != s->cutoff) {     // the cell grid and the pair list were sized for the old cutoff (+ skin)
+        s->binned = false;
+        s->list_valid = false;
+    }
     s->cutoff = cutoff;
     s->sw = sw;
     s->model.rc2 = cutoff * cutoff;
@@ -619,6 +639,7 @@ extern "C" int emdee_set_masses(emdee_system *s, const double *mass)
 extern "C" int emdee_set_exclusions(emdee_system *s, const int32_t *base, const uint64_t *mask)
 {
     SYS_ENTER(s, "emdee_set_exclusions");
+    s->list_valid = false;         // exclusions are applied when the pair list is built (k_list_build<EXCL>)
     if (!base || !mask) {
         s->has_excl = false;
         s->forces_valid = false;
@@ -970,6 +991,7 @@ static int do_bin(emdee_system *s, int ndiv)
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
+    s->last_bitmask = 0;        // f / en / vir are in the previous slot order: the getters fail until the next compute
     CUDA_TRY(cudaMemsetAsync(s->maxd2, 0, sizeof(unsigned), c->stream));
     if (s->grid_ok) EMDEE_TRY(choose_bricks(s));
     return EMDEE_OK;
@@ -1115,6 +1137,7 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
+    s->last_bitmask = 0;
     CUDA_TRY(cudaMemsetAsync(s->maxd2, 0, sizeof(unsigned), c->stream));
     EMDEE_TRY(choose_bricks(s));
     // brick layers whose halo reaches ghost planes (they must wait for the halo exchange)
@@ -1260,7 +1283,7 @@ static int launch_list_t(emdee_system *s, const CellArgs &a, int nblocks, bool F
     if (nblocks <= 0) return EMDEE_OK;
     if (s->fl_persistent) {     // one resident block per SM walks over the bricks (force_list_p.cuh)
         if (EW && !COUNT) return launch_list_p<MULTI, false, true>(s, a, nblocks, F);
-        return launch_list_p<MULTI, COUNT, false>(s, a, nblocks, true);
+        return launch_list_p<MULTI, COUNT, false>(s, a, nblocks, !COUNT);     // the counting pass leaves the forces alone
     }
     if (EW) EMDEE_FAIL(EMDEE_ERR_STATE, "launch_list: energies and virials need the persistent list kernel");
     // blocks of up to 192 threads run the 8-chain variant (more registers per thread), larger ones the 4-chain variant
@@ -1332,6 +1355,10 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     a.ljtab = s->ljtab; a.ntypes = s->ntypes;
     a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2];
     a.en = s->en; a.vir = s->vir;
+    if (audit) {       // side-effect free: the audit's own forces / energies / virials go to scratch arrays
+        EMDEE_TRY(ensure_audit_scratch(s));
+        a.fx = s->aud[0]; a.fy = s->aud[1]; a.fz = s->aud[2]; a.en = s->aud[3]; a.vir = s->aud[4];
+    }
     a.digest = s->digest;
     a.pairs = pairs;
     a.pair_cap = pair_cap;
@@ -1476,23 +1503,29 @@ static int launch_tiles_t(emdee_system *s, const TileArgs &a, int bitmask)
     return check_launch("k_force_tiles");
 }
 
-static int run_tiles(emdee_system *s, int bitmask, bool cull, int32_t *pairs = nullptr, int64_t pair_cap = 0)
+static int run_tiles(emdee_system *s, int bitmask, bool cull, int32_t *pairs = nullptr, int64_t pair_cap = 0, bool audit = false)
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
     if (s->tiles_default && s->ntiles == 0) EMDEE_TRY(default_tiles(s));
     const int64_t n = s->nown;
+    double *of[3] = {s->f[0], s->f[1], s->f[2]}, *oe = s->en, *ow = s->vir;
+    if (audit) {       // pair digest / pair set: outputs to scratch, the last compute's results stay
+        EMDEE_TRY(ensure_audit_scratch(s));
+        for (int k = 0; k < 3; k++) of[k] = s->aud[k];
+        oe = s->aud[3]; ow = s->aud[4];
+    }
     // compute_nonbonded! zeroes the selected outputs, then accumulates with atomics (src/nonbonded.jl:112-114)
-    if (bitmask & EMDEE_FORCES) for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(s->f[k], 0, sizeof(double) * n, c->stream));
-    if (bitmask & EMDEE_ENERGIES) CUDA_TRY(cudaMemsetAsync(s->en, 0, sizeof(double) * n, c->stream));
-    if (bitmask & EMDEE_VIRIALS) CUDA_TRY(cudaMemsetAsync(s->vir, 0, sizeof(double) * n, c->stream));
+    if (bitmask & EMDEE_FORCES) for (int k = 0; k < 3; k++) CUDA_TRY(cudaMemsetAsync(of[k], 0, sizeof(double) * n, c->stream));
+    if (bitmask & EMDEE_ENERGIES) CUDA_TRY(cudaMemsetAsync(oe, 0, sizeof(double) * n, c->stream));
+    if (bitmask & EMDEE_VIRIALS) CUDA_TRY(cudaMemsetAsync(ow, 0, sizeof(double) * n, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
     TileArgs a;
     a.tiles = s->tiles; a.ntiles = s->ntiles; a.N = s->N;
     a.slot_of_id = s->slot_of_id;
     a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2]; a.hs = A.hs; a.ts = A.ts;
     a.id = A.id; a.xbase = A.xbase; a.xmask = A.xmask;
-    a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2]; a.en = s->en; a.vir = s->vir;
+    a.fx = of[0]; a.fy = of[1]; a.fz = of[2]; a.en = oe; a.vir = ow;
     a.digest = s->digest;
     a.pairs = pairs;
     a.pair_cap = pair_cap;
@@ -1581,11 +1614,13 @@ extern "C" int emdee_get_positions(emdee_system *s, double *out)
 {
     SYS_ENTER(s, "emdee_get_positions");
     if (!s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_positions: positions were never set");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_positions"));      // a skin violation during emdee_vv_step means pairs were missed
     return get3(s, A.r, out, "emdee_get_positions");
 }
 extern "C" int emdee_get_velocities(emdee_system *s, double *out)
 {
     SYS_ENTER(s, "emdee_get_velocities");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_velocities"));
     return get3(s, A.v, out, "emdee_get_velocities");
 }
 extern "C" int emdee_get_forces(emdee_system *s, double *out)
@@ -1663,20 +1698,19 @@ extern "C" int emdee_pair_set_digest(emdee_system *s, uint64_t out[3])
     SYS_ENTER(s, "emdee_pair_set_digest");
     if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_pair_set_digest: null output");
     if (!s->binned || !s->has_atoms) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: needs LJ atoms, positions and emdee_bin");
-    // the audit pass recomputes forces/energies into the same arrays with the same values
+    // the audit pass re-evaluates every pair; its forces / energies / virials go to scratch arrays, so this call changes
+    // neither the results of the last compute nor which getters are valid
     if (s->grid_ok)
         EMDEE_TRY(run_cells(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true, nullptr, 0));
     else {
         if (!s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set_digest: box too small for a cell grid and a custom tile list is set");
-        EMDEE_TRY(run_tiles(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true));
+        EMDEE_TRY(run_tiles(s, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, true, nullptr, 0, true));
     }
     unsigned long long h[4];
     CUDA_TRY(cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     EMDEE_TRY(check_device_flag(s, "emdee_pair_set_digest"));
     out[0] = h[0]; out[1] = h[1]; out[2] = h[2];
-    s->last_mode = EMDEE_CUTOFF;
-    s->last_bitmask = 7;
     return EMDEE_OK;
 }
 
@@ -1688,7 +1722,7 @@ extern "C" int emdee_pair_set(emdee_system *s, int32_t *ij, int64_t cap, int64_t
     if (!s->grid_ok && !s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_pair_set: box too small for a cell grid and a custom tile list is set");
     int32_t *d = nullptr;
     EMDEE_TRY(dev_alloc(&d, (size_t)2 * std::max<int64_t>(cap, 1)));
-    int st = s->grid_ok ? run_cells(s, 7, true, d, cap) : run_tiles(s, 7, true, d, cap);
+    int st = s->grid_ok ? run_cells(s, 7, true, d, cap) : run_tiles(s, 7, true, d, cap, true);
     unsigned long long h[4] = {0, 0, 0, 0};
     if (st == EMDEE_OK && cudaMemcpyAsync(h, s->digest, sizeof(h), cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
     if (st == EMDEE_OK && cudaStreamSynchronize(c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
@@ -1704,8 +1738,6 @@ extern "C" int emdee_pair_set(emdee_system *s, int32_t *ij, int64_t cap, int64_t
     dev_free(d);
     if (st != EMDEE_OK) EMDEE_FAIL(st, "emdee_pair_set: device failure (%s)", cudaGetErrorString(cudaGetLastError()));
     EMDEE_TRY(check_device_flag(s, "emdee_pair_set"));
-    s->last_mode = EMDEE_CUTOFF;
-    s->last_bitmask = 7;
     if (*n > cap) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_pair_set: %lld pairs exceed the buffer capacity %lld", (long long)*n, (long long)cap);
     return EMDEE_OK;
 }
@@ -1899,6 +1931,7 @@ extern "C" int emdee_kinetic_energy(emdee_system *s, double *K)
 {
     SYS_ENTER(s, "emdee_kinetic_energy");
     if (!K) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_kinetic_energy: null output");
+    EMDEE_TRY(check_device_flag(s, "emdee_kinetic_energy"));
     const int nb = 128;
     EMDEE_TRY(ensure_tmp(s, sizeof(double) * nb));
     k_kinetic<<<nb, 256, 0, c->stream>>>(s->nlo, s->nown, A.v[0], A.v[1], A.v[2], A.mass, s->tmp);

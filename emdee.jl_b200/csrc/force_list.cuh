@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
         }
         if (COUNT) npair += np;
 
-        if (active) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
+        if (active && !COUNT) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }     // the counting pass leaves the forces alone
         grp = ngrp;
     }
     if (COUNT) {

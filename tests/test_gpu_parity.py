@@ -45,12 +45,16 @@ def test_reference_test_case_allpairs(em, oracle, lj_sample):
     tiles = em.nonbonded_computation_tiles(N)
     forces = np.zeros((N, 3)); energies = np.zeros(N); virials = np.zeros(N)
     em.compute_nonbonded_(forces, energies, virials, pos, L, tiles, model, atoms, em.FORCES | em.ENERGIES | em.VIRIALS)
-    # the reference's own criterion ...
-    assert (forces - forces_ref).max() < 1e-4 and (energies - energies_ref).max() < 1e-4 and (virials - virials_ref).max() < 1e-4
+    # the reference's own criterion (test/runtests.jl:39-41), GPU tile kernel against the CPU restatement of
+    # naively_compute_nonbonded! (the oracle's serial loop) -- both arms of the reference's test, one on each side ...
+    cpu = oracle.naive_allpairs(pos, L, oracle.lj_model(3.0, 2.5), atoms)
+    assert np.abs(forces - cpu[0]).max() < 1e-4 and np.abs(energies - cpu[1]).max() < 1e-4 and np.abs(virials - cpu[2]).max() < 1e-4
+    # ... the API mirror of naively_compute_nonbonded! (evaluated on the GPU) agrees with the tile kernel ...
+    assert np.abs(forces - forces_ref).max() < 1e-4 and np.abs(energies - energies_ref).max() < 1e-4 and np.abs(virials - virials_ref).max() < 1e-4
     # ... and the FP64 bar against the oracle / golden vectors
     ref = (g["allpairs_forces"], g["allpairs_energies"], g["allpairs_virials"])
     check_efw((forces, energies, virials), ref, "allpairs vs golden")
-    check_efw((forces, energies, virials), oracle.naive_allpairs(pos, L, oracle.lj_model(3.0, 2.5), atoms), "allpairs vs oracle")
+    check_efw((forces, energies, virials), cpu, "allpairs vs oracle")
     # Fortran-ordered 3xN outputs, as a Julia caller would hold them
     fF = np.zeros((3, N), order="F")
     em.compute_nonbonded_(fF, energies, virials, np.asfortranarray(pos.T), L, tiles, model, atoms, em.FORCES)
@@ -410,8 +414,8 @@ def test_pair_list_molecular(em, oracle, dioxin_water):
     s.synchronize()
     ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
     assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
-    n = s.list_pair_count()
-    assert n == ref["npairs"] or n == -1        # -1: more LJ classes than the pair table holds, no list
+    assert s.step_config()["pair_list"]          # 5 LJ classes fit the pair table: the stepping path is the pair list
+    assert s.list_pair_count() == ref["npairs"]
     s.close()
 
 
@@ -575,6 +579,59 @@ def test_thermostat_and_checkpoint(em, oracle):
         b.restore(dict(ck, N=N + 1))
     a.close()
     b.close()
+
+
+def test_state_invalidation(em, oracle, dioxin_water):
+    """Inputs changed after a compute must not be served from stale state (advisor, round 1): a new cutoff invalidates the
+    cell grid and the pair list; new or cleared exclusions invalidate the pair list (they are applied when it is built);
+    a re-binning invalidates the per-atom results (they are in the old slot order); the pair-set audit and the pair
+    count of totals() leave the last compute's results bit for bit alone."""
+    pos, L = em.workloads.fcc_lattice(12)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.set_skin(0.4)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    f0 = s.forces()
+    # audit passes are side-effect free
+    s.pair_set_digest()
+    s.totals()
+    assert np.array_equal(s.forces(), f0)
+    with pytest.raises(em.EmDeeError):
+        s.energies()                                  # the last compute selected FORCES only
+    # larger cutoff: the old grid / list would miss pairs
+    s.set_model(em.LennardJonesModel(3.0, 2.5))
+    with pytest.raises(em.EmDeeError):
+        s.compute(em.CUTOFF, 7)                       # needs a new binning
+    s.bin(1)
+    with pytest.raises(em.EmDeeError):
+        s.forces()                                    # results of the previous binning are in the old slot order
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 3.0, 2.5, atoms, ndiv=1)
+    assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    E, W, npairs = s.totals()
+    assert npairs == ref["npairs"] and abs(E - ref["E"]) <= E_TOL * abs(ref["E"])
+    s.close()
+    # exclusions set / cleared after a list was built (molecular fixture x 3^3, the pair-list kernels at molecular density)
+    w = em.workloads.molecular_system(dioxin_water, reps=3)
+    pos, L, atoms, (base, mask) = w["positions"], w["L"], w["atoms"], w["excl"]
+    s = make_system(em, pos, L, 10.0, 9.0, atoms)
+    s.set_skin(0.5)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref0 = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1)
+    assert s.totals()[2] == ref0["npairs"]
+    s.set_exclusions(base, mask)
+    s.compute(em.CUTOFF, 7)
+    ref1 = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
+    E, W, npairs = s.totals()
+    assert npairs == ref1["npairs"] < ref0["npairs"] and abs(E - ref1["E"]) <= E_TOL * abs(ref1["E"])
+    assert np.abs(s.forces() - ref1["forces"]).max() <= F_TOL * frms(ref1["forces"])
+    s.set_exclusions(None, None)
+    s.compute(em.CUTOFF, 7)
+    assert abs(s.totals()[0] - ref0["E"]) <= E_TOL * abs(ref0["E"])
+    s.close()
 
 
 def test_skin_violation_is_reported(em):
