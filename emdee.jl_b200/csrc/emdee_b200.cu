@@ -453,7 +453,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->src_of_new, s->cap));
     A(dev_alloc(&s->maxd2, 2));
     A(dev_alloc(&s->brick_counter, 2));
-    A(dev_alloc(&s->digest, 4));
+    A(dev_alloc(&s->digest, 16));        // [0..3] audit digest + pair counter, [8..15] role timers of FLP_TIMING builds
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
     A(dev_alloc(&s->brick_max, 1));
@@ -473,6 +473,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     CUDA_TRY(cudaMemsetAsync(s->A[0].xbase, 0, sizeof(int32_t) * N, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->A[0].xmask, 0, sizeof(uint64_t) * N, c->stream));
     CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->digest, 0, 16 * sizeof(unsigned long long), c->stream));
     EMDEE_TRY(check_launch("system init"));
     *out = s;
     return EMDEE_OK;
@@ -1264,6 +1265,7 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     CUDA_TRY(cudaMemsetAsync(s->brick_counter, 0, sizeof(int), s->ctx->stream));
     CellArgs ac = a;
     ac.brick_counter = s->brick_counter;
+    ac.timing = s->digest + 8;
     ac.vv_mode = 0;
     if (!COUNT && !EW && s->vv_mode != 0) {
         AtomArrays &A = s->A[s->cur];
@@ -1982,6 +1984,17 @@ extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
         for (cudaEvent_t e : s->prof_mid) cudaEventDestroy(e);
         s->prof_mid.clear(); s->prof_mid_of.clear();
     }
+#if FLP_TIMING
+    {
+        unsigned long long t[8];
+        CUDA_TRY(cudaMemcpy(t, s->digest + 8, sizeof(t), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(s->digest + 8, 0, sizeof(t)));
+        const double P = (double)t[3], Cn = (double)t[5];
+        fprintf(stderr, "[emdee] role timers: producers: wait-empty %.1f%% stage %.1f%% integrate %.1f%% other %.1f%% of their time (%.0f cycles per brick); "
+                        "consumers: wait-full %.1f%% of their time; %llu brick periods\n", 100 * t[0] / P, 100 * t[1] / P, 100 * t[2] / P,
+                100 * (P - t[0] - t[1] - t[2]) / P, P / std::max(1.0, (double)t[6]), 100 * t[4] / Cn, t[6]);
+    }
+#endif
     if (getenv("EMDEE_DEBUG"))
         for (int m = 0; m < 4; m++)
             if (n_mode[m]) fprintf(stderr, "[emdee] force kernel mode %d: %d launches, %.4f ms each\n", m, n_mode[m], per_mode[m] / n_mode[m]);

@@ -91,6 +91,7 @@ struct CellArgs {
     unsigned *vv_maxd2;               // adaptive re-binning (may be null)
     int vv_check_skin;
     int *brick_counter;               // persistent kernel: bricks beyond the first of each block are claimed here (zeroed per launch)
+    unsigned long long *timing;       // -DFLP_TIMING=1 builds: cycle counters of the persistent kernel's roles (else unused)
 };
 
 // Brick handled by launch index i (a launch covers one or two contiguous ranges of bricks).

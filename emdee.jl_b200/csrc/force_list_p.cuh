@@ -53,6 +53,18 @@ __host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntype
            (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t);
 }
 
+// -DFLP_TIMING=1: per-role cycle counters (clock64) accumulated into a.timing[8]: producers' wait for an empty buffer,
+// staging, integrator, rest; consumers' wait for a full buffer and total time (summed over consumer warps), bricks
+#ifndef FLP_TIMING
+#define FLP_TIMING 0
+#endif
+#if FLP_TIMING
+#define FLP_T(var) const long long var = clock64()
+#define FLP_TACC(slot, expr) do { if (lane == 0) tacc[slot] += (expr); } while (0)
+#else
+#define FLP_T(var)
+#define FLP_TACC(slot, expr)
+#endif
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
@@ -108,6 +120,10 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     for (int t = tid; t < a.ntypes * a.ntypes; t += FLP_THREADS) ljt[t] = a.ljtab[t];
     if (tid < FLP_QS) qguard[tid] = 0;
     __syncthreads();
+#if FLP_TIMING
+    long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long t_begin = clock64();
+#endif
 
     if (warp < FLP_NPROD) {
         // ================================ producers ================================
@@ -179,22 +195,37 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
             if (brick >= nbricks) {
+                FLP_T(tw0);
                 if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);
+                FLP_TACC(0, clock64() - tw0);
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
                 bar_arrive(1 + b, FLP_THREADS);
                 if (VV) {
                     // the atoms of the brick just released, then (after its release) those of the brick in the other buffer
+                    FLP_T(ta0);
                     if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);
+                    FLP_TACC(2, clock64() - ta0);
 #pragma unroll
                     for (int q = 1; q < NBUF; q++) {
                         const int ob = (k + q) % NBUF;
                         if (held_bid[ob] >= 0) {
+                            FLP_T(tw1);
                             bar_sync(1 + NBUF + ob, FLP_THREADS);
+                            FLP_T(ta1);
                             advance_atoms(held_bid[ob], held_nh[ob]);
+                            FLP_TACC(0, ta1 - tw1);
+                            FLP_TACC(2, clock64() - ta1);
                         }
                     }
                 }
+#if FLP_TIMING
+                if (warp == 0 && lane == 0) {
+                    tacc[3] = clock64() - t_begin;         // producers' total
+                    for (int q = 0; q < 4; q++) atomicAdd(a.timing + q, (unsigned long long)tacc[q]);
+                    atomicAdd(a.timing + 6, (unsigned long long)k);
+                }
+#endif
                 break;
             }
             const int bid = FC_BRICK_OF(a, brick);
@@ -271,7 +302,10 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     prefetch_l2(reinterpret_cast<const unsigned char *>(a.list8 + gs * a.lcap8 * 32) + part * 128);
                 }
             }
+            FLP_T(tw2);
             if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);       // empty[b]: the consumers are done with this buffer
+            FLP_T(ts0);
+            FLP_TACC(0, ts0 - tw2);
             if (tid == 0) {
                 B.pxy[0] = make_double2(1e30, 1e30);
                 B.pz[0] = 1e30;
@@ -301,10 +335,13 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             }
             __threadfence_block();
             bar_arrive(1 + b, FLP_THREADS);                           // full[b]
+            FLP_T(ta2);
+            FLP_TACC(1, ta2 - ts0);
             if (VV) {
                 if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);     // released before this staging started
                 held_bid[b] = bid; held_nh[b] = nh;
             }
+            FLP_TACC(2, clock64() - ta2);
             brick = nb;
         }
         return;
@@ -332,7 +369,9 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     for (int k = 0;; k++) {
         const int b = k % NBUF;
         const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
+        FLP_T(tc0);
         bar_sync(1 + b, FLP_THREADS);                                 // full[b]
+        FLP_TACC(4, clock64() - tc0);
         const int brick = B.scal[4];
         if (brick < 0) break;
         const int bid = FC_BRICK_OF(a, brick);
@@ -474,4 +513,10 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         for (int o = 16; o > 0; o >>= 1) npair += __shfl_xor_sync(0xffffffffu, npair, o);
         if (lane == 0 && npair) atomicAdd(a.digest, npair);
     }
+#if FLP_TIMING
+    if (lane == 0) {
+        atomicAdd(a.timing + 4, (unsigned long long)tacc[4]);
+        atomicAdd(a.timing + 5, (unsigned long long)(clock64() - t_begin));      // consumers' total, summed over warps
+    }
+#endif
 }

@@ -414,8 +414,11 @@ def test_pair_list_molecular(em, oracle, dioxin_water):
     s.synchronize()
     ref = oracle.cutoff_cells(s.positions(), L, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask))
     assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
-    assert s.step_config()["pair_list"]          # 5 LJ classes fit the pair table: the stepping path is the pair list
-    assert s.list_pair_count() == ref["npairs"]
+    # the single fixture box (L = 24.56 A, rc + skin = 11 A) holds only M = 2 cells per dimension: no cell grid, so this
+    # system steps on the culled tile kernel and has no pair list to audit (the pair list at molecular density is audited
+    # in test_config4_replicated_cell_grid); stated explicitly instead of accepting either outcome
+    assert not s.step_config()["pair_list"] and s.list_pair_count() == -1
+    assert s.pair_set_digest()[0] == ref["npairs"]
     s.close()
 
 
