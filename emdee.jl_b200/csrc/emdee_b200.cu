@@ -135,6 +135,19 @@ struct emdee_system {
     double vv_dt = 0;
     unsigned *maxd2 = nullptr;                // device: max |r - r_bin|^2 since the last binning (float bits), adaptive re-binning
     // slab decomposition (nranks > 1)
+    // Scaled positions of a slab system live in ONE allocation (nine arrays: A[0].s, A[1].s, s_alt, behind 64 flag words), mapped
+    // into both neighbours with one CUDA IPC handle: the fused integrator writes my boundary atoms' new positions straight into
+    // the neighbours' ghost slots over NVLink and raises a flag there (force_list_p.cuh), so a step needs no NCCL call.
+    double *spool = nullptr;
+    size_t spool_stride = 0;                          // doubles per array
+    void *peer_pool[2] = {nullptr, nullptr};          // lower / upper neighbour's pool (the same mapping when both are one peer)
+    bool peer_tried = false, peer_ok = false;
+    long long *peerinfo = nullptr;                    // device: [0..3] mine, [4..7] from the lower neighbour, [8..11] from the upper one
+    unsigned long long epoch = 0;                     // id of the last fused slab launch (flags carry it)
+    int ghost_state = 0;                              // ghost positions: 0 complete, 1 stale (exchange them), 2 being written by the neighbours' launch `epoch`
+    bool p2p_launch = false;                          // the launch being issued uses peer-mapped halos
+    unsigned long long p2p_wait = 0, p2p_publish = 0;
+    int hi_layer0 = 0;                                // first brick z-layer whose halo reaches the upper ghost planes (unclamped)
     bool decomposed = false;
     int z0 = 0, nz = 0;                               // my global planes [z0, z0+nz)
     int64_t lo_send_a = 0, lo_send_n = 0, hi_send_a = 0, hi_send_n = 0;   // slot ranges my neighbours need as ghosts
@@ -452,11 +465,26 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->order, s->cap));
     A(dev_alloc(&s->src_of_new, s->cap));
     A(dev_alloc(&s->maxd2, 2));
-    A(dev_alloc(&s->brick_counter, 2));
+    A(dev_alloc(&s->brick_counter, 4));      // [0] brick cursor of the persistent kernel, [1], [2] boundary bricks advanced (peer halos)
     A(dev_alloc(&s->digest, 16));        // [0..3] audit digest + pair counter, [8..15] role timers of FLP_TIMING builds
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
     A(dev_alloc(&s->brick_max, 1));
+    if (c->nranks > 1 && st == EMDEE_OK) {
+        for (int b = 0; b < 2; b++)
+            for (int k = 0; k < 3; k++) dev_free(s->A[b].s[k]);
+        s->spool_stride = ((size_t)s->cap + 2 + 31) & ~(size_t)31;
+        A(dev_alloc(&s->spool, 64 + 9 * s->spool_stride));
+        if (st == EMDEE_OK) {
+            for (int k = 0; k < 3; k++) {
+                s->A[0].s[k] = s->spool + 64 + (size_t)k * s->spool_stride;
+                s->A[1].s[k] = s->spool + 64 + (size_t)(3 + k) * s->spool_stride;
+                s->s_alt[k] = s->spool + 64 + (size_t)(6 + k) * s->spool_stride;
+            }
+            if (cudaMemsetAsync(s->spool, 0, 64 * sizeof(double), c->stream) != cudaSuccess) st = EMDEE_ERR_CUDA;
+        }
+        A(dev_alloc(&s->peerinfo, 12));
+    }
     if (c->nranks > 1) {
         A(dev_alloc(&s->sendcount, 2));
         A(dev_alloc(&s->recvcount, 2));
@@ -484,6 +512,13 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     if (!s) return EMDEE_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->spool) {        // the scaled positions are slices of the pool
+        for (int k = 0; k < 3; k++) { s->A[0].s[k] = nullptr; s->A[1].s[k] = nullptr; s->s_alt[k] = nullptr; }
+        if (s->peer_pool[0]) cudaIpcCloseMemHandle(s->peer_pool[0]);
+        if (s->peer_pool[1] && s->peer_pool[1] != s->peer_pool[0]) cudaIpcCloseMemHandle(s->peer_pool[1]);
+        dev_free(s->spool);
+        dev_free(s->peerinfo);
+    }
     free_atoms(s->A[0]);
     free_atoms(s->A[1]);
     for (int k = 0; k < 3; k++) dev_free(s->f[k]);
@@ -1031,10 +1066,51 @@ static int slab_halo_positions(emdee_system *s, cudaStream_t st)
     return EMDEE_OK;
 }
 
+// Collective over the slab ranks (first re-binning): every rank exports its position pool with one CUDA IPC handle, hands it to
+// both ring neighbours through NCCL, and maps theirs.  All ranks use the peer-mapped halo or none does (min over ranks).
+static int ensure_peer_mapping(emdee_system *s)
+{
+    emdee_ctx *c = s->ctx;
+    if (s->peer_tried) return EMDEE_OK;
+    s->peer_tried = true;
+    const char *e = getenv("EMDEE_P2P");
+    int ok = (e && atoi(e) == 0) ? 0 : 1;
+    cudaIpcMemHandle_t mine, from[2];
+    memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, s->spool) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    EMDEE_TRY(ensure_tmp(s, 512));
+    char *d = reinterpret_cast<char *>(s->tmp);
+    CUDA_TRY(cudaMemcpyAsync(d, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(ncclGroupStart());
+    EMDEE_TRY(slab_exchange(c, c->stream, d, 64, d, 64, d + 64, 64, d + 128, 64, 1));
+    NCCL_TRY(ncclGroupEnd());
+    CUDA_TRY(cudaMemcpyAsync(&from[0], d + 64, 64, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&from[1], d + 128, 64, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    const int lower = (c->rank + c->nranks - 1) % c->nranks, upper = (c->rank + 1) % c->nranks;
+    if (ok && cudaIpcOpenMemHandle(&s->peer_pool[0], from[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; s->peer_pool[0] = nullptr; cudaGetLastError(); }
+    if (ok) {
+        if (lower == upper) s->peer_pool[1] = s->peer_pool[0];
+        else if (cudaIpcOpenMemHandle(&s->peer_pool[1], from[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; s->peer_pool[1] = nullptr; cudaGetLastError(); }
+    }
+    int32_t *flag = reinterpret_cast<int32_t *>(d + 256);
+    int32_t h = ok;
+    CUDA_TRY(cudaMemcpyAsync(flag, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+    NCCL_TRY(g_nccl.AllReduce(flag, flag, 1, ncclInt32, ncclMin, c->comm, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(&h, flag, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    s->peer_ok = h != 0;
+    if (getenv("EMDEE_DEBUG"))
+        fprintf(stderr, "[emdee] rank %d: peer-mapped halos %s (mine %d, all ranks %d)\n", c->rank, s->peer_ok ? "on" : "off (ncclSend/ncclRecv halos)", ok, h);
+    return EMDEE_OK;
+}
+
 static int do_bin_slab(emdee_system *s, int ndiv)
 {
     emdee_ctx *c = s->ctx;
     const int G = c->nranks;
+    EMDEE_TRY(ensure_peer_mapping(s));
     const double Mf = std::floor((double)ndiv * s->L / (s->cutoff + s->skin));
     if (!(Mf >= 1) || Mf > 2000) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: M=%g cells per dimension out of range", Mf);
     const int M = (int)Mf, R = ndiv;
@@ -1134,7 +1210,14 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     GHOST_X(B.hs, double); GHOST_X(B.ts, double);
     GHOST_X(B.id, int32_t); GHOST_X(B.type, int32_t); GHOST_X(B.xbase, int32_t); GHOST_X(B.xmask, uint64_t);
 #undef GHOST_X
+    {   // what the neighbours need to address my ghost slots: [0] my first upper-ghost slot, [1] which pool array holds the current
+        // positions (the buffer rotation must be the same on every rank)
+        const long long info[4] = {(long long)own_end, (long long)((B.s[0] - (s->spool + 64)) / (ptrdiff_t)s->spool_stride), 0, 0};
+        CUDA_TRY(cudaMemcpyAsync(s->peerinfo, info, sizeof(info), cudaMemcpyHostToDevice, c->stream));
+        EMDEE_TRY(slab_exchange(c, c->stream, s->peerinfo, 4, s->peerinfo, 4, s->peerinfo + 4, 4, s->peerinfo + 8, 4, sizeof(long long)));
+    }
     NCCL_TRY(ncclGroupEnd());
+    s->ghost_state = 0;
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
@@ -1145,6 +1228,13 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     const int bz = s->g.bz, nbz = s->g.nbz;
     s->brick_lo_end = std::min(nbz, (R + bz - 1) / bz);
     s->brick_hi_begin = std::max(s->brick_lo_end, (nz - R) / bz);
+    s->hi_layer0 = std::max(0, (nz - R) / bz);
+    if (getenv("EMDEE_DEBUG")) {     // the buffer rotation is the same on every rank (the peers address my arrays by it)
+        long long h[12];
+        CUDA_TRY(cudaMemcpyAsync(h, s->peerinfo, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        if (h[5] != h[1] || h[9] != h[1]) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: position-buffer rotation differs between slab ranks (%lld, %lld, %lld)", h[5], h[1], h[9]);
+    }
     return EMDEE_OK;
 }
 
@@ -1262,7 +1352,7 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
     // registers of its SM, so NCCL could not start before the first block retires otherwise)
     const int sms = std::max(1, s->ctx->sm_count - s->reserve_sms);
-    CUDA_TRY(cudaMemsetAsync(s->brick_counter, 0, sizeof(int), s->ctx->stream));
+    CUDA_TRY(cudaMemsetAsync(s->brick_counter, 0, 4 * sizeof(int), s->ctx->stream));
     CellArgs ac = a;
     ac.brick_counter = s->brick_counter;
     ac.timing = s->digest + 8;
@@ -1274,6 +1364,27 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
         ac.vv_mass = A.mass;
         ac.vv_maxd2 = s->vv_track ? s->maxd2 : nullptr;
         ac.vv_check_skin = s->vv_check_skin;
+        if (s->p2p_launch) {
+            emdee_ctx *c = s->ctx;
+            const int layer = s->g.nbx * s->g.nby;
+            ac.p2p = 1;
+            ac.p2p_lo_layers = s->brick_lo_end; ac.p2p_hi_layer0 = s->hi_layer0;
+            ac.p2p_nlo = s->brick_lo_end * layer; ac.p2p_nhi = (s->g.nbz - s->hi_layer0) * layer;
+            ac.lo_send_a = (int)s->lo_send_a; ac.lo_send_n = (int)s->lo_send_n; ac.hi_send_a = (int)s->hi_send_a; ac.hi_send_n = (int)s->hi_send_n;
+            for (int k = 0; k < 3; k++) {      // the neighbours rotate their position buffers as I do: same offset inside the pool
+                const ptrdiff_t off = s->s_alt[k] - s->spool;
+                ac.peer_lo[k] = reinterpret_cast<double *>(s->peer_pool[0]) + off;
+                ac.peer_hi[k] = reinterpret_cast<double *>(s->peer_pool[1]) + off;
+            }
+            ac.peer_info = s->peerinfo + 4;
+            ac.flag_lo_peer = reinterpret_cast<unsigned long long *>(s->peer_pool[0]) + 1;   // the lower neighbour's "from above" word
+            ac.flag_hi_peer = reinterpret_cast<unsigned long long *>(s->peer_pool[1]) + 0;   // the upper neighbour's "from below" word
+            ac.flag_from_lo = reinterpret_cast<unsigned long long *>(s->spool) + 0;
+            ac.flag_from_hi = reinterpret_cast<unsigned long long *>(s->spool) + 1;
+            ac.wait_epoch = s->p2p_wait; ac.publish_epoch = s->p2p_publish;
+            ac.p2p_done = s->brick_counter + 1;
+            (void)c;
+        }
     }
     kern<<<std::min(nblocks, sms), FLP_THREADS, smem, s->ctx->stream>>>(ac, nblocks, store_f ? 1 : 0);
     s->ctx->launches++;
@@ -1348,7 +1459,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     emdee_ctx *c = s->ctx;
     if ((s->ntypes > 0) != s->fc_typed) EMDEE_TRY(choose_bricks(s));   // LJ classes changed since binning: re-size shared memory
     AtomArrays &A = s->A[s->cur];
-    CellArgs a;
+    CellArgs a = {};
     a.g = s->g;
     a.cell_start = s->cell_start;
     a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2];
@@ -1462,6 +1573,18 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         ranges[0][0] = s->brick_lo_end * layer; ranges[0][1] = (s->brick_hi_begin - s->brick_lo_end) * layer;
         ranges[1][0] = 0; ranges[1][1] = s->brick_lo_end * layer;
         second_first = s->brick_hi_begin * layer; ranges[1][2] = s->fc_nblocks - s->brick_hi_begin * layer;
+    }
+    a.block_split2 = 0x7fffffff;
+    a.block_first3 = 0;
+    if (s->p2p_launch) {
+        // ONE launch per step: the bricks whose halo reaches ghost planes come first (their atoms' new positions are what the
+        // neighbours wait for), then the interior; the kernel itself waits for the neighbours' flags where it has to
+        a.block_first = 0; a.block_split = s->brick_lo_end * layer;
+        a.block_first2 = s->brick_hi_begin * layer; a.block_split2 = s->fc_nblocks - s->brick_hi_begin * layer;
+        a.block_first3 = s->brick_lo_end * layer;
+        EMDEE_TRY(launch_cells(s, a, s->fc_nblocks, F, EW, s->has_excl, audit, mode));
+        if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
+        return EMDEE_OK;
     }
     for (int k = 0; k < 2; k++) {
         if (k == 1 && halo && c->nranks > 1) {
@@ -1795,7 +1918,10 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     if (!(dt > 0) || nsteps < 0) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_vv_step: dt=%g, nsteps=%lld", dt, (long long)nsteps);
     const bool adaptive = rebin_every < 0 && s->skin > 0;      // rebin_every < 0: re-bin when the skin is used up
     int64_t resume_at = -1;          // >= 0: the fused loop handed this step over after its kick, drift and re-binning
-    if (s->fuse_vv && c->nranks == 1 && list_capable(s) && s->fl_persistent && nsteps > 0) {
+    // slab decomposition: the fused loop needs the neighbours' position pools mapped (peer halos) and a re-binning decision
+    // every rank takes alike without a read-back (fixed cadence, or never)
+    const bool slab_fused = c->nranks > 1 && s->decomposed && s->peer_ok && !adaptive;
+    if (s->fuse_vv && (c->nranks == 1 || slab_fused) && list_capable(s) && s->fl_persistent && nsteps > 0) {
         // One kernel per step: the stepping kernel's epilogue finishes step n (second half-kick) and starts step n+1
         // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
         // k_vv only starts the first step of the call.
@@ -1806,7 +1932,10 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         const int64_t unfuse_at = ue ? atoll(ue) : -1;
         for (int64_t st = 0; st < nsteps; st++) {
             bool rebin = !s->list_valid || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
-            if (!drifted) EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1, adaptive && !rebin));
+            if (!drifted) {
+                EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1, adaptive && !rebin));
+                s->ghost_state = 1;        // slab: the neighbours' atoms moved too
+            }
             if (adaptive && !rebin) {
                 unsigned bits = 0;
                 CUDA_TRY(cudaMemcpyAsync(&bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
@@ -1817,7 +1946,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
             }
             s->kick_pending = false;
             s->steps_since_bin++;
-            if (rebin) EMDEE_TRY(do_bin(s, s->ndiv));
+            if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));      // (a slab re-binning also refreshes the ghosts)
             if (!(list_capable(s) && s->fl_persistent) || (rebin && st > 0 && st == unfuse_at)) {
                 // the re-binning chose bricks whose two staging buffers no longer fit (denser cells): this step's atoms are
                 // already kicked, drifted and re-binned, so evaluate its forces with the generic path and carry on there
@@ -1835,9 +1964,20 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
             s->vv_dt = dt;
             s->vv_check_skin = (!adaptive && !next_rebin) ? 1 : 0;
             s->vv_track = adaptive;
+            if (slab_fused) {
+                // ghost positions: exchanged by NCCL after k_vv started this call (state 1), complete after a re-binning (0), or
+                // being written by the neighbours' previous launch, whose id their flags will carry (2)
+                if (s->ghost_state == 1) { EMDEE_TRY(slab_halo_positions(s, c->stream)); s->ghost_state = 0; }
+                s->p2p_launch = true;
+                s->p2p_wait = s->ghost_state == 2 ? s->epoch : 0;
+                s->epoch++;
+                s->p2p_publish = (!last && !next_rebin) ? s->epoch : 0;     // a re-binning exchanges the ghosts itself
+            }
             const int rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 2);
             s->vv_mode = 0;
+            s->p2p_launch = false;
             EMDEE_TRY(rc_);
+            if (slab_fused) s->ghost_state = s->p2p_publish ? 2 : (last ? 0 : 1);
             if (!last) {
                 AtomArrays &Ac = s->A[s->cur];
                 for (int k = 0; k < 3; k++) std::swap(Ac.s[k], s->s_alt[k]);      // the drifted positions become current
@@ -1924,7 +2064,7 @@ extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
     out[3] = s->grid_ok ? s->fc_cap : 0;
     out[4] = listed ? 1 : 0;
     out[5] = listed && s->fl_persistent ? 1 : 0;
-    out[6] = listed && s->fl_persistent && s->fuse_vv && c->nranks == 1 ? 1 : 0;
+    out[6] = listed && s->fl_persistent && s->fuse_vv && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
     out[7] = s->lcap8;
     return EMDEE_OK;
 }

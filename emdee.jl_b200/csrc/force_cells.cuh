@@ -65,6 +65,7 @@ struct CellArgs {
     int *err;                         // device error flag (capacity overflow)
     int block_first;                  // first brick of this launch (launches may cover a z-layer range) ...
     int block_split, block_first2;    // ... or two ranges: launch index i >= block_split maps to block_first2 + (i - block_split)
+    int block_split2, block_first3;   // ... or three: i >= block_split + block_split2 maps to block_first3 + (i - block_split - block_split2)
     // pair list: home atom h of a brick (flattened over its home rows) belongs to group h/32, lane h%32;
     // chunk c of that atom is the uint4 list8[((brick*gmax + h/32)*lcap8 + c)*32 + h%32] = 8 x (staged index + 1)
     uint4 *list8;
@@ -92,10 +93,27 @@ struct CellArgs {
     int vv_check_skin;
     int *brick_counter;               // persistent kernel: bricks beyond the first of each block are claimed here (zeroed per launch)
     unsigned long long *timing;       // -DFLP_TIMING=1 builds: cycle counters of the persistent kernel's roles (else unused)
+    // Slab decomposition with peer-mapped halos (k_force_list_p, VV variant): the integrator writes the new scaled position of
+    // every atom of my boundary planes straight into the neighbour's ghost slots over NVLink (peer memory), then raises a flag
+    // there once all bricks of that side are done; bricks whose halo reaches ghost planes wait for the neighbour's flag.
+    int p2p;                          // 0: off (single GPU, or halo by ncclSend/ncclRecv)
+    int p2p_lo_layers, p2p_hi_layer0; // brick z-layers [0, lo_layers) read lower ghosts; layers >= hi_layer0 read upper ghosts
+    int p2p_nlo, p2p_nhi;             // bricks holding atoms the lower / upper neighbour needs (they publish when all are advanced)
+    int lo_send_a, lo_send_n, hi_send_a, hi_send_n;   // my slot ranges the neighbours hold as ghosts
+    double *peer_lo[3], *peer_hi[3];  // neighbours' NEXT-step scaled-position arrays (peer-mapped)
+    const long long *peer_info;       // [0] lower neighbour's first upper-ghost slot (my lower planes land there); upper ghosts start at 0
+    unsigned long long *flag_lo_peer, *flag_hi_peer;      // flags I raise: in the lower neighbour's "from upper" word, the upper neighbour's "from lower" word
+    const unsigned long long *flag_from_lo, *flag_from_hi; // flags I wait on (local memory, written by the neighbours)
+    unsigned long long wait_epoch;    // ghosts of this launch are complete when the flags reach this value (0: already complete)
+    unsigned long long publish_epoch; // value I raise after my boundary atoms are advanced (0: nothing is published)
+    int *p2p_done;                    // [0] lower-side bricks advanced, [1] upper-side (zeroed per launch)
 };
 
 // Brick handled by launch index i (a launch covers one or two contiguous ranges of bricks).
-#define FC_BRICK_OF(a, i) ((i) < (a).block_split ? (a).block_first + (i) : (a).block_first2 + ((i) - (a).block_split))
+#define FC_BRICK_OF(a, i)                                                                                      \
+    ((i) < (a).block_split ? (a).block_first + (i)                                                             \
+                           : ((i) - (a).block_split < (a).block_split2 ? (a).block_first2 + ((i) - (a).block_split) \
+                                                                       : (a).block_first3 + ((i) - (a).block_split - (a).block_split2)))
 
 // Brick geometry shared by the kernels that stage a brick.
 struct BrickGeom {
@@ -137,7 +155,9 @@ __device__ __noinline__ bool exact_in_range(const double *sx, const double *sy, 
                                             double L, const LJModel m, double *xval)
 {
     double vx, vy, vz;
-    const double r2 = min_image_r2(sx[slot_i], sy[slot_i], sz[slot_i], sx[slot_j], sy[slot_j], sz[slot_j], L, vx, vy, vz);
+    // L2-only loads: in a slab decomposition ghost positions are written by the neighbouring GPUs during the launch
+    const double r2 = min_image_r2(__ldcg(sx + slot_i), __ldcg(sy + slot_i), __ldcg(sz + slot_i), __ldcg(sx + slot_j), __ldcg(sy + slot_j),
+                                   __ldcg(sz + slot_j), L, vx, vy, vz);
     double x = __dmul_rn(__dsub_rn(r2, m.rs2), m.id2);
     x = (x < 0.0 || x > 1.0) ? 0.0 : (x == 1.0 ? 0.5 : x);
     *xval = x;

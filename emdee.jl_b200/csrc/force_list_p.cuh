@@ -26,9 +26,6 @@
 #ifndef FLP_STAGE_U
 #define FLP_STAGE_U 9        // atoms per producer thread in flight: ~2300 staged atoms / 128 threads = two batches
 #endif
-#ifndef FLP_PRELOAD2
-#define FLP_PRELOAD2 0       // 1: the recipes of the SECOND staging batch are also loaded before the buffer is handed over
-#endif                       // (opt-in experiment of DESIGN section 9 item 2; written after round 1's GPU budget was spent: unmeasured)
 #ifndef FLP_NPROD
 #define FLP_NPROD 4
 #endif
@@ -67,6 +64,17 @@ __host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntype
 #endif
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 struct BrickBuf {
     double2 *pxy;
@@ -144,6 +152,8 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         auto advance_atoms = [&](int vbid, int vnh) {
             const int2 *vrecipe = a.recipe + (size_t)vbid * a.rcap;
             unsigned dmax = 0;
+            const bool push = VV && a.p2p && a.publish_epoch != 0 && a.vv_mode == 2;
+            const long long peer_lo_first = push ? a.peer_info[0] : 0;       // the lower neighbour's first upper-ghost slot
             constexpr int W = 3;                 // atoms per thread in flight: the chain home index -> slot -> data is pure latency
             for (int h00 = 0; h00 < vnh; h00 += W * PN) {
                 int slot[W];
@@ -176,7 +186,13 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                             v = __fma_rn(hk, f3[u][c3], v);                           // first half-kick of the next step
                             const double r = __fma_rn(a.vv_dt, v, r3[u][c3]);         // drift
                             a.vv_r[c3][slot[u]] = r;
-                            a.vv_snew[c3][slot[u]] = __ddiv_rn(r, a.L);
+                            const double sn = __ddiv_rn(r, a.L);
+                            a.vv_snew[c3][slot[u]] = sn;
+                            if (push) {      // my boundary planes are the neighbours' ghosts: same order, one contiguous range per side
+                                const unsigned ol = (unsigned)(slot[u] - a.lo_send_a), oh = (unsigned)(slot[u] - a.hi_send_a);
+                                if (ol < (unsigned)a.lo_send_n) a.peer_lo[c3][peer_lo_first + ol] = sn;
+                                if (oh < (unsigned)a.hi_send_n) a.peer_hi[c3][oh] = sn;
+                            }
                             const double d = r - rb3[u][c3];
                             d2 = fma(d, d, d2);
                         }
@@ -190,6 +206,33 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 dmax = __reduce_max_sync(0xffffffffu, dmax);
                 if (lane == 0 && dmax > *a.vv_maxd2) atomicMax(a.vv_maxd2, dmax);
             }
+            if (push) {
+                // publish: when every brick holding atoms a neighbour needs has been advanced, raise that neighbour's flag
+                // (stores to peer memory -> system-scope fence by every writer -> producers' barrier -> counter -> flag)
+                const int bzi = vbid / (g.nbx * g.nby);
+                const bool in_lo = bzi < a.p2p_lo_layers, in_hi = bzi >= a.p2p_hi_layer0;
+                if (in_lo || in_hi) {
+                    __threadfence_system();
+                    bar_sync(1 + 2 * NBUF, PN);
+                    if (tid == 0) {
+                        if (in_lo && atomicAdd(&a.p2p_done[0], 1) + 1 == a.p2p_nlo) { __threadfence_system(); st_release_sys(a.flag_lo_peer, a.publish_epoch); }
+                        if (in_hi && atomicAdd(&a.p2p_done[1], 1) + 1 == a.p2p_nhi) { __threadfence_system(); st_release_sys(a.flag_hi_peer, a.publish_epoch); }
+                    }
+                }
+            }
+        };
+        // ghosts written by the neighbours (peer memory): a brick whose halo reaches ghost planes waits for the neighbour's flag
+        bool seen_lo = !(VV && a.p2p && a.wait_epoch != 0), seen_hi = seen_lo;
+        auto wait_flag = [&](const unsigned long long *f) {
+            if (tid == 0) {
+                const long long t0 = clock64();
+                while (ld_acquire_sys(f) < a.wait_epoch) {
+                    __nanosleep(64);
+                    if (clock64() - t0 > (1ll << 32)) { atomicCAS(a.err, 0, 6); break; }      // ~2 s: the neighbour never published
+                }
+                __threadfence_system();
+            }
+            bar_sync(1 + 2 * NBUF, PN);
         };
         for (int k = 0;; k++) {
             const int b = k % NBUF;
@@ -249,7 +292,8 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     rc[u] = i < n1 ? recipe[i] : make_int2(0, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < U; u++) { sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x]; }
+                // L2-only loads: ghost slots are written by the neighbouring GPUs (peer memory), L1 may hold a stale line
+                for (int u = 0; u < U; u++) { sx[u] = __ldcg(a.sx + rc[u].x); sy[u] = __ldcg(a.sy + rc[u].x); sz[u] = __ldcg(a.sz + rc[u].x); }
             };
             auto store_batch = [&](int i0) {
 #pragma unroll
@@ -269,17 +313,14 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     if (MULTI) B.ptyp[i] = (uint8_t)a.type[rc[u].x];
                 }
             };
+            if (VV && a.p2p) {
+                const int bzi = bid / (g.nbx * g.nby);
+                if (!seen_lo && bzi < a.p2p_lo_layers) { wait_flag(a.flag_from_lo); seen_lo = true; }
+                if (!seen_hi && bzi >= a.p2p_hi_layer0) { wait_flag(a.flag_from_hi); seen_hi = true; }
+            }
             // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
             // time, and the staging latency that follows the hand-over is what the consumers then wait for
             load_batch(1 + tid);
-#if FLP_PRELOAD2
-            int2 rc2[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = 1 + tid + (U + u) * PN;
-                rc2[u] = i < n1 ? recipe[i] : make_int2(0, 0);
-            }
-#endif
             if (tid == 0) claimed[k & 1] = gridDim.x + atomicAdd(a.brick_counter, 1);
             bar_sync(1 + 2 * NBUF, PN);        // producers only; ids 1..NBUF are full[], NBUF+1..2*NBUF empty[]
             const int nb = claimed[k & 1];
@@ -318,18 +359,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 B.scal[4] = brick;
             }
             store_batch(1 + tid);
-#if FLP_PRELOAD2
-            {                                       // second batch: its recipes are already in registers, one round trip less
-#pragma unroll
-                for (int u = 0; u < U; u++) rc[u] = rc2[u];
-#pragma unroll
-                for (int u = 0; u < U; u++) { sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x]; }
-                store_batch(1 + tid + U * PN);
-            }
-            for (int i0 = 1 + tid + 2 * U * PN; i0 < n1; i0 += U * PN) {
-#else
             for (int i0 = 1 + tid + U * PN; i0 < n1; i0 += U * PN) {
-#endif
                 load_batch(i0);
                 store_batch(i0);
             }

@@ -702,8 +702,13 @@ def test_slab_decomposition_multi_gpu():
     if ngpu < 2:
         pytest.skip("needs at least 2 GPUs")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    for world, ndiv in ((2, 1), (min(ngpu, 4), 2)):
-        env = dict(os.environ, SLAB_N="16", SLAB_NDIV=str(ndiv))
+    cases = [(2, 1, 16)]                      # (ranks, ndiv, fcc cells per dimension)
+    if ngpu >= 4:
+        cases.append((4, 2, 16))
+    if ngpu >= 8:
+        cases.append((8, 1, 40))              # N = 256,000: M = 22 planes over 8 ranks
+    for world, ndiv, n in cases:
+        env = dict(os.environ, SLAB_N=str(n), SLAB_NDIV=str(ndiv))
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                               "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "slab_worker.py")],
                              env=env, capture_output=True, text=True, timeout=900)
