@@ -419,10 +419,9 @@ def run_b200(args):
         dist.broadcast_object_list(ids, src=0)
         ctx.comm_init(rank, world, ids[0])
 
-    if world > 1 and args.rebin_every < 0:
-        # the adaptive criterion costs an all-reduce and a host read-back per step: at 8 GPUs (0.5 ms steps) that is more
-        # than the re-binnings it saves (measured: 0.65 vs 0.49 ms/step), so slab runs re-bin at a fixed, safe cadence
-        args.rebin_every = 5
+    # rebin_every = -1 (default): one GPU re-bins on the step on which an atom has moved more than skin/2 (a 4-byte read-back per
+    # step); slab runs choose the interval at every re-binning from the largest displacement of the interval that ended there
+    # (max over ranks, read back with the re-binning's own synchronisation), so their steps need no read-back at all
     w = workload(args)
     N, L = w["N"], w["L"]
     s = em.NonbondedSystem(N, L, ctx)
@@ -594,7 +593,8 @@ def run_b200(args):
             "dtype": "f64", "data": "synthetic",
             "config": common_config(args, w, N, L),
             "run": {"skin": args.skin, "brick_cells": list(cfg["brick"]), "brick_capacity": cfg["brick_capacity"],
-                    "rebin_every": args.rebin_every if args.rebin_every >= 0 else "adaptive (skin/2 criterion)",
+                    "rebin_every": args.rebin_every if args.rebin_every >= 0 else ("adaptive (skin/2 criterion)" if world == 1 else
+                                   "adaptive (interval chosen at every re-binning from the last interval's largest displacement)"),
                     "rebins_in_timed_steps": int(rebins),
                     "decomposition": "z-slabs x%d" % world if world > 1 else "single GPU",
                     "pairs": pairs, "wall_ms_per_step": wall / args.steps * 1e3},

@@ -148,6 +148,13 @@ struct emdee_system {
     bool p2p_launch = false;                          // the launch being issued uses peer-mapped halos
     unsigned long long p2p_wait = 0, p2p_publish = 0;
     int hi_layer0 = 0;                                // first brick z-layer whose halo reaches the upper ghost planes (unclamped)
+    // values a slab re-binning reads back together with its slot marks (one host synchronisation instead of three)
+    bool pre_valid = false;
+    int pre_maxpop = 0, pre_cap = 0;
+    // re-binning cadence of a slab run with rebin_every < 0: chosen at every re-binning from the largest displacement of the
+    // interval that just ended (max over ranks, read back with the marks), so that no step needs a read-back
+    int slab_interval = 4;
+    double last_dmax_ratio = 0;                       // max displacement of the last interval / (skin/2)
     bool decomposed = false;
     int z0 = 0, nz = 0;                               // my global planes [z0, z0+nz)
     int64_t lo_send_a = 0, lo_send_n = 0, hi_send_a = 0, hi_send_n = 0;   // slot ranges my neighbours need as ghosts
@@ -155,6 +162,8 @@ struct emdee_system {
     int32_t *sendcount = nullptr, *recvcount = nullptr, *list_lo = nullptr, *list_hi = nullptr;
     double *migbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // send lo, send hi, recv lo, recv hi
     int64_t migcap = 0;
+    double *ghostbuf[4] = {nullptr, nullptr, nullptr, nullptr}; // packed ghost atoms: send lo, send hi, recv lo, recv hi
+    int64_t ghostcap = 0;
     // force kernel configuration
     int fc_cap = 0, fc_ncs = 0, fc_block = 256, fc_nblocks = 0;
     bool fc_typed = false;
@@ -535,6 +544,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->list8); dev_free(s->list_n); dev_free(s->recipe); dev_free(s->homeidx); dev_free(s->brickhdr);
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
+    for (int k = 0; k < 4; k++) dev_free(s->ghostbuf[k]);
     delete s;
     return EMDEE_OK;
 }
@@ -824,9 +834,11 @@ static int choose_bricks(emdee_system *s)
     const size_t per_sm = c->smem_optin + 1024;          // usable shared memory per SM (1 KB reserved per block)
     const int64_t ntot = s->nlo + s->nown + s->nhi;
     const double per_cell = (double)ntot / (double)std::max<int64_t>(1, (int64_t)g.M * g.M * g.nzt);
-    int maxpop = 0;
-    CUDA_TRY(cudaMemcpyAsync(&maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    int maxpop = s->pre_maxpop;
+    if (!s->pre_valid) {
+        CUDA_TRY(cudaMemcpyAsync(&maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+    }
     static const int blocks[] = {384, 256, 192, 128, 64};
     static const int lblocks[] = {256, 192, 128, 96, 64};
     // largest k_force_cells block that fits next to `cap` staged atoms (0: none)
@@ -858,8 +870,8 @@ static int choose_bricks(emdee_system *s)
     // (one tiny kernel + sync per re-binning)
     if (s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK") && std::fabs(per_cell - s->fc_per_cell) <= 0.08 * s->fc_per_cell && R == s->fc_R) {
         set_brick_shape(s, s->fc_shape);
-        int cap = 0;
-        EMDEE_TRY(brick_capacity(s, &cap));
+        int cap = s->pre_cap;              // (a slab re-binning measured it for this shape before its one synchronisation)
+        if (!s->pre_valid) EMDEE_TRY(brick_capacity(s, &cap));
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const size_t need = listed ? fl_smem_bytes(cap, ncs, s->fl_block, std::max(s->ntypes, 1)) : fc_smem_bytes(cap, ncs, s->fc_block, typed);
         if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin)
@@ -1106,11 +1118,33 @@ static int ensure_peer_mapping(emdee_system *s)
     return EMDEE_OK;
 }
 
+// EMDEE_DEBUG=2: wall-clock anatomy of the slab re-binnings (a stream synchronisation at every phase boundary: perturbs the run)
+static double g_rebin_phase[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+static int g_rebin_count = 0;
+static double wall_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+#define REBIN_PHASE(k)                                                   \
+    if (phase_dbg) {                                                     \
+        CUDA_TRY(cudaStreamSynchronize(c->stream));                      \
+        const double now_ = wall_ms();                                   \
+        g_rebin_phase[k] += now_ - phase_t0;                             \
+        phase_t0 = now_;                                                 \
+    }
+
 static int do_bin_slab(emdee_system *s, int ndiv)
 {
     emdee_ctx *c = s->ctx;
     const int G = c->nranks;
     EMDEE_TRY(ensure_peer_mapping(s));
+    const char *dbg_ = getenv("EMDEE_DEBUG");
+    const bool phase_dbg = dbg_ && atoi(dbg_) >= 2;
+    if (phase_dbg) CUDA_TRY(cudaStreamSynchronize(c->stream));
+    double phase_t0 = wall_ms();
+    g_rebin_count++;
     const double Mf = std::floor((double)ndiv * s->L / (s->cutoff + s->skin));
     if (!(Mf >= 1) || Mf > 2000) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: M=%g cells per dimension out of range", Mf);
     const int M = (int)Mf, R = ndiv;
@@ -1168,6 +1202,7 @@ static int do_bin_slab(emdee_system *s, int ndiv)
                   s->gcell[s->cur], s->lcell[s->cur], s->cell_start, s->err);
         n_in += nrecv[0] + nrecv[1];
     }
+    REBIN_PHASE(0)       // cell index, migration (counts, payload, unpack)
     // ---- populations of the ghost planes come from the neighbours' boundary planes ----------------
     int32_t *cnt = s->cell_start;
     NCCL_TRY(ncclGroupStart());
@@ -1181,7 +1216,42 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     const int64_t mark_idx[5] = {plane * R, plane * 2 * R, plane * nz, plane * (R + nz), s->ncell};
     for (int k = 0; k < 5; k++)
         CUDA_TRY(cudaMemcpyAsync(&marks[k], s->cell_start + mark_idx[k], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    // read back in the same synchronisation: the densest cell, the staged-atom capacity of the previous brick shape (what
+    // choose_bricks needs when it keeps that shape), and the largest displacement of the interval that ends here
+    int pre_maxpop = 0, pre_brickmax = 0;
+    unsigned dmax_bits = 0;
+    const bool pre = s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK");
+    if (pre) {
+        set_brick_shape(s, s->fc_shape);
+        CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
+        LAUNCH_1D(c, k_brick_max, (int64_t)(g.nbx * g.nby * g.nbz), g, s->cell_start, s->brick_max);
+        CUDA_TRY(cudaMemcpyAsync(&pre_brickmax, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CUDA_TRY(cudaMemcpyAsync(&pre_maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    if (!first_time) {
+        NCCL_TRY(g_nccl.AllReduce(s->maxd2, s->maxd2 + 1, 1, ncclUint32, ncclMax, c->comm, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(&dmax_bits, s->maxd2 + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    }
     CUDA_TRY(cudaStreamSynchronize(c->stream));
+    REBIN_PHASE(1)       // ghost-plane populations, scan, marks
+    s->pre_valid = pre;
+    s->pre_maxpop = pre_maxpop;
+    s->pre_cap = std::max(64, (pre_brickmax + 4) & ~3);
+    if (!first_time && s->skin > 0) {
+        float d2;
+        memcpy(&d2, &dmax_bits, 4);
+        s->last_dmax_ratio = std::sqrt((double)d2) / (0.5 * s->skin);
+        // next interval: one step longer while a linear (ballistic) extrapolation of this interval's largest displacement stays
+        // below 85 % of skin/2; shorter when this one came close.  The skin check in the integrator stays armed.
+        const int k = std::max<int64_t>(1, s->steps_since_bin);
+        if (s->last_dmax_ratio > 0 && k >= s->slab_interval) {
+            if (s->last_dmax_ratio * (k + 1) / k < 0.85) s->slab_interval = k + 1;
+            else if (s->last_dmax_ratio > 0.92) s->slab_interval = std::max(1, k - 1);
+            else s->slab_interval = k;
+        }
+        if (getenv("EMDEE_DEBUG") && c->rank == 0)
+            fprintf(stderr, "[emdee] slab re-binning after %d steps: max displacement %.3f of skin/2, next interval %d\n", k, s->last_dmax_ratio, s->slab_interval);
+    }
     const int64_t nlo = marks[0], own_end = marks[3], ntot = marks[4];
     if (ntot > s->cap) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: slab holds %lld atoms incl. ghosts, capacity %lld", (long long)ntot, (long long)s->cap);
     const int64_t nown = own_end - nlo;
@@ -1195,6 +1265,7 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     ga.slot_of_id = nullptr; ga.has_vel = 1; ga.has_excl = 1;
     LAUNCH_1D(c, k_gather, nown, ga);
     EMDEE_TRY(check_launch("slab binning"));
+    REBIN_PHASE(2)       // scatter, rank in cell, gather
     s->cur = 1 - s->cur;
     s->nlo = nlo; s->nown = nown; s->nhi = ntot - own_end;
     s->lo_send_a = marks[0]; s->lo_send_n = marks[1] - marks[0];
@@ -1202,28 +1273,42 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     s->decomposed = true;
     // ---- ghost atoms: static per-atom data and current scaled positions ----------------------------
     AtomArrays &B = s->A[s->cur];
-    NCCL_TRY(ncclGroupStart());
-#define GHOST_X(arr, T)                                                                                          \
-    EMDEE_TRY(slab_exchange(c, c->stream, (arr) + s->lo_send_a, s->lo_send_n, (arr) + s->hi_send_a, s->hi_send_n, \
-                            (arr), s->nlo, (arr) + own_end, s->nhi, sizeof(T)))
-    GHOST_X(B.s[0], double); GHOST_X(B.s[1], double); GHOST_X(B.s[2], double);
-    GHOST_X(B.hs, double); GHOST_X(B.ts, double);
-    GHOST_X(B.id, int32_t); GHOST_X(B.type, int32_t); GHOST_X(B.xbase, int32_t); GHOST_X(B.xmask, uint64_t);
-#undef GHOST_X
+    {   // one packed message per neighbour (pack -> ncclSend/ncclRecv -> unpack)
+        const int64_t need = std::max(std::max(s->lo_send_n, s->hi_send_n), std::max(s->nlo, s->nhi));
+        if (need > s->ghostcap) {
+            for (int k = 0; k < 4; k++) dev_free(s->ghostbuf[k]);
+            s->ghostcap = need + need / 4 + 1024;
+            for (int k = 0; k < 4; k++) EMDEE_TRY(dev_alloc(&s->ghostbuf[k], (size_t)GHOST_FIELDS * s->ghostcap));
+        }
+        LAUNCH_1D(c, k_pack_ghosts, s->lo_send_n, s->lo_send_a, (int)s->lo_send_n, B, s->ghostbuf[0]);
+        LAUNCH_1D(c, k_pack_ghosts, s->hi_send_n, s->hi_send_a, (int)s->hi_send_n, B, s->ghostbuf[1]);
+    }
     {   // what the neighbours need to address my ghost slots: [0] my first upper-ghost slot, [1] which pool array holds the current
         // positions (the buffer rotation must be the same on every rank)
         const long long info[4] = {(long long)own_end, (long long)((B.s[0] - (s->spool + 64)) / (ptrdiff_t)s->spool_stride), 0, 0};
         CUDA_TRY(cudaMemcpyAsync(s->peerinfo, info, sizeof(info), cudaMemcpyHostToDevice, c->stream));
-        EMDEE_TRY(slab_exchange(c, c->stream, s->peerinfo, 4, s->peerinfo, 4, s->peerinfo + 4, 4, s->peerinfo + 8, 4, sizeof(long long)));
     }
+    NCCL_TRY(ncclGroupStart());
+    EMDEE_TRY(slab_exchange(c, c->stream, s->ghostbuf[0], (size_t)GHOST_FIELDS * s->lo_send_n, s->ghostbuf[1], (size_t)GHOST_FIELDS * s->hi_send_n,
+                            s->ghostbuf[2], (size_t)GHOST_FIELDS * s->nlo, s->ghostbuf[3], (size_t)GHOST_FIELDS * s->nhi, sizeof(double)));
+    EMDEE_TRY(slab_exchange(c, c->stream, s->peerinfo, 4, s->peerinfo, 4, s->peerinfo + 4, 4, s->peerinfo + 8, 4, sizeof(long long)));
     NCCL_TRY(ncclGroupEnd());
+    LAUNCH_1D(c, k_unpack_ghosts, s->nlo, (int64_t)0, (int)s->nlo, s->ghostbuf[2], B);
+    LAUNCH_1D(c, k_unpack_ghosts, s->nhi, own_end, (int)s->nhi, s->ghostbuf[3], B);
+    EMDEE_TRY(check_launch("ghost atoms"));
+    REBIN_PHASE(3)       // ghost atoms
     s->ghost_state = 0;
     s->binned = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
     s->last_bitmask = 0;
     CUDA_TRY(cudaMemsetAsync(s->maxd2, 0, sizeof(unsigned), c->stream));
-    EMDEE_TRY(choose_bricks(s));
+    {
+        const int rc_ = choose_bricks(s);
+        s->pre_valid = false;
+        EMDEE_TRY(rc_);
+    }
+    REBIN_PHASE(4)       // brick configuration
     // brick layers whose halo reaches ghost planes (they must wait for the halo exchange)
     const int bz = s->g.bz, nbz = s->g.nbz;
     s->brick_lo_end = std::min(nbz, (R + bz - 1) / bz);
@@ -1346,7 +1431,8 @@ template <bool MULTI, bool COUNT, bool EW>
 static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
 {
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
-    if (!COUNT && !EW && s->vv_mode != 0) kern = k_force_list_p<MULTI, false, 2, false, true, true>;
+    if (!COUNT && !EW && s->vv_mode != 0)
+        kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
     const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
@@ -1920,7 +2006,11 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     int64_t resume_at = -1;          // >= 0: the fused loop handed this step over after its kick, drift and re-binning
     // slab decomposition: the fused loop needs the neighbours' position pools mapped (peer halos) and a re-binning decision
     // every rank takes alike without a read-back (fixed cadence, or never)
-    const bool slab_fused = c->nranks > 1 && s->decomposed && s->peer_ok && !adaptive;
+    const bool slab_fused = c->nranks > 1 && s->decomposed && s->peer_ok;
+    // slab runs with rebin_every < 0 re-bin at an interval chosen at the previous re-binning (do_bin_slab) instead of
+    // reading the displacement back on every step
+    const bool slab_adaptive = slab_fused && adaptive;
+    const bool adaptive1 = adaptive && !slab_adaptive;      // per-step read-back (single GPU)
     if (s->fuse_vv && (c->nranks == 1 || slab_fused) && list_capable(s) && s->fl_persistent && nsteps > 0) {
         // One kernel per step: the stepping kernel's epilogue finishes step n (second half-kick) and starts step n+1
         // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
@@ -1931,12 +2021,14 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         const char *ue = getenv("EMDEE_DEBUG_UNFUSE_AT");
         const int64_t unfuse_at = ue ? atoll(ue) : -1;
         for (int64_t st = 0; st < nsteps; st++) {
-            bool rebin = !s->list_valid || (rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every);
+            // steps between re-binnings: the caller's, or (slab runs with rebin_every < 0) the interval the last re-binning chose
+            auto every = [&]() { return rebin_every > 0 ? rebin_every : (slab_adaptive ? s->slab_interval : 0); };
+            bool rebin = !s->list_valid || (every() > 0 && s->steps_since_bin + 1 >= every());
             if (!drifted) {
-                EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive ? 0 : 1, adaptive && !rebin));
+                EMDEE_TRY(launch_vv(s, dt, 1, rebin || adaptive1 ? 0 : 1, (adaptive1 && !rebin) || slab_adaptive));
                 s->ghost_state = 1;        // slab: the neighbours' atoms moved too
             }
-            if (adaptive && !rebin) {
+            if (adaptive1 && !rebin) {
                 unsigned bits = 0;
                 CUDA_TRY(cudaMemcpyAsync(&bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
                 CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1959,11 +2051,11 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 s->list_valid = true;
             }
             const bool last = st == nsteps - 1;
-            const bool next_rebin = rebin_every > 0 && s->steps_since_bin + 1 >= rebin_every;
+            const bool next_rebin = every() > 0 && s->steps_since_bin + 1 >= every();
             s->vv_mode = last ? 1 : 2;
             s->vv_dt = dt;
-            s->vv_check_skin = (!adaptive && !next_rebin) ? 1 : 0;
-            s->vv_track = adaptive;
+            s->vv_check_skin = (!adaptive1 && !next_rebin) ? 1 : 0;
+            s->vv_track = adaptive1 || slab_adaptive;
             if (slab_fused) {
                 // ghost positions: exchanged by NCCL after k_vv started this call (state 1), complete after a re-binning (0), or
                 // being written by the neighbours' previous launch, whose id their flags will carry (2)
@@ -2123,6 +2215,13 @@ extern "C" int emdee_profile_end(emdee_system *s, double *ms, int64_t *launches)
                 ti / n, tw / n, tb / n, (int)n);
         for (cudaEvent_t e : s->prof_mid) cudaEventDestroy(e);
         s->prof_mid.clear(); s->prof_mid_of.clear();
+    }
+    if (g_rebin_count && getenv("EMDEE_DEBUG") && atoi(getenv("EMDEE_DEBUG")) >= 2) {
+        fprintf(stderr, "[emdee] rank %d: %d slab re-binnings, wall ms each: migration %.3f, populations+scan+marks %.3f, sort+gather %.3f, ghosts %.3f, bricks %.3f\n",
+                c->rank, g_rebin_count, g_rebin_phase[0] / g_rebin_count, g_rebin_phase[1] / g_rebin_count, g_rebin_phase[2] / g_rebin_count,
+                g_rebin_phase[3] / g_rebin_count, g_rebin_phase[4] / g_rebin_count);
+        for (int k = 0; k < 8; k++) g_rebin_phase[k] = 0;
+        g_rebin_count = 0;
     }
 #if FLP_TIMING
     {

@@ -151,13 +151,21 @@ __device__ __noinline__ int staged_slot(int j, const int *cs, const int *gbase, 
 // for pairs whose local-frame r2 is within 3*2^-20 of rc2.  Also returns the oracle's own clamped x
 // (src/lennard_jones.jl:36-37: x < 0 -> 0, x > 1 -> 0, x == 1 -> 0.5) so that the switching function is
 // evaluated on the same branch.
+// CG: L2-only loads.  In a slab decomposition with peer-mapped halos the ghost positions are written by the neighbouring
+// GPUs while the kernel runs, and L1 may hold a stale copy of a line that straddles owned and ghost slots.  (A separate
+// instantiation: the plain-load version must stay exactly as it is -- its loads are part of what the compiler schedules
+// around in the callers' hot loops.)
+template <bool CG = false>
 __device__ __noinline__ bool exact_in_range(const double *sx, const double *sy, const double *sz, int slot_i, int slot_j,
                                             double L, const LJModel m, double *xval)
 {
     double vx, vy, vz;
-    // L2-only loads: in a slab decomposition ghost positions are written by the neighbouring GPUs during the launch
-    const double r2 = min_image_r2(__ldcg(sx + slot_i), __ldcg(sy + slot_i), __ldcg(sz + slot_i), __ldcg(sx + slot_j), __ldcg(sy + slot_j),
-                                   __ldcg(sz + slot_j), L, vx, vy, vz);
+    double r2;
+    if (CG)
+        r2 = min_image_r2(__ldcg(sx + slot_i), __ldcg(sy + slot_i), __ldcg(sz + slot_i), __ldcg(sx + slot_j), __ldcg(sy + slot_j),
+                          __ldcg(sz + slot_j), L, vx, vy, vz);
+    else
+        r2 = min_image_r2(sx[slot_i], sy[slot_i], sz[slot_i], sx[slot_j], sy[slot_j], sz[slot_j], L, vx, vy, vz);
     double x = __dmul_rn(__dsub_rn(r2, m.rs2), m.id2);
     x = (x < 0.0 || x > 1.0) ? 0.0 : (x == 1.0 ? 0.5 : x);
     *xval = x;

@@ -74,7 +74,7 @@ struct LaneRedo {
 // is within 3*2^-20 of rc2 as outside, only remembering that it met one.  A lane that met one (about one lane
 // in a hundred warp tasks for a fluid; every lane for a lattice with a shell exactly at rc) discards its result
 // and re-evaluates its list here, taking the oracle's exact decision (and the oracle's clamped x) for those pairs.
-template <bool MULTI, bool EW = false>
+template <bool MULTI, bool EW = false, bool CG = false>
 __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned long long *npair)
 {
     const double2 q0 = w.pxy[w.me];
@@ -96,7 +96,7 @@ __device__ __noinline__ void careful_lane(const LaneRedo &w, double *f, unsigned
         double xval = 0.0;
         if (where == 0) {
             const int slot_j = w.recipe ? w.recipe[j].x : staged_slot(j, w.cs, w.gbase, w.ncs);
-            if (!exact_in_range(w.sx, w.sy, w.sz, w.slot_i, slot_j, w.L, w.model, &xval)) continue;
+            if (!exact_in_range<CG>(w.sx, w.sy, w.sz, w.slot_i, slot_j, w.L, w.model, &xval)) continue;
             xover = true;
         }
         double2 pr = ljrow[0];

@@ -110,7 +110,10 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 #else
 #define FLP_BOUNDS __launch_bounds__(FLP_THREADS, 1)
 #endif
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false>
+// P2P: slab decomposition with peer-mapped halos (see CellArgs): ghost positions are written by the neighbouring GPUs during
+// the launch, so staged coordinates are read with L2-only loads, boundary bricks wait for the neighbours' flags, and the
+// integrator pushes my boundary atoms to the neighbours.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false>
 __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
@@ -152,7 +155,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         auto advance_atoms = [&](int vbid, int vnh) {
             const int2 *vrecipe = a.recipe + (size_t)vbid * a.rcap;
             unsigned dmax = 0;
-            const bool push = VV && a.p2p && a.publish_epoch != 0 && a.vv_mode == 2;
+            const bool push = VV && P2P && a.publish_epoch != 0 && a.vv_mode == 2;
             const long long peer_lo_first = push ? a.peer_info[0] : 0;       // the lower neighbour's first upper-ghost slot
             constexpr int W = 3;                 // atoms per thread in flight: the chain home index -> slot -> data is pure latency
             for (int h00 = 0; h00 < vnh; h00 += W * PN) {
@@ -222,7 +225,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             }
         };
         // ghosts written by the neighbours (peer memory): a brick whose halo reaches ghost planes waits for the neighbour's flag
-        bool seen_lo = !(VV && a.p2p && a.wait_epoch != 0), seen_hi = seen_lo;
+        bool seen_lo = !(VV && P2P && a.wait_epoch != 0), seen_hi = seen_lo;
         auto wait_flag = [&](const unsigned long long *f) {
             if (tid == 0) {
                 const long long t0 = clock64();
@@ -293,7 +296,10 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
 #pragma unroll
                 // L2-only loads: ghost slots are written by the neighbouring GPUs (peer memory), L1 may hold a stale line
-                for (int u = 0; u < U; u++) { sx[u] = __ldcg(a.sx + rc[u].x); sy[u] = __ldcg(a.sy + rc[u].x); sz[u] = __ldcg(a.sz + rc[u].x); }
+                for (int u = 0; u < U; u++) {
+                    if (P2P) { sx[u] = __ldcg(a.sx + rc[u].x); sy[u] = __ldcg(a.sy + rc[u].x); sz[u] = __ldcg(a.sz + rc[u].x); }
+                    else { sx[u] = a.sx[rc[u].x]; sy[u] = a.sy[rc[u].x]; sz[u] = a.sz[rc[u].x]; }
+                }
             };
             auto store_batch = [&](int i0) {
 #pragma unroll
@@ -313,7 +319,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     if (MULTI) B.ptyp[i] = (uint8_t)a.type[rc[u].x];
                 }
             };
-            if (VV && a.p2p) {
+            if (VV && P2P) {
                 const int bzi = bid / (g.nbx * g.nby);
                 if (!seen_lo && bzi < a.p2p_lo_layers) { wait_flag(a.flag_from_lo); seen_lo = true; }
                 if (!seen_hi && bzi >= a.p2p_hi_layer0) { wait_flag(a.flag_from_hi); seen_hi = true; }
@@ -525,7 +531,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 rd.entries = reinterpret_cast<const uint16_t *>(lp);
                 rd.sx = a.sx; rd.sy = a.sy; rd.sz = a.sz; rd.L = a.L; rd.model = a.model; rd.fast = a.fast; rd.rc2hi = a.rc2hi;
                 double f3[5];
-                careful_lane<MULTI, EW>(rd, f3, &np);
+                careful_lane<MULTI, EW, P2P>(rd, f3, &np);
                 fx = f3[0]; fy = f3[1]; fz = f3[2];
                 if (EW) { e = f3[3]; w = f3[4]; }
             }

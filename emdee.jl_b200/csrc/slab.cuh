@@ -97,6 +97,37 @@ __global__ void k_unpack_migrants(int n, const double *__restrict__ buf, int64_t
     atomicAdd(count + lc, 1);
 }
 
+// Ghost atoms at a re-binning: everything the force kernels need of a boundary atom, packed field-major into ONE message per
+// neighbour (field f of atom a at buf[f*n + a]) -- nine separate array slices per side cost 36 NCCL operations per re-binning.
+#define GHOST_FIELDS 8   // doubles per ghost atom: s(3) hs ts | (id,type) | xbase | xmask
+__global__ void k_pack_ghosts(int64_t first, int n, AtomArrays A, double *__restrict__ buf)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int64_t i = first + a;
+#pragma unroll
+    for (int c = 0; c < 3; c++) buf[(size_t)c * n + a] = A.s[c][i];
+    buf[(size_t)3 * n + a] = A.hs[i];
+    buf[(size_t)4 * n + a] = A.ts[i];
+    buf[(size_t)5 * n + a] = __hiloint2double(A.type[i], A.id[i]);
+    buf[(size_t)6 * n + a] = __longlong_as_double((long long)A.xbase[i]);
+    buf[(size_t)7 * n + a] = __longlong_as_double((long long)A.xmask[i]);
+}
+__global__ void k_unpack_ghosts(int64_t first, int n, const double *__restrict__ buf, AtomArrays A)
+{
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= n) return;
+    const int64_t i = first + a;
+#pragma unroll
+    for (int c = 0; c < 3; c++) A.s[c][i] = buf[(size_t)c * n + a];
+    A.hs[i] = buf[(size_t)3 * n + a];
+    A.ts[i] = buf[(size_t)4 * n + a];
+    A.id[i] = __double2loint(buf[(size_t)5 * n + a]);
+    A.type[i] = __double2hiint(buf[(size_t)5 * n + a]);
+    A.xbase[i] = (int32_t)__double_as_longlong(buf[(size_t)6 * n + a]);
+    A.xmask[i] = (uint64_t)__double_as_longlong(buf[(size_t)7 * n + a]);
+}
+
 // Scatter that skips the trash cell (leavers / foreign atoms).
 __global__ void k_scatter_slab(int64_t first, int64_t n, const int32_t *__restrict__ lcell, int ncell,
                                const int32_t *__restrict__ cell_start, int32_t *__restrict__ fill,

@@ -74,7 +74,7 @@ def main():
     # through peer memory (fused integrator), every fifth step re-bins (migration); 40 steps in all
     nsteps, dt = 40, 0.005
     s.vv_step(dt, 23, rebin_every=5)
-    s.vv_step(dt, nsteps - 23, rebin_every=5)
+    s.vv_step(dt, nsteps - 23, rebin_every=-1)        # interval chosen by the library at every re-binning
     s.synchronize()
     ids1 = set(s.local_ids().tolist())
     res["migrated_out_of_this_rank0_slab"] = len(ids0 - ids1)
