@@ -62,6 +62,7 @@ SIGNATURES = {
     "emdee_set_velocities": [_p, _p],
     "emdee_set_masses": [_p, _p],
     "emdee_set_exclusions": [_p, _p, _p],
+    "emdee_set_pairs14": [_p, _p, _i64, _d],
     "emdee_set_skin": [_p, _d],
     "emdee_bin": [_p, _i],
     "emdee_get_cells_per_dimension": [_p, C.POINTER(C.c_int32)],

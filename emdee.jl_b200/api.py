@@ -220,6 +220,15 @@ class NonbondedSystem:
         m = np.ascontiguousarray(mask, dtype=np.uint64)
         call("emdee_set_exclusions", self._h, _ptr(b), _ptr(m))
 
+    def set_pairs14(self, pairs, scale):
+        """Pairs three bonds apart (workloads.pairs14) interact with `scale` (the force field's lj14scale, src/modelling.jl:199)
+        times the ordinary Lennard-Jones interaction.  pairs=None clears."""
+        if pairs is None:
+            call("emdee_set_pairs14", self._h, None, 0, 1.0)
+            return
+        ij = np.ascontiguousarray(pairs, dtype=np.int32).reshape(-1, 2)
+        call("emdee_set_pairs14", self._h, _ptr(ij), ij.shape[0], float(scale))
+
     def set_skin(self, skin):
         call("emdee_set_skin", self._h, float(skin))
 

@@ -16,6 +16,7 @@
 #include "force_tiles.cuh"
 #include "integrate.cuh"
 #include "slab.cuh"
+#include "pairs14.cuh"
 
 #define FC_REGS_ESTIMATE 128   // registers per thread of k_force_cells assumed by the residency model
 #define FL_REGS_ESTIMATE 128   // same for k_force_list (__launch_bounds__(256, 2))
@@ -196,6 +197,10 @@ struct emdee_system {
     unsigned long long *digest = nullptr;     // device {count, sum, xor} + pair counter at [3]
     int *err = nullptr;                       // device error flag
     int *brick_max = nullptr;
+    // 1-4 pairs (lj14scale): corrected after every CUTOFF force evaluation (pairs14.cuh)
+    int32_t *pairs14 = nullptr;
+    int64_t n14 = 0;
+    double scale14 = 1.0;
     // tiles for ALLPAIRS_REFERENCE
     int32_t *tiles = nullptr;
     int64_t ntiles = 0;
@@ -545,6 +550,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->sendcount); dev_free(s->recvcount); dev_free(s->list_lo); dev_free(s->list_hi);
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     for (int k = 0; k < 4; k++) dev_free(s->ghostbuf[k]);
+    dev_free(s->pairs14);
     delete s;
     return EMDEE_OK;
 }
@@ -700,6 +706,41 @@ extern "C" int emdee_set_exclusions(emdee_system *s, const int32_t *base, const 
     s->has_excl = true;
     s->forces_valid = false;
     return check_launch("set_exclusions");
+}
+
+extern "C" int emdee_set_pairs14(emdee_system *s, const int32_t *ij, int64_t n, double scale)
+{
+    SYS_ENTER(s, "emdee_set_pairs14");
+    dev_free(s->pairs14);
+    s->n14 = 0;
+    s->scale14 = 1.0;
+    s->forces_valid = false;
+    if (!ij || n == 0) return EMDEE_OK;
+    if (n < 0 || !std::isfinite(scale)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_pairs14: n=%lld, scale=%g", (long long)n, scale);
+    if (c->nranks > 1) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_set_pairs14: 1-4 scaling is not available in a slab decomposition");
+    for (int64_t k = 0; k < n; k++)
+        if (ij[2 * k] < 0 || ij[2 * k + 1] >= s->N || ij[2 * k] >= ij[2 * k + 1])
+            EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_pairs14: pair %lld = (%d,%d) must satisfy 0 <= i < j < N", (long long)k, ij[2 * k], ij[2 * k + 1]);
+    EMDEE_TRY(dev_alloc(&s->pairs14, (size_t)2 * n));
+    CUDA_TRY(cudaMemcpy(s->pairs14, ij, sizeof(int32_t) * 2 * n, cudaMemcpyHostToDevice));
+    s->n14 = n;
+    s->scale14 = scale;
+    return EMDEE_OK;
+}
+
+// (scale - 1) x the interaction of every 1-4 pair inside the cutoff, added to the selected outputs of the evaluation just made
+static int apply_pairs14(emdee_system *s, int bitmask)
+{
+    if (s->n14 == 0 || s->scale14 == 1.0) return EMDEE_OK;
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    Pairs14Args a;
+    a.n = s->n14; a.ij = s->pairs14; a.slot_of_id = s->slot_of_id;
+    a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2]; a.hs = A.hs; a.ts = A.ts;
+    a.L = s->L; a.cm1 = s->scale14 - 1.0; a.model = s->model; a.bitmask = bitmask;
+    a.fx = s->f[0]; a.fy = s->f[1]; a.fz = s->f[2]; a.en = s->en; a.vir = s->vir;
+    LAUNCH_1D(c, k_pairs14, a.n, a);
+    return check_launch("k_pairs14");
 }
 
 extern "C" int emdee_set_tiles(emdee_system *s, const int32_t *tiles, int64_t ntiles)
@@ -1132,6 +1173,7 @@ static double wall_ms()
         CUDA_TRY(cudaStreamSynchronize(c->stream));                      \
         const double now_ = wall_ms();                                   \
         g_rebin_phase[k] += now_ - phase_t0;                             \
+        if (c->rank == 0) fprintf(stderr, "[emdee] re-binning %d phase %d: %.3f ms\n", g_rebin_count, k, now_ - phase_t0); \
         phase_t0 = now_;                                                 \
     }
 
@@ -1788,6 +1830,7 @@ extern "C" int emdee_compute_nonbonded(emdee_system *s, int mode, int bitmask)
             if (!s->tiles_default) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_compute_nonbonded: box too small for a cell grid and a custom tile list is set");
             EMDEE_TRY(run_tiles(s, bitmask, true));
         }
+        EMDEE_TRY(apply_pairs14(s, bitmask));
     } else
         EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded: unknown mode %d", mode);
     s->last_mode = mode;
@@ -2011,7 +2054,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
     // reading the displacement back on every step
     const bool slab_adaptive = slab_fused && adaptive;
     const bool adaptive1 = adaptive && !slab_adaptive;      // per-step read-back (single GPU)
-    if (s->fuse_vv && (c->nranks == 1 || slab_fused) && list_capable(s) && s->fl_persistent && nsteps > 0) {
+    if (s->fuse_vv && s->n14 == 0 && (c->nranks == 1 || slab_fused) && list_capable(s) && s->fl_persistent && nsteps > 0) {
         // One kernel per step: the stepping kernel's epilogue finishes step n (second half-kick) and starts step n+1
         // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
         // k_vv only starts the first step of the call.
@@ -2123,6 +2166,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         }
         else
             EMDEE_TRY(run_tiles(s, EMDEE_FORCES, true));
+        EMDEE_TRY(apply_pairs14(s, EMDEE_FORCES));
         s->kick_pending = true;
     }
     if (s->kick_pending) {
@@ -2156,7 +2200,7 @@ extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
     out[3] = s->grid_ok ? s->fc_cap : 0;
     out[4] = listed ? 1 : 0;
     out[5] = listed && s->fl_persistent ? 1 : 0;
-    out[6] = listed && s->fl_persistent && s->fuse_vv && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
+    out[6] = listed && s->fl_persistent && s->fuse_vv && s->n14 == 0 && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
     out[7] = s->lcap8;
     return EMDEE_OK;
 }

@@ -155,6 +155,12 @@ __device__ __noinline__ int staged_slot(int j, const int *cs, const int *gbase, 
 // GPUs while the kernel runs, and L1 may hold a stale copy of a line that straddles owned and ghost slots.  (A separate
 // instantiation: the plain-load version must stay exactly as it is -- its loads are part of what the compiler schedules
 // around in the callers' hot loops.)
+__device__ __forceinline__ double ld_cg_f64(const double *p)      // L2-only load the compiler may schedule like a plain one
+{
+    double v;
+    asm("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+    return v;
+}
 template <bool CG = false>
 __device__ __noinline__ bool exact_in_range(const double *sx, const double *sy, const double *sz, int slot_i, int slot_j,
                                             double L, const LJModel m, double *xval)
@@ -162,8 +168,8 @@ __device__ __noinline__ bool exact_in_range(const double *sx, const double *sy, 
     double vx, vy, vz;
     double r2;
     if (CG)
-        r2 = min_image_r2(__ldcg(sx + slot_i), __ldcg(sy + slot_i), __ldcg(sz + slot_i), __ldcg(sx + slot_j), __ldcg(sy + slot_j),
-                          __ldcg(sz + slot_j), L, vx, vy, vz);
+        r2 = min_image_r2(ld_cg_f64(sx + slot_i), ld_cg_f64(sy + slot_i), ld_cg_f64(sz + slot_i), ld_cg_f64(sx + slot_j), ld_cg_f64(sy + slot_j),
+                          ld_cg_f64(sz + slot_j), L, vx, vy, vz);
     else
         r2 = min_image_r2(sx[slot_i], sy[slot_i], sz[slot_i], sx[slot_j], sy[slot_j], sz[slot_j], L, vx, vy, vz);
     double x = __dmul_rn(__dsub_rn(r2, m.rs2), m.id2);

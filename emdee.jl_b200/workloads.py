@@ -113,6 +113,30 @@ def exclusion_masks(N, bonds, max_distance=2):
     return base.astype(np.int32), mask
 
 
+def pairs14(N, bonds):
+    """Pairs of atoms exactly three bonds apart (graph distance 3: the "1-4" pairs whose Lennard-Jones interaction a force
+    field scales by lj14scale, src/modelling.jl:199), as an (n,2) int32 array with i<j in lexicographic order."""
+    bonds = np.asarray(bonds, dtype=np.int64).reshape(-1, 2)
+    nbr = [set() for _ in range(N)]
+    for a, b in bonds:
+        nbr[a].add(int(b))
+        nbr[b].add(int(a))
+    out = []
+    for i in range(N):
+        if not nbr[i]:
+            continue
+        seen = {i}
+        frontier = {i}
+        for _ in range(3):
+            nxt = set()
+            for k in frontier:
+                nxt |= nbr[k]
+            frontier = nxt - seen
+            seen |= frontier
+        out.extend((i, j) for j in sorted(frontier) if j > i)      # the last frontier: distance exactly 3
+    return np.asarray(out, dtype=np.int32).reshape(-1, 2)
+
+
 def replicate_molecular(pos, box, bonds, per_atom, reps, jitter=0.01, seed=SEED):
     """Replicate a molecular configuration reps^3 times into a cubic box of edge reps*box
     (config 4: the reference's test PDB replicated 9x9x9).  Copy k shifts every atom by the copy
@@ -151,5 +175,10 @@ def molecular_system(fixture, reps=9, jitter=0.01, seed=SEED):
                                             reps, jitter, seed)
     # the exclusion window of copy k is the window of copy 0 shifted by k*N0 atom ids
     base = (base0.astype(np.int64)[None, :] + (np.arange(reps ** 3, dtype=np.int64) * N0)[:, None]).reshape(-1)
+    # 1-4 pairs of copy k are those of copy 0 shifted by k*N0; the scale is the force field's lj14scale
+    p14_0 = pairs14(N0, fixture["bonds"]).astype(np.int64)
+    p14 = (p14_0[None, :, :] + (np.arange(reps ** 3, dtype=np.int64) * N0)[:, None, None]).reshape(-1, 2).astype(np.int32)
+    lj14 = float(fixture["lj14scale"]) if "lj14scale" in fixture else 1.0
     return dict(positions=pos, L=L, atoms=np.ascontiguousarray(per["atoms"]), masses=np.ascontiguousarray(per["mass"]),
-                excl=(base.astype(np.int32), np.ascontiguousarray(per["mask"])), bonds=bonds, cutoff=10.0, switch=9.0)
+                excl=(base.astype(np.int32), np.ascontiguousarray(per["mask"])), bonds=bonds, cutoff=10.0, switch=9.0,
+                pairs14=(p14, lj14))

@@ -77,6 +77,10 @@ int emdee_set_masses(emdee_system *sys, const double *mass_N);
 /* Intramolecular exclusions as a bitmask (adjacency source: src/modelling.jl:19-23,297-304):
  * pair (i,j) is excluded iff 0 <= j-base[i] < 64 and bit (j-base[i]) of mask[i] is set. NULL clears. */
 int emdee_set_exclusions(emdee_system *sys, const int32_t *base_N, const uint64_t *mask_N);
+/* 1-4 scaling: lj14scale of the force field (src/modelling.jl:199, test/data/dibenzo-p-dioxin-in-water.xml:84; parsed and
+ * never applied by the reference).  Pairs (i<j, global ids) three bonds apart interact with `scale` times an ordinary pair's
+ * energy / virial / force in EMDEE_CUTOFF evaluations and in emdee_vv_step.  NULL or n = 0 clears.  Single GPU. */
+int emdee_set_pairs14(emdee_system *sys, const int32_t *ij_2xn, int64_t n, double scale);
 /* Extra cell-edge margin so that binning stays valid while atoms move < skin/2 (0 = reference cells). */
 int emdee_set_skin(emdee_system *sys, double skin);
 

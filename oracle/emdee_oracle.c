@@ -304,6 +304,40 @@ int64_t oracle_pair_set_cells(int64_t N, const double *pos, double L, double cut
     return n;
 }
 
+/* 1-4 scaling (lj14scale: parsed at src/modelling.jl:199 from the force-field file, test/data/dibenzo-p-dioxin-in-water.xml:84,
+ * and never applied by the reference -- "parity unpinned", this definition IS the pin): a pair of atoms three bonds apart
+ * interacts with lj14scale times the Lennard-Jones energy / virial / force of an ordinary pair.  Stated as a correction to an
+ * evaluation that treated those pairs at full strength: every listed pair (i<j) inside the cutoff (same pair-set predicate,
+ * dist2 above) adds (scale-1)*(E, W) -- half to each atom, like every pair (src/nonbonded.jl:93-94) -- and (scale-1)*f_ij.
+ * Serial, in list order.  Returns the number of listed pairs inside the cutoff; dtot[0..1] += correction of sum E, sum W. */
+int64_t oracle_pairs14_correction(int64_t N, const double *pos, double L, double cutoff, double sw, const double *atoms,
+                                  const int32_t *ij, int64_t n14, double scale, int bitmask,
+                                  double *forces, double *energies, double *virials, double dtot[2])
+{
+    double model[3];
+    oracle_lj_model_f64(cutoff, sw, model);
+    const double rc2 = model[0], c = scale - 1.0;
+    int64_t inside = 0;
+    (void)N;
+    for (int64_t k = 0; k < n14; k++) {
+        const int64_t i = ij[2 * k], j = ij[2 * k + 1];
+        double si[3], sj[3], v[3];
+        for (int d = 0; d < 3; d++) { si[d] = pos[3 * i + d] / L; sj[d] = pos[3 * j + d] / L; }
+        const double r2 = dist2(si, sj, L, v);
+        if (!(r2 <= rc2)) continue;
+        inside++;
+        double E, W;
+        interaction_f64(r2, model, atoms[2 * i], atoms[2 * i + 1], atoms[2 * j], atoms[2 * j + 1], &E, &W);
+        const double q = c * (W / r2);
+        if (bitmask & 1)
+            for (int d = 0; d < 3; d++) { forces[3 * i + d] += q * v[d]; forces[3 * j + d] -= q * v[d]; }
+        if (bitmask & 2) { energies[i] += 0.5 * c * E; energies[j] += 0.5 * c * E; }
+        if (bitmask & 4) { virials[i] += 0.5 * c * W; virials[j] += 0.5 * c * W; }
+        if (dtot) { dtot[0] += c * E; dtot[1] += c * W; }
+    }
+    return inside;
+}
+
 /* Velocity-Verlet (the reference has no integrator, F6 -- "parity unpinned", this
  * definition IS the pin):  v += (dt/2m) f ; r += dt v (no wrapping) ; f = F(r) ; v += (dt/2m) f,
  * written with explicit fma so that CPU and GPU round identically per step.

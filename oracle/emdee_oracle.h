@@ -51,6 +51,11 @@ int oracle_cutoff_cells(int64_t N, const double *pos, double L, double cutoff, d
                         double *forces, double *energies, double *virials,
                         double totals[2], int64_t *npairs, uint64_t digest[3]);
 
+/* 1-4 scaling as a correction (lj14scale, src/modelling.jl:199; never applied by the reference) */
+int64_t oracle_pairs14_correction(int64_t N, const double *pos, double L, double cutoff, double sw, const double *atoms,
+                                  const int32_t *ij, int64_t n14, double scale, int bitmask,
+                                  double *forces, double *energies, double *virials, double dtot[2]);
+
 /* velocity-Verlet (defined by the oracle) */
 int oracle_vv_steps(int64_t N, double *pos, double *vel, double *forces, const double *mass, double L,
                     double cutoff, double sw, const double *atoms, int ndiv,

@@ -57,6 +57,8 @@ def lib(fast=False):
         L.oracle_pair_set_cells.argtypes = [_i64, _p, _d, _d, C.c_int, _p, _p, _p, _i64]
         L.oracle_cutoff_cells.restype = C.c_int
         L.oracle_cutoff_cells.argtypes = [_i64, _p, _d, _d, _d, _p, C.c_int, _p, _p, C.c_int, _p, _p, _p, _p, _p, _p]
+        L.oracle_pairs14_correction.restype = _i64
+        L.oracle_pairs14_correction.argtypes = [_i64, _p, _d, _d, _d, _p, _p, _i64, _d, C.c_int, _p, _p, _p, _p]
         L.oracle_vv_steps.restype = C.c_int
         L.oracle_vv_steps.argtypes = [_i64, _p, _p, _p, _p, _d, _d, _d, _p, C.c_int, _p, _p, _d, _i64]
         _LIBS[name] = L
@@ -171,8 +173,15 @@ def pair_set_cells(pos, L, cutoff, ndiv=1, excl=None):
     return ij
 
 
-def cutoff_cells(pos, L, cutoff, switch, atoms, ndiv=1, excl=None, bitmask=7, fast=False):
-    """Returns dict(forces, energies, virials, E, W, npairs, digest)."""
+def _fma(a, b, c):
+    """Element-wise a*b + c in extended precision, rounded to double (within one ulp of the fma() the C oracle uses)."""
+    return (np.asarray(a, dtype=np.longdouble) * np.asarray(b, dtype=np.longdouble) + np.asarray(c, dtype=np.longdouble)).astype(np.float64)
+
+
+def cutoff_cells(pos, L, cutoff, switch, atoms, ndiv=1, excl=None, bitmask=7, fast=False, pairs14=None):
+    """Returns dict(forces, energies, virials, E, W, npairs, digest).  pairs14 = (ij (n,2) int32 with i<j, scale): pairs three
+    bonds apart interact with `scale` times the ordinary pair's E / W / force (oracle_pairs14_correction); the pair set and
+    its digest are those of the unscaled evaluation."""
     pos = _arr(pos, np.float64); atoms = _arr(atoms, np.float64)
     N = pos.shape[0]
     eb, em = _excl(excl)
@@ -182,14 +191,27 @@ def cutoff_cells(pos, L, cutoff, switch, atoms, ndiv=1, excl=None, bitmask=7, fa
                                        _ptr(f), _ptr(e), _ptr(w), _ptr(tot), C.byref(npairs), _ptr(dig))
     if rc:
         raise RuntimeError("oracle_cutoff_cells failed with status %d" % rc)
-    return dict(forces=f, energies=e, virials=w, E=float(tot[0]), W=float(tot[1]), npairs=int(npairs.value), digest=dig)
+    n14 = None
+    if pairs14 is not None:
+        ij = _arr(pairs14[0], np.int32).reshape(-1, 2)
+        n14 = int(lib(fast).oracle_pairs14_correction(N, _ptr(pos), L, cutoff, switch, _ptr(atoms), _ptr(ij), ij.shape[0], float(pairs14[1]),
+                                                     bitmask, _ptr(f), _ptr(e), _ptr(w), _ptr(tot)))
+    return dict(forces=f, energies=e, virials=w, E=float(tot[0]), W=float(tot[1]), npairs=int(npairs.value), digest=dig, n14_inside=n14)
 
 
-def vv_steps(pos, vel, forces, mass, L, cutoff, switch, atoms, dt, nsteps, ndiv=1, excl=None, fast=False):
+def vv_steps(pos, vel, forces, mass, L, cutoff, switch, atoms, dt, nsteps, ndiv=1, excl=None, fast=False, pairs14=None):
     """In-place velocity-Verlet on copies; returns (pos, vel, forces)."""
     pos = np.array(pos, dtype=np.float64, order="C"); vel = np.array(vel, dtype=np.float64, order="C")
     forces = np.array(forces, dtype=np.float64, order="C")
     mass = _arr(mass, np.float64); atoms = _arr(atoms, np.float64)
+    if pairs14 is not None:      # same update as oracle_vv_steps (one fma per line), forces with the 1-4 correction
+        h = (0.5 * dt / mass)[:, None]
+        for _ in range(int(nsteps)):
+            vel = _fma(h, forces, vel)
+            pos = _fma(dt, vel, pos)
+            forces = cutoff_cells(pos, L, cutoff, switch, atoms, ndiv=ndiv, excl=excl, bitmask=1, fast=fast, pairs14=pairs14)["forces"]
+            vel = _fma(h, forces, vel)
+        return pos, vel, forces
     eb, em = _excl(excl)
     rc = lib(fast).oracle_vv_steps(pos.shape[0], _ptr(pos), _ptr(vel), _ptr(forces), _ptr(mass), L, cutoff, switch,
                                    _ptr(atoms), ndiv, _ptr(eb), _ptr(em), dt, nsteps)

@@ -151,6 +151,27 @@ def cutoff_compute(pos, L, cutoff, switch, atoms, excl_base=None, excl_mask=None
     return f, e, w, np.stack([i, j], axis=1).astype(np.int32)
 
 
+def pairs14_correction(pos, L, cutoff, switch, atoms, ij, scale):
+    """numpy twin of oracle_pairs14_correction (lj14scale, src/modelling.jl:199; never applied by the reference): listed pairs
+    inside the cutoff add (scale-1) x (E, W, f_ij).  Returns (df (N,3), de (N,), dw (N,), n_inside)."""
+    model = lj_model(cutoff, switch)
+    N = pos.shape[0]
+    ij = np.asarray(ij, dtype=np.int64).reshape(-1, 2)
+    i, j = ij[:, 0], ij[:, 1]
+    rv = _min_image_vectors(pos, L, i, j)
+    r2 = cutoff_r2(rv)
+    keep = r2 <= model[0]
+    i, j, rv, r2 = i[keep], j[keep], rv[keep], r2[keep]
+    E, W = interaction(r2, model, atoms[i, 0], atoms[i, 1], atoms[j, 0], atoms[j, 1])
+    c = scale - 1.0
+    fij = (c * (W / r2))[:, None] * rv
+    f = np.zeros((N, 3)); e = np.zeros(N); w = np.zeros(N)
+    np.add.at(f, i, fij); np.add.at(f, j, -fij)
+    np.add.at(e, i, 0.5 * c * E); np.add.at(e, j, 0.5 * c * E)
+    np.add.at(w, i, 0.5 * c * W); np.add.at(w, j, 0.5 * c * W)
+    return f, e, w, int(keep.sum())
+
+
 def mix64(z):
     """splitmix64 finaliser on uint64 arrays (wrap-around arithmetic)."""
     z = np.asarray(z, dtype=np.uint64)

@@ -96,8 +96,17 @@ def dioxin_water():
     f2, e2, w2, ij = on.cutoff_compute(pos, box, 10.0, 9.0, atoms, base, mask)
     assert np.array_equal(on.pair_digest(ij), cut["digest"]) and ij.shape[0] == cut["npairs"]
     assert np.abs(f2 - cut["forces"]).max() < 1e-11 and np.abs(e2 - cut["energies"]).max() < 1e-12
+    # the same evaluation with the force field's lj14scale applied to the pairs three bonds apart (C oracle vs numpy twin)
+    p14 = wl.pairs14(len(names), bonds)
+    lj14 = float(nb.get("lj14scale"))
+    cut14 = oc.cutoff_cells(pos, box, 10.0, 9.0, atoms, ndiv=1, excl=(base, mask), pairs14=(p14, lj14))
+    df, de, dw, n14 = on.pairs14_correction(pos, box, 10.0, 9.0, atoms, p14, lj14)
+    assert n14 == cut14["n14_inside"] == p14.shape[0] and np.array_equal(cut14["digest"], cut["digest"])
+    assert np.abs(f2 + df - cut14["forces"]).max() < 1e-11 and np.abs(e2 + de - cut14["energies"]).max() < 1e-12
+    assert abs((e2 + de).sum() - cut14["E"]) < 1e-9 and abs((w2 + dw).sum() - cut14["W"]) < 1e-9
     np.savez_compressed(
         os.path.join(HERE, "dioxin_water.npz"), positions=pos, box=box, bonds=bonds, residue=resi.astype(np.int32),
+        pairs14=p14, cutoff14_forces=cut14["forces"], cutoff14_E=cut14["E"], cutoff14_W=cut14["W"],
         type_index=tidx, type_names=np.array(types), type_sigma_nm=np.array([lj[t][0] for t in types]),
         type_epsilon=np.array([lj[t][1] for t in types]), type_mass=np.array([tmass[t] for t in types]),
         lj14scale=float(nb.get("lj14scale")),

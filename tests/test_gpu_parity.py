@@ -637,6 +637,59 @@ def test_state_invalidation(em, oracle, dioxin_water):
     s.close()
 
 
+def test_pairs14_scaling(em, oracle, dioxin_water):
+    """lj14scale (src/modelling.jl:199, test/data/dibenzo-p-dioxin-in-water.xml:84: 0.5; parsed and never applied by the
+    reference -- the oracle pins it): pairs three bonds apart at half strength, through the C ABI against the oracle and the
+    golden vectors.  Single fixture box (no cell grid: tiles), 3x3x3 replications (cell-list and pair-list kernels), and a few
+    velocity-Verlet steps (the correction sits between the force kernel and the kick, so the integrator is not fused)."""
+    g = dioxin_water
+    pos, L = g["positions"], float(g["box"])
+    N = pos.shape[0]
+    tidx = g["type_index"]
+    atoms = np.stack([0.5 * g["type_sigma_nm"][tidx] * 10.0, 2.0 * np.sqrt(g["type_epsilon"][tidx])], axis=1)
+    base, mask = em.workloads.exclusion_masks(N, g["bonds"])
+    s = make_system(em, pos, L, 10.0, 9.0, atoms)
+    s.set_exclusions(base, mask)
+    s.set_pairs14(g["pairs14"], float(g["lj14scale"]))
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    E, W, npairs = s.totals()
+    assert abs(E - float(g["cutoff14_E"])) <= E_TOL * abs(float(g["cutoff14_E"])) and abs(W - float(g["cutoff14_W"])) <= E_TOL * abs(float(g["cutoff14_W"]))
+    assert np.abs(s.forces() - g["cutoff14_forces"]).max() <= F_TOL * frms(g["cutoff14_forces"])
+    assert npairs == int(g["cutoff_npairs"])                       # the pair set is the unscaled one
+    s.set_pairs14(None, 1.0)
+    s.compute(em.CUTOFF, 7)
+    assert abs(s.totals()[0] - float(g["cutoff_E"])) <= E_TOL * abs(float(g["cutoff_E"]))
+    with pytest.raises(em.EmDeeError):
+        s.set_pairs14(np.array([[3, 3]]), 0.5)                     # i < j is required
+    s.close()
+    # replicated system: cell grid, pair list, stepping
+    w = em.workloads.molecular_system(dioxin_water, reps=3)
+    pos, L, atoms, excl, p14 = w["positions"], w["L"], w["atoms"], w["excl"], w["pairs14"]
+    assert p14[0].shape[0] == 47 * 27 and p14[1] == 0.5
+    N = pos.shape[0]
+    s = make_system(em, pos, L, 10.0, 9.0, atoms)
+    s.set_exclusions(*excl)
+    s.set_pairs14(*p14)
+    s.set_masses(w["masses"])
+    s.set_velocities(em.workloads.maxwell_velocities(N, 2.494, w["masses"]))
+    s.set_skin(0.5)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 10.0, 9.0, atoms, ndiv=1, excl=excl, pairs14=p14)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]))
+    assert np.array_equal(s.pair_set_digest(), ref["digest"]) and ref["n14_inside"] == 47 * 27
+    assert not s.step_config()["fused_vv"] and s.step_config()["pair_list"]
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.005, 3, rebin_every=2)
+    s.synchronize()
+    po, vo, fo = oracle.vv_steps(pos, w["positions"] * 0 + em.workloads.maxwell_velocities(N, 2.494, w["masses"]), ref["forces"], w["masses"], L, 10.0, 9.0,
+                                 atoms, 0.005, 3, ndiv=1, excl=excl, pairs14=p14)
+    assert np.abs(s.positions() - po).max() <= 1e-10 and np.abs(s.velocities() - vo).max() <= 1e-9
+    assert np.abs(s.forces() - fo).max() <= 1e-8 * frms(fo)
+    s.close()
+
+
 def test_skin_violation_is_reported(em):
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
