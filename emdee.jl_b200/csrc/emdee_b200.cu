@@ -190,6 +190,9 @@ struct emdee_system {
     int lcap8 = 24;                           // chunks per atom (192 entries; grown from the density, or EMDEE_LIST_CHUNKS)
     bool lcap8_forced = false;
     bool list_valid = false, use_list = true;
+    // Newton's third law inside the brick (EMDEE_N3=1, fused velocity-Verlet steps only): the list then holds every pair of
+    // two home atoms once; the other list kernels need the full list, so the flavour of the valid list is tracked
+    bool want_n3 = false, list_n3 = false, build_n3 = false;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
     double2 *ljtab = nullptr;                 // pair table of the LJ parameter classes
@@ -464,6 +467,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_PERSIST")) s->want_persistent = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_FUSE_VV")) s->fuse_vv = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_N3")) s->want_n3 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -1453,7 +1457,7 @@ template <bool EXCL>
 static int launch_build_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
-    auto kern = k_list_build<EXCL>;
+    auto kern = s->build_n3 ? k_list_build<EXCL, true> : k_list_build<EXCL, false>;
     const size_t smem = lb_smem_bytes(s->fc_cap, s->fc_ncs, LB_MAX_BLOCK, EXCL);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nblocks, LB_MAX_BLOCK, smem, s->ctx->stream>>>(a);
@@ -1473,9 +1477,12 @@ template <bool MULTI, bool COUNT, bool EW>
 static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
 {
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
-    if (!COUNT && !EW && s->vv_mode != 0)
-        kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
-    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2);
+    const bool n3 = !COUNT && !EW && s->vv_mode != 0 && s->list_n3;
+    if (!COUNT && !EW && s->vv_mode != 0) {
+        if (n3) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, true>;
+        else kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
+    }
+    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, n3 ? s->fc_gmax : 0);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
     // registers of its SM, so NCCL could not start before the first block retires otherwise)
@@ -1580,11 +1587,31 @@ extern "C" int emdee_fp16_threshold(const double half_extent[3], double rcut, fl
     return EMDEE_OK;
 }
 
+// Newton's third law inside the brick is usable when the persistent kernel runs, the home index fits the recipe's 11 spare
+// bits, and the accumulators fit next to the two staging buffers
+static bool n3_usable(const emdee_system *s)
+{
+    return s->want_n3 && s->fl_persistent && s->fc_gmax * 32 < 2047 &&
+           flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, s->fc_gmax) <= s->ctx->smem_optin;
+}
+
 // halo: when true (slab decomposition, inside the step loop) the ghost positions are refreshed on the
 // communication stream while the interior brick layers compute; the boundary layers wait for them.
 static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, int64_t pair_cap, bool halo = false, int mode = 0)
 {
     emdee_ctx *c = s->ctx;
+    if (mode >= 2 && s->list_valid) {
+        // the fused velocity-Verlet launch walks a half list (N3), every other list kernel the full one: rebuild on a change
+        const bool need = mode == 2 && s->vv_mode != 0 && n3_usable(s);
+        if (s->list_n3 != need) {
+            const int vm = s->vv_mode;
+            const bool pl = s->p2p_launch;
+            s->vv_mode = 0; s->p2p_launch = false; s->build_n3 = need;
+            const int rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1);
+            s->vv_mode = vm; s->p2p_launch = pl;
+            EMDEE_TRY(rc_);
+        }
+    }
     if ((s->ntypes > 0) != s->fc_typed) EMDEE_TRY(choose_bricks(s));   // LJ classes changed since binning: re-size shared memory
     AtomArrays &A = s->A[s->cur];
     CellArgs a = {};
@@ -1739,6 +1766,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         }
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
+    if (mode == 1) { s->list_n3 = s->build_n3; s->build_n3 = false; }
     return EMDEE_OK;
 }
 
@@ -2090,6 +2118,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 break;
             }
             if (!s->list_valid) {
+                s->build_n3 = n3_usable(s);
                 EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1));
                 s->list_valid = true;
             }

@@ -32,21 +32,28 @@
 #define FLP_NCONS (FLP_THREADS / 32 - FLP_NPROD)
 #define FLP_QS (FLP_NCONS * 32)          // row stride of the consumers' stacks
 
-__host__ __device__ inline size_t flp_buf_bytes(int cap, int ncs_max, int ntypes)
+// n3_groups > 0 (Newton's third law inside the brick): per buffer also the home index + 1 of every staged atom (uint16) and
+// the force accumulators of the home atoms (3 doubles per lane of every 32-atom group)
+__host__ __device__ inline size_t flp_buf_bytes(int cap, int ncs_max, int ntypes, int n3_groups = 0)
 {
     const size_t cap1 = (size_t)cap + 1;
     size_t b = cap1 * (sizeof(double2) + sizeof(double) + sizeof(uint2));
     if (ntypes > 1) b += (cap1 + 15) & ~(size_t)15;
     b = (b + 15) & ~(size_t)15;
     b += 8 * sizeof(int);                         // scal[]
-    return (b + 15) & ~(size_t)15;
+    b = (b + 15) & ~(size_t)15;
+    if (n3_groups > 0) {
+        b += (cap1 * sizeof(uint16_t) + 15) & ~(size_t)15;
+        b += (size_t)n3_groups * 32 * 3 * sizeof(double);
+    }
+    return b;
 }
 // nbuf staging buffers; the per-lane stacks shrink to 24 entries when three buffers are wanted (a brick period is
 // set by its slowest warp task, a third buffer lets the other warps run ahead instead of waiting for it)
 __host__ __device__ inline int flp_qcap(int nbuf) { return nbuf >= 3 ? 24 : FL_QCAP; }
-__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf)
+__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf, int n3_groups = 0)
 {
-    return nbuf * flp_buf_bytes(cap, ncs_max, ntypes) + (size_t)ntypes * ntypes * sizeof(double2) +
+    return nbuf * flp_buf_bytes(cap, ncs_max, ntypes, n3_groups) + (size_t)ntypes * ntypes * sizeof(double2) +
            (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t);
 }
 
@@ -82,6 +89,8 @@ struct BrickBuf {
     uint2 *ph;
     uint8_t *ptyp;
     int *scal;            // [0] home atoms, [1] staged atoms + 1, [3] task cursor, [4] brick (-1: done)
+    uint16_t *phome;      // N3: home index + 1 of a staged atom (0: halo atom)
+    double *acc;          // N3: force accumulators of the home atoms, acc[3 * home index + c]
 };
 __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int ncs_max, bool multi)
 {
@@ -95,6 +104,9 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
     if (multi) off += (cap1 + 15) & ~(size_t)15;
     off = (off + 15) & ~(size_t)15;
     b.scal = reinterpret_cast<int *>(base + off);
+    off = (off + 8 * sizeof(int) + 15) & ~(size_t)15;
+    b.phome = reinterpret_cast<uint16_t *>(base + off);
+    b.acc = reinterpret_cast<double *>(base + off + ((cap1 * sizeof(uint16_t) + 15) & ~(size_t)15));
     return b;
 }
 
@@ -113,7 +125,10 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // P2P: slab decomposition with peer-mapped halos (see CellArgs): ghost positions are written by the neighbouring GPUs during
 // the launch, so staged coordinates are read with L2-only loads, boundary bricks wait for the neighbours' flags, and the
 // integrator pushes my boundary atoms to the neighbours.
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false>
+// N3: the list holds every pair of two home atoms once (k_list_build<.., N3>); the evaluating lane adds the reaction to the
+// partner's accumulator in shared memory (FP64 compare-and-swap loops), home atoms' own sums go to the same accumulators at the
+// end of a warp task, and the producers write a brick's forces out once its consumers have released the buffer.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false>
 __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
@@ -121,7 +136,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap1 = a.cap + 1;
-    const size_t bufsz = flp_buf_bytes(a.cap, a.ncs_max, a.ntypes);
+    const size_t bufsz = flp_buf_bytes(a.cap, a.ncs_max, a.ntypes, N3 ? a.gmax : 0);
     double2 *ljt = reinterpret_cast<double2 *>(smem_raw + NBUF * bufsz);
     uint16_t *qguard = reinterpret_cast<uint16_t *>(ljt + a.ntypes * a.ntypes);
     uint16_t *queue = qguard + FLP_QS;
@@ -130,6 +145,11 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int t = tid; t < a.ntypes * a.ntypes; t += FLP_THREADS) ljt[t] = a.ljtab[t];
     if (tid < FLP_QS) qguard[tid] = 0;
+    if (N3)
+        for (int q = 0; q < NBUF; q++) {
+            double *acc0 = brick_buf(smem_raw + q * bufsz, a.cap, a.ncs_max, MULTI).acc;
+            for (int t = tid; t < a.gmax * 96; t += FLP_THREADS) acc0[t] = 0.0;
+        }
     __syncthreads();
 #if FLP_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -224,6 +244,17 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
             }
         };
+        // N3: the forces of a released brick's home atoms leave shared memory (and the accumulators are cleared for the next brick);
+        // thread tid handles the same home atoms as in advance_atoms, which reads these forces back from global memory
+        auto flush_forces = [&](const BrickBuf &Bf, int vbid, int vnh) {
+            const int2 *vrecipe = a.recipe + (size_t)vbid * a.rcap;
+            for (int h = tid; h < vnh && (h >> 5) < a.gmax; h += PN) {
+                const int st = a.homeidx[((size_t)vbid * a.gmax + (h >> 5)) * 32 + (h & 31)];
+                const int slot = vrecipe[st].x;
+                a.fx[slot] = Bf.acc[3 * h]; a.fy[slot] = Bf.acc[3 * h + 1]; a.fz[slot] = Bf.acc[3 * h + 2];
+                Bf.acc[3 * h] = 0.0; Bf.acc[3 * h + 1] = 0.0; Bf.acc[3 * h + 2] = 0.0;
+            }
+        };
         // ghosts written by the neighbours (peer memory): a brick whose halo reaches ghost planes waits for the neighbour's flag
         bool seen_lo = !(VV && P2P && a.wait_epoch != 0), seen_hi = seen_lo;
         auto wait_flag = [&](const unsigned long long *f) {
@@ -244,6 +275,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 FLP_T(tw0);
                 if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);
                 FLP_TACC(0, clock64() - tw0);
+                if (N3 && held_bid[b] >= 0) flush_forces(B, held_bid[b], held_nh[b]);
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
                 bar_arrive(1 + b, FLP_THREADS);
@@ -259,6 +291,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                             FLP_T(tw1);
                             bar_sync(1 + NBUF + ob, FLP_THREADS);
                             FLP_T(ta1);
+                            if (N3) flush_forces(brick_buf(smem_raw + ob * bufsz, a.cap, a.ncs_max, MULTI), held_bid[ob], held_nh[ob]);
                             advance_atoms(held_bid[ob], held_nh[ob]);
                             FLP_TACC(0, ta1 - tw1);
                             FLP_TACC(2, clock64() - ta1);
@@ -308,7 +341,8 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     if (i >= n1) continue;
                     const int cc = rc[u].y;
                     const double cx = ((double)(ux0 + (cc & 255)) + 0.5) * invM, cy = ((double)(uy0 + ((cc >> 8) & 255)) + 0.5) * invM,
-                                 cz = ((double)(uz0 + (cc >> 16)) + 0.5) * invM;
+                                 cz = ((double)(uz0 + (N3 ? (cc >> 16) & 31 : cc >> 16)) + 0.5) * invM;
+                    if (N3) B.phome[i] = (uint16_t)((unsigned)cc >> 21);
                     double dx = sx[u] - cx, dy = sy[u] - cy, dz = sz[u] - cz;
                     dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);      // image nearest to the staged cell
                     const double px = a.L * (dx + (cx - bcx)), py = a.L * (dy + (cy - bcy)), pzv = a.L * (dz + (cz - bcz));
@@ -353,7 +387,9 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);       // empty[b]: the consumers are done with this buffer
             FLP_T(ts0);
             FLP_TACC(0, ts0 - tw2);
+            if (N3 && held_bid[b] >= 0) flush_forces(B, held_bid[b], held_nh[b]);
             if (tid == 0) {
+                if (N3) B.phome[0] = 0;
                 B.pxy[0] = make_double2(1e30, 1e30);
                 B.pz[0] = 1e30;
                 const __half2 far = __floats2half2_rn(60000.0f, 60000.0f), farz = __floats2half2_rn(60000.0f, 0.0f);
@@ -415,6 +451,8 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         const double *pz = B.pz;
         const uint2 *ph = B.ph;
         const uint8_t *ptyp = B.ptyp;
+        const uint16_t *phome = B.phome;
+        double *acc = B.acc;
         const int2 *recipe = a.recipe + (size_t)bid * a.rcap;
         const int nh = B.scal[0];
         const int ngroups = (nh + 31) >> 5;
@@ -472,6 +510,13 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
                 if (EW) { e += t < 0 ? Eg : 0.0; w += t < 0 ? Wg : 0.0; }
                 if (COUNT) np += t < 0 ? 1 : 0;
+                if (N3) {      // the partner is a home atom of this brick: it does not list me, its share is added here
+                    const unsigned hj = phome[j];
+                    if (hj != 0 && t < 0) {
+                        double *aj = acc + 3 * (hj - 1);
+                        atomicAdd(aj, -qf * vx); atomicAdd(aj + 1, -qf * vy); atomicAdd(aj + 2, -qf * vz);
+                    }
+                }
             };
             auto pair_eval = [&](int idx) {
                 const int j = queue[max(idx, -1) * FLP_QS + ctid];
@@ -524,7 +569,32 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             }
             drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
 
-            if (tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
+            if (N3 && tmin <= 2u) {
+                // pairs within 3e-6 of rc2 were left out by the hot loop (both sides): add the ones the oracle's decision keeps
+                const int nslots = ((nent + 7) >> 3) << 3;
+                const uint16_t *ent = reinterpret_cast<const uint16_t *>(lp);
+                for (int kk = 0; kk < nslots; kk++) {
+                    const int j = ent[((kk >> 3) << 8) + (kk & 7)];
+                    if (j == 0) continue;
+                    const double2 j0 = pxy[j];
+                    const double vx = pix - j0.x, vy = piy - j0.y, vz = piz - pz[j];
+                    const double r2 = fma(vz, vz, fma(vy, vy, vx * vx));
+                    if (pair_in_range(r2, a.rc2hi) != 0) continue;
+                    double xval = 0.0;
+                    if (!exact_in_range<P2P>(a.sx, a.sy, a.sz, slot_i, recipe[j].x, a.L, a.model, &xval)) continue;
+                    double2 pr = ljrow[0];
+                    if (MULTI) pr = ljrow[ptyp[j]];
+                    double Eg = 0, Wg = 0;
+                    const double qf = lj_pair_q<false>(r2, pr.x, pr.y, a.fast, true, xval, Eg, Wg);
+                    fx = fma(qf, vx, fx); fy = fma(qf, vy, fy); fz = fma(qf, vz, fz);
+                    const unsigned hj = phome[j];
+                    if (hj != 0) {
+                        double *aj = acc + 3 * (hj - 1);
+                        atomicAdd(aj, -qf * vx); atomicAdd(aj + 1, -qf * vy); atomicAdd(aj + 2, -qf * vz);
+                    }
+                }
+            }
+            if (!N3 && tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
                 LaneRedo rd;
                 rd.pxy = pxy; rd.pz = pz; rd.ptyp = ptyp; rd.ljt = ljt; rd.cs = nullptr; rd.gbase = nullptr; rd.recipe = recipe;
                 rd.ncs = 0; rd.ntypes = a.ntypes; rd.me = me; rd.slot_i = slot_i; rd.nent = nent;
@@ -537,12 +607,15 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             }
             if (COUNT) npair += np;
             if (active) {
-                if (store_f) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
+                if (N3) {      // own sums join the reactions other lanes have added; the producers write the totals out
+                    double *ai = acc + 3 * h;
+                    atomicAdd(ai, fx); atomicAdd(ai + 1, fy); atomicAdd(ai + 2, fz);
+                } else if (store_f) { a.fx[slot_i] = fx; a.fy[slot_i] = fy; a.fz[slot_i] = fz; }
                 if (EW) { a.en[slot_i] = 0.5 * e; a.vir[slot_i] = 0.5 * w; }
             }
             grp = ngrp;
         }
-        if (VV) __threadfence_block();                                // the producers read this brick's forces after empty[b]
+        if (VV || N3) __threadfence_block();                          // the producers read this brick's forces after empty[b]
         bar_arrive(1 + NBUF + b, FLP_THREADS);                        // empty[b]
     }
     if (COUNT) {

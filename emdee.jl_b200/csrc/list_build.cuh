@@ -44,7 +44,11 @@ __host__ __device__ inline size_t lb_smem_bytes(int cap, int ncs_max, int block,
     return b;
 }
 
-template <bool EXCL>
+// N3 (Newton's third law inside the brick): a pair of two HOME atoms of the brick is listed once, by the atom with the smaller
+// staged index (the force kernel adds the reaction to the partner's accumulator in shared memory); pairs with a halo atom stay
+// listed from the home side as before (the brick that owns the halo atom evaluates its side itself).  The recipe then also
+// carries each staged atom's home index + 1 (bits 21..31 of the cell code; 0: a halo atom).
+template <bool EXCL, bool N3 = false>
 __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(CellArgs a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -124,7 +128,15 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         rec[4] = __float2half_rn((float)pz);
         if (EXCL) pid[idx] = a.id[slot];
         // the staging recipe of this brick: slot and staged-cell coordinates of every staged atom
-        if (idx + 1 < a.rcap) recipe[idx + 1] = make_int2(slot, ccode);
+        int code = ccode;
+        if (N3) {
+            const int cx = ccode & 255, cy = (ccode >> 8) & 255, cz = ccode >> 16;
+            if (cx >= R && cx < R + nhx && cy >= R && cy < R + nhy && cz >= R && cz < R + nhz) {
+                const int hrow_ = cz * syn + cy;
+                code |= (hstart[(cz - R) * nhy + (cy - R)] + (idx - cs[hrow_ * sxn + R]) + 1) << 21;
+            }
+        }
+        if (idx + 1 < a.rcap) recipe[idx + 1] = make_int2(slot, code);
     });
     {   // header and home list (home atom h -> staged index + 1)
         const int nh = hstart[nhy * nhz];
@@ -162,6 +174,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         const int self = a0 + lane;
         const bool active = self < a1;
         const int me = active ? self : a0;
+        const int h0own = cs[hrow * sxn + R];          // first home atom of the task's own row (N3)
         // own coordinates, duplicated in both halves; an inactive lane sits far away and accepts nothing
         const __half *mrec = hph + (me >> 1) * 8 + (me & 1);
         const __half hfar = __float2half(-60000.0f);
@@ -230,7 +243,10 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
             const __half2 dz = __hsub2(*reinterpret_cast<const __half2 *>(&c.z), iz);
             const __half2 r2 = __hfma2(dz, dz, __hfma2(dy, dy, __hmul2(dx, dx)));
             bool lo = __hle(__low2half(r2), __low2half(th)), hi = __hle(__high2half(r2), __high2half(th));
-            if (decltype(SELF)::value) { lo = lo && (2 * q != me); hi = hi && (2 * q + 1 != me); }
+            if (decltype(SELF)::value) {
+                if (N3) { lo = lo && (2 * q < h0own || 2 * q > me); hi = hi && (2 * q + 1 < h0own || 2 * q + 1 > me); }
+                else { lo = lo && (2 * q != me); hi = hi && (2 * q + 1 != me); }
+            }
             push(lo, 2 * q + 1);
             push(hi, 2 * q + 2);
         };
@@ -262,7 +278,14 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
             const int row = (czi + rw / nwin - R) * syn + (cyi + rw % nwin - R);
             const int p0 = cs[row * sxn + cxa - R];
             const int p1 = min(cs[row * sxn + cxb + R + 1], nstaged);
-            if (p0 < p1) {
+            if (N3 && row < hrow) {
+                // a home row in front of mine: its home atoms list me, not the other way round -- scan what lies beside them
+                const int ry = row % syn, rz = row / syn;
+                const bool homerow = ry >= R && ry < R + nhy && rz >= R && rz < R + nhz;
+                const int h0 = homerow ? cs[row * sxn + R] : p1, h1 = homerow ? cs[row * sxn + R + nhx] : p1;
+                if (p0 < min(p1, h0)) scan_row(p0, min(p1, h0), std::false_type());
+                if (max(p0, h1) < p1) scan_row(max(p0, h1), p1, std::false_type());
+            } else if (p0 < p1) {
                 if (row == hrow) scan_row(p0, p1, std::true_type());
                 else scan_row(p0, p1, std::false_type());
             }

@@ -260,14 +260,18 @@ def test_exclusions_molecular(em, oracle, dioxin_water):
     s.close()
 
 
-@pytest.mark.parametrize("fuse_vv", [0, 1, 2])
+@pytest.mark.parametrize("fuse_vv", [0, 1, 2, 3])
 def test_velocity_verlet(em, oracle, fuse_vv, monkeypatch):
     """fuse_vv = 1: kick and drift run in the stepping kernel (one kernel per step) instead of k_vv; 2: the fused loop
     hands over to the generic loop in the middle of a call (what happens when a re-binning picks bricks whose two
-    staging buffers no longer fit; forced here at the re-binning of step 5 by EMDEE_DEBUG_UNFUSE_AT)."""
+    staging buffers no longer fit; forced here at the re-binning of step 5 by EMDEE_DEBUG_UNFUSE_AT); 3: the fused loop
+    with Newton's third law inside the brick (EMDEE_N3=1: half list for home-home pairs, reactions through shared-memory
+    accumulators)."""
     monkeypatch.setenv("EMDEE_FUSE_VV", str(min(fuse_vv, 1)))
     if fuse_vv == 2:
         monkeypatch.setenv("EMDEE_DEBUG_UNFUSE_AT", "5")
+    if fuse_vv == 3:
+        monkeypatch.setenv("EMDEE_N3", "1")
     pos, L = em.workloads.fcc_lattice(8)
     N = pos.shape[0]
     atoms = em.workloads.lj_fluid_atoms(N)
@@ -325,7 +329,7 @@ def test_velocity_verlet(em, oracle, fuse_vv, monkeypatch):
     s.close()
 
 
-@pytest.mark.parametrize("variant", ["persistent", "fused_vv", "block_per_brick", "ndiv2", "no_list"])
+@pytest.mark.parametrize("variant", ["persistent", "fused_vv", "n3", "block_per_brick", "ndiv2", "no_list"])
 def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     """The stepping path (pair list built on the re-binning step, walked by k_force_list_p afterwards): after
     steps that only walked the list, forces and the evaluated pair count equal the oracle's at the same
@@ -333,7 +337,8 @@ def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     so the count is the sharp check.  Variants: the persistent kernel (default), the block-per-brick kernel
     it falls back to when two staging buffers do not fit, cells of half the edge (ndiv = 2), and stepping
     without a list (window scan on every step)."""
-    monkeypatch.setenv("EMDEE_FUSE_VV", "1" if variant == "fused_vv" else "0")
+    monkeypatch.setenv("EMDEE_FUSE_VV", "1" if variant in ("fused_vv", "n3") else "0")
+    monkeypatch.setenv("EMDEE_N3", "1" if variant == "n3" else "0")       # Newton's third law inside the brick (fused steps only)
     if variant == "block_per_brick":
         monkeypatch.setenv("EMDEE_PERSIST", "0")
     if variant == "no_list":
@@ -364,10 +369,13 @@ def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     s.close()
 
 
-def test_pair_list_shell_exactly_at_cutoff(em, oracle):
+@pytest.mark.parametrize("n3", [0, 1])
+def test_pair_list_shell_exactly_at_cutoff(em, oracle, n3, monkeypatch):
     """Simple-cubic lattice with spacing rc/2: six neighbours of every atom sit at r = rc up to the rounding of
     the oracle's s = r/L sequence, so every lane takes the exact-decision path.  Pair set and count must match
-    the oracle bit for bit in the single-point kernel and in the stepping kernel."""
+    the oracle bit for bit in the single-point kernel and in the stepping kernel (n3 = 1: the variant with Newton's
+    third law inside the brick, whose exact path adds the borderline pairs instead of redoing the lane)."""
+    monkeypatch.setenv("EMDEE_N3", str(n3))
     n, a0 = 12, 1.25
     L = n * a0
     g = np.arange(n) * a0
