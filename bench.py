@@ -549,19 +549,32 @@ def run_b200(args):
             parity = {"ok": False, "error": repr(ex)}
 
     # ---- e2e: host buffers in, host buffers out, through the C ABI ---------------------------------
-    pos_h = torch.from_numpy(w["pos"].copy()).pin_memory().numpy()
-    f_h = torch.empty((N, 3), dtype=torch.float64).pin_memory().numpy()
-    e_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
-    w_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+    # One GPU: the whole arrays.  Slab ranks: every rank moves the window of the id-ordered host arrays that covers the atoms it
+    # holds (emdee_get_local_id_range: owned + ghosts; for these lattices ids run with z, so a window is about N/ranks rows)
+    # and receives the rows of the atoms it owns -- per call the ranks together move about what one GPU moves alone.
     s.set_skin(0.0)
+    s.bin(args.ndiv)
+    id0, cnt = s.local_id_range() if world > 1 else (0, N)
+    pos_h = torch.from_numpy(w["pos"][id0:id0 + cnt].copy()).pin_memory().numpy()
+    f_h = torch.empty((cnt, 3), dtype=torch.float64).pin_memory().numpy()
+    e_h = torch.empty(cnt, dtype=torch.float64).pin_memory().numpy()
+    w_h = torch.empty(cnt, dtype=torch.float64).pin_memory().numpy()
 
     def e2e_once():
-        s.set_positions(pos_h)
+        if world > 1:
+            s.set_positions_range(id0, pos_h)
+        else:
+            s.set_positions(pos_h)
         s.bin(args.ndiv)
         s.compute(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS)
-        s.forces(f_h)
-        s.energies(e_h)
-        s.virials(w_h)
+        if world > 1:
+            s.forces_range(id0, f_h)
+            s.energies_range(id0, e_h)
+            s.virials_range(id0, w_h)
+        else:
+            s.forces(f_h)
+            s.energies(e_h)
+            s.virials(w_h)
 
     e2e_once()
     pairs_e2e = allsum(float(s.pair_set_digest()[0]))
@@ -571,9 +584,12 @@ def run_b200(args):
         e2e_once()
     barrier()
     e2e_t = allmax((time.perf_counter() - t0) / args.e2e_iters)
-    e2e = {"value": pairs_e2e / e2e_t, "unit": "pair-interactions/s", "h2d_bytes_per_step": 24 * N,
-           "d2h_bytes_per_step": 40 * N, "ms_per_call": e2e_t * 1e3, "atom_evals_per_s": N / e2e_t,
-           "call": "set_positions(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> forces/energies/virials(host)"}
+    rows = allsum(float(cnt))
+    e2e = {"value": pairs_e2e / e2e_t, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(24 * rows),
+           "d2h_bytes_per_step": int(40 * rows), "ms_per_call": e2e_t * 1e3, "atom_evals_per_s": N / e2e_t,
+           "call": ("set_positions(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> forces/energies/virials(host)" if world == 1 else
+                    "per rank, on the id window of the atoms it holds: set_positions_range(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> "
+                    "forces/energies/virials_range(host); bytes are summed over ranks")}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

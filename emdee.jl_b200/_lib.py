@@ -63,6 +63,11 @@ SIGNATURES = {
     "emdee_set_masses": [_p, _p],
     "emdee_set_exclusions": [_p, _p, _p],
     "emdee_set_pairs14": [_p, _p, _i64, _d],
+    "emdee_get_local_id_range": [_p, C.POINTER(_i64), C.POINTER(_i64)],
+    "emdee_set_positions_range": [_p, _i64, _i64, _p],
+    "emdee_get_forces_range": [_p, _i64, _i64, _p],
+    "emdee_get_energies_range": [_p, _i64, _i64, _p],
+    "emdee_get_virials_range": [_p, _i64, _i64, _p],
     "emdee_set_skin": [_p, _d],
     "emdee_bin": [_p, _i],
     "emdee_get_cells_per_dimension": [_p, C.POINTER(C.c_int32)],

@@ -202,6 +202,31 @@ class NonbondedSystem:
             raise ValueError("positions must hold N atoms")
         call("emdee_set_positions", self._h, _ptr(p))
 
+    def local_id_range(self):
+        """(first id, count): the smallest window of global ids covering every atom this rank holds (owned + ghosts)."""
+        a, n = C.c_int64(), C.c_int64()
+        call("emdee_get_local_id_range", self._h, C.byref(a), C.byref(n))
+        return int(a.value), int(n.value)
+
+    def set_positions_range(self, id_first, rows):
+        """Rows id_first.. of the (N, 3) position array (a slab rank uploads only the atoms it holds)."""
+        p = np.ascontiguousarray(rows, dtype=np.float64)
+        if p.ndim != 2 or p.shape[1] != 3:
+            raise ValueError("rows must be (count, 3)")
+        call("emdee_set_positions_range", self._h, int(id_first), p.shape[0], _ptr(p))
+
+    def forces_range(self, id_first, out):
+        call("emdee_get_forces_range", self._h, int(id_first), out.shape[0], _ptr(out))
+        return out
+
+    def energies_range(self, id_first, out):
+        call("emdee_get_energies_range", self._h, int(id_first), out.shape[0], _ptr(out))
+        return out
+
+    def virials_range(self, id_first, out):
+        call("emdee_get_virials_range", self._h, int(id_first), out.shape[0], _ptr(out))
+        return out
+
     def set_velocities(self, velocities):
         v = _as_3xN(velocities, "velocities")
         call("emdee_set_velocities", self._h, _ptr(v))

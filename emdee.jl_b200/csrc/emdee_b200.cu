@@ -667,6 +667,71 @@ extern "C" int emdee_set_positions(emdee_system *s, const double *pos)
     return check_launch("set_positions");
 }
 
+// ---- windows of the id-ordered host arrays: a slab rank moves only the rows of the atoms it holds ----------------------------
+extern "C" int emdee_get_local_id_range(emdee_system *s, int64_t *id_first, int64_t *count)
+{
+    SYS_ENTER(s, "emdee_get_local_id_range");
+    if (!id_first || !count) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_local_id_range: null output");
+    if (ntot == s->N) { *id_first = 0; *count = s->N; return EMDEE_OK; }      // not decomposed (yet): every atom is here
+    EMDEE_TRY(ensure_tmp(s, 2 * sizeof(int)));
+    const int init[2] = {0x7fffffff, -1};
+    CUDA_TRY(cudaMemcpyAsync(s->tmp, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH_1D(c, k_id_range, ntot, ntot, A.id, reinterpret_cast<int *>(s->tmp));
+    int lohi[2];
+    CUDA_TRY(cudaMemcpyAsync(lohi, s->tmp, sizeof(lohi), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *id_first = lohi[0];
+    *count = (int64_t)lohi[1] - lohi[0] + 1;
+    return check_launch("k_id_range");
+}
+
+extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int64_t count, const double *pos)
+{
+    SYS_ENTER(s, "emdee_set_positions_range");
+    if (!pos || id_first < 0 || count < 0 || id_first + count > s->N)
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: rows [%lld, %lld) of %lld", (long long)id_first, (long long)(id_first + count), (long long)s->N);
+    EMDEE_TRY(upload(s, pos, sizeof(double) * 3 * count));
+    LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, A.id, id_first, count, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
+    LAUNCH_1D(c, k_scale_positions, ntot, ntot, A.r[0], A.r[1], A.r[2], s->L, A.s[0], A.s[1], A.s[2]);
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (flag == 7) {
+        CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: the window does not cover every atom this rank holds (emdee_get_local_id_range)");
+    }
+    s->has_pos = true;
+    s->binned = false;
+    s->forces_valid = false;
+    s->kick_pending = false;
+    return check_launch("set_positions_range");
+}
+
+static int get3_range(emdee_system *s, double *const src[3], int64_t id_first, int64_t count, double *out, const char *what)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    if (!out || id_first < 0 || count < 0 || id_first + count > s->N) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: bad window", what);
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * count));
+    CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * 3 * count, c->stream));
+    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, src[0], src[1], src[2], s->tmp);
+    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_launch(what);
+}
+static int get1_range(emdee_system *s, const double *src, int64_t id_first, int64_t count, double *out, const char *what)
+{
+    emdee_ctx *c = s->ctx;
+    AtomArrays &A = s->A[s->cur];
+    if (!out || id_first < 0 || count < 0 || id_first + count > s->N) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: bad window", what);
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * count));
+    CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * count, c->stream));
+    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, src, s->tmp);
+    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    return check_launch(what);
+}
+
 extern "C" int emdee_set_velocities(emdee_system *s, const double *vel)
 {
     SYS_ENTER(s, "emdee_set_velocities");
@@ -1827,6 +1892,8 @@ static int check_device_flag(emdee_system *s, const char *where)
         if (flag == 2) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: a brick overflowed its shared-memory staging area", where);
         if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its capacity (set EMDEE_LIST_CHUNKS higher or EMDEE_LIST=0)", where);
         if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
+        if (flag == 6) EMDEE_FAIL(EMDEE_ERR_NCCL, "%s: a neighbouring rank never published its boundary atoms (peer-mapped halo timed out after ~2 s)", where);
+        if (flag == 7) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: a position window did not cover every atom this rank holds", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
     }
     return EMDEE_OK;
@@ -1925,6 +1992,28 @@ extern "C" int emdee_get_virials(emdee_system *s, double *out)
     if (!(s->last_bitmask & EMDEE_VIRIALS)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_virials: the last compute did not select VIRIALS");
     EMDEE_TRY(check_device_flag(s, "emdee_get_virials"));
     return get1(s, s->vir, out, "emdee_get_virials");
+}
+
+extern "C" int emdee_get_forces_range(emdee_system *s, int64_t id_first, int64_t count, double *out)
+{
+    SYS_ENTER(s, "emdee_get_forces_range");
+    if (!(s->last_bitmask & EMDEE_FORCES)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_forces_range: the last compute did not select FORCES");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_forces_range"));
+    return get3_range(s, s->f, id_first, count, out, "emdee_get_forces_range");
+}
+extern "C" int emdee_get_energies_range(emdee_system *s, int64_t id_first, int64_t count, double *out)
+{
+    SYS_ENTER(s, "emdee_get_energies_range");
+    if (!(s->last_bitmask & EMDEE_ENERGIES)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_energies_range: the last compute did not select ENERGIES");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_energies_range"));
+    return get1_range(s, s->en, id_first, count, out, "emdee_get_energies_range");
+}
+extern "C" int emdee_get_virials_range(emdee_system *s, int64_t id_first, int64_t count, double *out)
+{
+    SYS_ENTER(s, "emdee_get_virials_range");
+    if (!(s->last_bitmask & EMDEE_VIRIALS)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_virials_range: the last compute did not select VIRIALS");
+    EMDEE_TRY(check_device_flag(s, "emdee_get_virials_range"));
+    return get1_range(s, s->vir, id_first, count, out, "emdee_get_virials_range");
 }
 
 __global__ void k_sum_ew(int64_t first, int64_t n, const double *__restrict__ en, const double *__restrict__ vir,

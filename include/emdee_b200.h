@@ -108,6 +108,16 @@ int emdee_get_virials(emdee_system *sys, double *virials_N);
 /* sum of per-atom energies / virials and the number of pairs in the set (this rank's atoms). */
 int emdee_get_totals(emdee_system *sys, double *E, double *W, int64_t *npairs);
 
+/* Windows of the id-ordered host arrays (additive; a slab rank then moves only the rows of the atoms it holds over PCIe instead
+ * of all N): [*id_first, *id_first + *count) is the smallest id window covering every atom this rank holds (owned + ghosts; all
+ * N before the first emdee_bin of a decomposed system).  emdee_set_positions_range takes rows id_first.. of the 3xN array and
+ * fails if the window misses an atom the rank holds; the getters fill the rows of atoms this rank OWNS and zero the rest. */
+int emdee_get_local_id_range(emdee_system *sys, int64_t *id_first, int64_t *count);
+int emdee_set_positions_range(emdee_system *sys, int64_t id_first, int64_t count, const double *pos_3xcount);
+int emdee_get_forces_range(emdee_system *sys, int64_t id_first, int64_t count, double *forces_3xcount);
+int emdee_get_energies_range(emdee_system *sys, int64_t id_first, int64_t count, double *energies_count);
+int emdee_get_virials_range(emdee_system *sys, int64_t id_first, int64_t count, double *virials_count);
+
 /* Pair-set audit (the pair enumeration find_action_partners1! was heading to, src/cells.jl:224-297):
  * sorted (i<j) pairs for small N, or (count, sum hash, xor hash) with hash = splitmix64((i<<32)|j). */
 int emdee_pair_set(emdee_system *sys, int32_t *ij_2xcap, int64_t cap, int64_t *n);

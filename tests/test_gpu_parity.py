@@ -609,6 +609,11 @@ def test_state_invalidation(em, oracle, dioxin_water):
     s.pair_set_digest()
     s.totals()
     assert np.array_equal(s.forces(), f0)
+    # id windows of the host arrays (what slab ranks use to move only their own rows): one GPU holds every atom
+    assert s.local_id_range() == (0, N)
+    assert np.array_equal(s.forces_range(100, np.empty((50, 3))), f0[100:150])
+    with pytest.raises(em.EmDeeError):
+        s.set_positions_range(10, pos[10:N - 5])      # the window must cover every atom the rank holds
     with pytest.raises(em.EmDeeError):
         s.energies()                                  # the last compute selected FORCES only
     # larger cutoff: the old grid / list would miss pairs
