@@ -70,6 +70,7 @@ SIGNATURES = {
     "emdee_get_virials_range": [_p, _i64, _i64, _p],
     "emdee_set_skin": [_p, _d],
     "emdee_bin": [_p, _i],
+    "emdee_update_cells": [_p, C.POINTER(_i64)],
     "emdee_get_cells_per_dimension": [_p, C.POINTER(C.c_int32)],
     "emdee_get_cell_index": [_p, _p],
     "emdee_get_cell_population": [_p, _p],

@@ -202,6 +202,13 @@ class NonbondedSystem:
             raise ValueError("positions must hold N atoms")
         call("emdee_set_positions", self._h, _ptr(p))
 
+    def update_cells(self):
+        """Incremental form of update_cells! (src/cells.jl:196-222) after set_positions: returns the number of atoms whose cell
+        changed; 0 means the sorted order, the cell table (and, within skin/2, the pair list) were kept as they are."""
+        m = C.c_int64()
+        call("emdee_update_cells", self._h, C.byref(m))
+        return int(m.value)
+
     def local_id_range(self):
         """(first id, count): the smallest window of global ids covering every atom this rank holds (owned + ghosts)."""
         a, n = C.c_int64(), C.c_int64()
@@ -512,9 +519,14 @@ class Cells:
         self._sys.set_model(LennardJonesModel(self.cutoff, 0.5 * self.cutoff))
         self._refresh(p)
 
-    def _refresh(self, p):
+    def _refresh(self, p, incremental=False):
         self._sys.set_positions(p)
-        self._sys.bin(self.ndiv)
+        if incremental:
+            self.movers = self._sys.update_cells()      # atoms that changed cell (src/cells.jl:79-85); 0: nothing to relink
+            if self.movers == 0:
+                return
+        else:
+            self._sys.bin(self.ndiv)
         self.M = self._sys.cells_per_dimension()
         self.index = self._sys.cell_index()
         self.population = self._sys.cell_population()
@@ -559,10 +571,12 @@ class Cells:
 
 
 def update_cells_(cells, r, L):
-    """update_cells!(cells, r, L) -- src/cells.jl:196-222: re-bin after the atoms moved."""
+    """update_cells!(cells, r, L) -- src/cells.jl:196-222: re-bin after the atoms moved.  Incremental like the reference's: the
+    cell of every atom is recomputed on the device and only if some atom changed cell are the lists rebuilt
+    (cells.movers holds the count)."""
     if float(L) != cells._sys.L:
         raise ValueError("update_cells!: L differs from the box the cells were built for")
-    cells._refresh(_as_3xN(r, "r"))
+    cells._refresh(_as_3xN(r, "r"), incremental=True)
     return None
 
 

@@ -53,6 +53,33 @@ __global__ void k_cell_index(int64_t first, int64_t n, const double *__restrict_
     atomicAdd(count + lc, 1);
 }
 
+// update_cells! (src/cells.jl:196-222) starts by recomputing every atom's cell (clean_cells!, :79-85) and unlinking the atoms
+// whose cell changed: count those "movers" against the cell each atom was sorted into at the last binning, and track the
+// largest displacement since then (decides whether a pair list built with a skin is still valid).
+__global__ void k_count_movers(int64_t first, int64_t n, const double *__restrict__ sx, const double *__restrict__ sy,
+                               const double *__restrict__ sz, int M, const int32_t *__restrict__ gcell,
+                               const double *__restrict__ rx, const double *__restrict__ ry, const double *__restrict__ rz,
+                               const double *__restrict__ bx, const double *__restrict__ by, const double *__restrict__ bz,
+                               unsigned long long *__restrict__ movers, unsigned *__restrict__ maxd2)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int moved = 0;
+    unsigned d2b = 0;
+    if (k < n) {
+        const int64_t i = first + k;
+        const int x = cell_coord(sx[i], M), y = cell_coord(sy[i], M), z = cell_coord(sz[i], M);
+        moved = (x + M * (y + M * z)) != gcell[i];
+        const double dx = rx[i] - bx[i], dy = ry[i] - by[i], dz = rz[i] - bz[i];
+        d2b = __float_as_uint(__double2float_ru(fma(dz, dz, fma(dy, dy, dx * dx))));
+    }
+    const unsigned any = __ballot_sync(0xffffffffu, moved);
+    d2b = __reduce_max_sync(0xffffffffu, d2b);
+    if ((threadIdx.x & 31) == 0) {
+        if (any) atomicAdd(movers, (unsigned long long)__popc(any));
+        if (d2b > *maxd2) atomicMax(maxd2, d2b);
+    }
+}
+
 // ---- exclusive scan of int32 counts, three phases, warp-shuffle scans inside each block ----------
 #define SCAN_BLOCK 512
 #define SCAN_ITEMS 8

@@ -120,6 +120,7 @@ struct emdee_system {
     int64_t nlo = 0, nown = 0, nhi = 0;   // lower ghosts, owned, upper ghosts
     // cell grid
     bool binned = false, grid_ok = false;
+    bool order_valid = false;                 // slot order and gcell[] are those of a binning with the current cutoff, skin and ndiv
     int ndiv = 0;
     GridDesc g{};
     int64_t ncell = 0, ncell_cap = 0;
@@ -579,6 +580,7 @@ extern "C" int emdee_set_model(emdee_system *s, double cutoff, double sw)
     if (cutoff != s->cutoff) {     // the cell grid and the pair list were sized for the old cutoff (+ skin)
         s->binned = false;
         s->list_valid = false;
+        s->order_valid = false;
     }
     s->cutoff = cutoff;
     s->sw = sw;
@@ -596,6 +598,7 @@ extern "C" int emdee_set_skin(emdee_system *s, double skin)
     if (!(skin >= 0) || !std::isfinite(skin)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_skin: skin=%g must be >= 0", skin);
     s->skin = skin;
     s->binned = false;
+    s->order_valid = false;
     return EMDEE_OK;
 }
 
@@ -1147,6 +1150,7 @@ static int do_bin(emdee_system *s, int ndiv)
     EMDEE_TRY(check_launch("binning"));
     s->cur = 1 - s->cur;
     s->binned = true;
+    s->order_valid = true;
     s->steps_since_bin = 0;
     s->forces_valid = false;
     s->last_bitmask = 0;        // f / en / vir are in the previous slot order: the getters fail until the next compute
@@ -1441,6 +1445,39 @@ extern "C" int emdee_bin(emdee_system *s, int ndiv)
     if (ndiv < 1 || ndiv > 4) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_bin: ndiv=%d must be in [1,4]", ndiv);
     if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_bin: a velocity-Verlet step is half-finished");
     return c->nranks > 1 ? do_bin_slab(s, ndiv) : do_bin(s, ndiv);
+}
+
+// update_cells!(cells, r, L), src/cells.jl:196-222, after new positions were set: recompute every atom's cell; if no atom
+// changed cell the sorted order, the cell table and (while no atom has moved more than skin/2 since the binning) the pair
+// list stay as they are -- no sort, no gather, no list build; otherwise the movers are re-linked by a full (cell, id) re-sort
+// (atoms are stored densely in cell order, so one mover shifts everything behind it).  *movers: atoms whose cell changed.
+extern "C" int emdee_update_cells(emdee_system *s, int64_t *movers)
+{
+    SYS_ENTER(s, "emdee_update_cells");
+    if (!s->has_model || !s->has_pos) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_update_cells: set the model (cutoff) and positions first");
+    if (s->ndiv < 1) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_update_cells: call emdee_bin once first (it fixes ndiv)");
+    if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_update_cells: a velocity-Verlet step is half-finished");
+    if (movers) *movers = -1;
+    if (c->nranks > 1 || !s->order_valid) return emdee_bin(s, s->ndiv);          // slabs migrate atoms: always the full path
+    EMDEE_TRY(ensure_tmp(s, 16));
+    CUDA_TRY(cudaMemsetAsync(s->tmp, 0, 16, c->stream));
+    unsigned long long *dm = reinterpret_cast<unsigned long long *>(s->tmp);
+    unsigned *dd = reinterpret_cast<unsigned *>(dm + 1);
+    LAUNCH_1D(c, k_count_movers, s->nown, s->nlo, s->nown, A.s[0], A.s[1], A.s[2], s->g.M, s->gcell[s->cur], A.r[0], A.r[1], A.r[2],
+              A.rb[0], A.rb[1], A.rb[2], dm, dd);
+    unsigned long long h[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(h, s->tmp, 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    EMDEE_TRY(check_launch("k_count_movers"));
+    if (movers) *movers = (int64_t)h[0];
+    if (h[0] != 0) return do_bin(s, s->ndiv);
+    float d2;
+    const unsigned bits = (unsigned)(h[1] & 0xffffffffu);
+    memcpy(&d2, &bits, 4);
+    if ((double)d2 > 0.25 * s->skin * s->skin) s->list_valid = false;      // a list built with a skin holds only while atoms stay within skin/2
+    s->binned = true;
+    s->last_bitmask = 0;
+    return EMDEE_OK;
 }
 
 extern "C" int emdee_get_cells_per_dimension(emdee_system *s, int32_t *M)

@@ -88,6 +88,11 @@ int emdee_set_skin(emdee_system *sys, double skin);
  * M = floor(ndiv*L/(cutoff+skin)) (src/cells.jl:36), cell index of src/cells.jl:79-85, atoms sorted by
  * (cell, id).  Replaces distribute!/clean_cells!/collect_baskets!/renew_cells! (src/cells.jl:46-174). */
 int emdee_bin(emdee_system *sys, int ndiv);
+/* update_cells!(cells, r, L), src/cells.jl:196-222, incremental: after emdee_set_positions, recompute every atom's cell; if no
+ * atom changed cell, the sorted order and cell table are kept (and the pair list too while no atom has moved more than skin/2
+ * since the binning); otherwise the movers are re-linked by a full (cell, id) re-sort.  *movers = atoms whose cell changed
+ * (-1 when the full path was taken without counting: first use, new cutoff or skin, slab decomposition). */
+int emdee_update_cells(emdee_system *sys, int64_t *movers);
 int emdee_get_cells_per_dimension(emdee_system *sys, int32_t *M);
 int emdee_get_cell_index(emdee_system *sys, int32_t *index_N);           /* 1-based, id order (Cells.index) */
 int emdee_get_cell_population(emdee_system *sys, int32_t *pop_M3);       /* Cells.population */

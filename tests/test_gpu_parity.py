@@ -136,6 +136,19 @@ def test_cells_bit_exact(em, oracle, lj_sample, ndiv):
     fresh = em.Cells(y, 10.0, 3.0, ndiv=ndiv)
     assert np.array_equal(cells.index, fresh.index) and np.array_equal(cells.population, fresh.population)
     assert np.array_equal(cells.index, oracle.cell_index(y, 10.0, M))
+    # the update is incremental (src/cells.jl:196-222): the movers are exactly the atoms whose cell index changed ...
+    assert cells.movers == int((oracle.cell_index(y, 10.0, M) != idx).sum()) > 0
+    # ... and a displacement that moves no atom across a cell face relinks nothing and leaves every array as it is
+    idx_y = oracle.cell_index(y, 10.0, M)
+    edge = 10.0 / M
+    frac = np.mod(y, edge) / edge
+    room = np.minimum(frac, 1.0 - frac).min() * edge          # distance of the closest atom to a cell face
+    z = y + 0.25 * room
+    assert np.array_equal(oracle.cell_index(z, 10.0, M), idx_y)
+    perm_before = cells.perm.copy()
+    em.update_cells_(cells, z, 10.0)
+    assert cells.movers == 0 and np.array_equal(cells.perm, perm_before) and np.array_equal(cells.index, idx_y)
+    assert np.array_equal(cells._sys.cell_index(), idx_y) and np.array_equal(cells._sys.cell_order()[0], perm_before)
 
 
 def test_cell_index_edge_cases(em, oracle):
