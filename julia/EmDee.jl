@@ -105,6 +105,9 @@ set_masses!(s::NonbondedSystem, m::Vector{Float64}) =
     check(ccall((:emdee_set_masses, libemdee), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.handle, m))
 set_exclusions!(s::NonbondedSystem, base::Vector{Int32}, mask::Vector{UInt64}) =
     check(ccall((:emdee_set_exclusions, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{UInt64}), s.handle, base, mask))
+# lj14scale of the force field (src/modelling.jl:199): pairs three bonds apart, 0-based ids with i < j, 2 x n column-major
+set_pairs14!(s::NonbondedSystem, ij::Matrix{Int32}, scale::Real) =
+    check(ccall((:emdee_set_pairs14, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}, Int64, Cdouble), s.handle, ij, size(ij, 2), scale))
 set_skin!(s::NonbondedSystem, skin::Real) =
     check(ccall((:emdee_set_skin, libemdee), Cint, (Ptr{Cvoid}, Cdouble), s.handle, skin))
 set_tiles!(s::NonbondedSystem, tiles::Vector{Tuple{Int32,Int32}}) =
@@ -220,6 +223,33 @@ function Cells(r::Matrix{Float64}, L, cutoff; ndiv=2, num_threads=256)
     return refresh!(Cells(0, cutoff, ndiv, Int32[], Int32[], s), r)
 end
 
-update_cells!(cells::Cells, r::Matrix{Float64}, L) = (refresh!(cells, r); nothing)
+# update_cells!(cells, r, L), src/cells.jl:196-222: incremental -- the device counts the atoms whose cell changed and re-sorts
+# only if there are any; the host arrays are refreshed in that case only
+function update_cells!(cells::Cells, r::Matrix{Float64}, L)
+    s = cells.system
+    set_positions!(s, r)
+    movers = Ref{Int64}(0)
+    check(ccall((:emdee_update_cells, libemdee), Cint, (Ptr{Cvoid}, Ref{Int64}), s.handle, movers))
+    if movers[] != 0
+        check(ccall((:emdee_get_cell_index, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}), s.handle, cells.index))
+        check(ccall((:emdee_get_cell_population, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}), s.handle, cells.population))
+    end
+    return nothing
+end
+
+# Slab ranks (multi-GPU): move only the rows of the id-ordered host arrays that cover the atoms this rank holds
+function local_id_range(s::NonbondedSystem)
+    a = Ref{Int64}(0); n = Ref{Int64}(0)
+    check(ccall((:emdee_get_local_id_range, libemdee), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), s.handle, a, n))
+    return a[], n[]
+end
+set_positions_range!(s::NonbondedSystem, id_first::Integer, rows::Matrix{Float64}) =
+    check(ccall((:emdee_set_positions_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, size(rows, 2), rows))
+forces_range!(out::Matrix{Float64}, s::NonbondedSystem, id_first::Integer) =
+    check(ccall((:emdee_get_forces_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, size(out, 2), out))
+energies_range!(out::Vector{Float64}, s::NonbondedSystem, id_first::Integer) =
+    check(ccall((:emdee_get_energies_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, length(out), out))
+virials_range!(out::Vector{Float64}, s::NonbondedSystem, id_first::Integer) =
+    check(ccall((:emdee_get_virials_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, length(out), out))
 
 end
