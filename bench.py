@@ -550,9 +550,11 @@ def run_b200(args):
 
     # ---- e2e: host buffers in, host buffers out, through the C ABI ---------------------------------
     # One GPU: the whole arrays.  Slab ranks: every rank moves the window of the id-ordered host arrays that covers the atoms it
-    # holds (emdee_get_local_id_range: owned + ghosts; for these lattices ids run with z, so a window is about N/ranks rows)
-    # and receives the rows of the atoms it owns -- per call the ranks together move about what one GPU moves alone.
+    # owns (emdee_get_local_id_range; for these lattices ids run with z, so a window is about N/ranks rows) and receives the
+    # rows of those atoms -- per call the ranks together move about what one GPU moves alone.  The windows are those of the
+    # decomposition of the uploaded positions themselves (one untimed full-array call first).
     s.set_skin(0.0)
+    s.set_positions(w["pos"])
     s.bin(args.ndiv)
     id0, cnt = s.local_id_range() if world > 1 else (0, N)
     pos_h = torch.from_numpy(w["pos"][id0:id0 + cnt].copy()).pin_memory().numpy()
@@ -628,4 +630,12 @@ if __name__ == "__main__":
     if a.impl == "reference":
         run_reference(a)
     else:
-        run_b200(a)
+        try:
+            run_b200(a)
+        except BaseException:
+            # one failing rank must not leave the others waiting in a collective until the launcher's timeout
+            import traceback
+
+            traceback.print_exc()
+            sys.stderr.flush()
+            os._exit(1)

@@ -210,13 +210,13 @@ class NonbondedSystem:
         return int(m.value)
 
     def local_id_range(self):
-        """(first id, count): the smallest window of global ids covering every atom this rank holds (owned + ghosts)."""
+        """(first id, count): the smallest window of global ids covering every atom this rank owns."""
         a, n = C.c_int64(), C.c_int64()
         call("emdee_get_local_id_range", self._h, C.byref(a), C.byref(n))
         return int(a.value), int(n.value)
 
     def set_positions_range(self, id_first, rows):
-        """Rows id_first.. of the (N, 3) position array (a slab rank uploads only the atoms it holds)."""
+        """Rows id_first.. of the (N, 3) position array (a slab rank uploads only the atoms it owns; bin() refreshes the ghosts)."""
         p = np.ascontiguousarray(rows, dtype=np.float64)
         if p.ndim != 2 or p.shape[1] != 3:
             raise ValueError("rows must be (count, 3)")

@@ -675,11 +675,11 @@ extern "C" int emdee_get_local_id_range(emdee_system *s, int64_t *id_first, int6
 {
     SYS_ENTER(s, "emdee_get_local_id_range");
     if (!id_first || !count) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_local_id_range: null output");
-    if (ntot == s->N) { *id_first = 0; *count = s->N; return EMDEE_OK; }      // not decomposed (yet): every atom is here
+    if (s->nown == s->N) { *id_first = 0; *count = s->N; return EMDEE_OK; }   // not decomposed (yet): every atom is here
     EMDEE_TRY(ensure_tmp(s, 2 * sizeof(int)));
     const int init[2] = {0x7fffffff, -1};
     CUDA_TRY(cudaMemcpyAsync(s->tmp, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH_1D(c, k_id_range, ntot, ntot, A.id, reinterpret_cast<int *>(s->tmp));
+    LAUNCH_1D(c, k_id_range, s->nown, s->nlo, s->nown, A.id, reinterpret_cast<int *>(s->tmp));
     int lohi[2];
     CUDA_TRY(cudaMemcpyAsync(lohi, s->tmp, sizeof(lohi), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -694,14 +694,14 @@ extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int6
     if (!pos || id_first < 0 || count < 0 || id_first + count > s->N)
         EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: rows [%lld, %lld) of %lld", (long long)id_first, (long long)(id_first + count), (long long)s->N);
     EMDEE_TRY(upload(s, pos, sizeof(double) * 3 * count));
-    LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, A.id, id_first, count, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
+    LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, s->nlo, s->nlo + s->nown, A.id, id_first, count, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
     LAUNCH_1D(c, k_scale_positions, ntot, ntot, A.r[0], A.r[1], A.r[2], s->L, A.s[0], A.s[1], A.s[2]);
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     if (flag == 7) {
         CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
-        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: the window does not cover every atom this rank holds (emdee_get_local_id_range)");
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: the window does not cover every atom this rank owns (emdee_get_local_id_range)");
     }
     s->has_pos = true;
     s->binned = false;
@@ -1930,7 +1930,7 @@ static int check_device_flag(emdee_system *s, const char *where)
         if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its capacity (set EMDEE_LIST_CHUNKS higher or EMDEE_LIST=0)", where);
         if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
         if (flag == 6) EMDEE_FAIL(EMDEE_ERR_NCCL, "%s: a neighbouring rank never published its boundary atoms (peer-mapped halo timed out after ~2 s)", where);
-        if (flag == 7) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: a position window did not cover every atom this rank holds", where);
+        if (flag == 7) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: a position window did not cover every atom this rank owns", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
     }
     return EMDEE_OK;

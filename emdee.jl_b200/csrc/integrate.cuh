@@ -101,14 +101,20 @@ __global__ void k_get3(int64_t first, int64_t n, const int32_t *__restrict__ id,
     out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
 }
 // the same for a window [id0, id0 + n) of the id-ordered host array (slab ranks move only the rows of the atoms they hold)
-__global__ void k_set3_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, const double *__restrict__ in,
-                             double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2, int *__restrict__ err)
+// slots [own0, own1) are atoms the rank owns (the window must cover them); ghosts outside the window keep their values (the
+// next re-binning refreshes every ghost from its owner)
+__global__ void k_set3_range(int64_t first, int64_t cnt, int64_t own0, int64_t own1, const int32_t *__restrict__ id, int64_t id0, int64_t n,
+                             const double *__restrict__ in, double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
+                             int *__restrict__ err)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
     const int64_t i = first + k;
     const int64_t g = (int64_t)id[i] - id0;
-    if (g < 0 || g >= n) { atomicCAS(err, 0, 7); return; }
+    if (g < 0 || g >= n) {
+        if (i >= own0 && i < own1) atomicCAS(err, 0, 7);
+        return;
+    }
     d0[i] = in[3 * g]; d1[i] = in[3 * g + 1]; d2[i] = in[3 * g + 2];
 }
 __global__ void k_get3_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, const double *__restrict__ d0,
@@ -129,11 +135,11 @@ __global__ void k_get1_range(int64_t first, int64_t cnt, const int32_t *__restri
     const int64_t g = (int64_t)id[first + k] - id0;
     if (g >= 0 && g < n) out[g] = d[first + k];
 }
-// smallest and largest global id among slots [0, cnt)
-__global__ void k_id_range(int64_t cnt, const int32_t *__restrict__ id, int *__restrict__ lohi)
+// smallest and largest global id among slots [first, first + cnt)
+__global__ void k_id_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int *__restrict__ lohi)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int v = k < cnt ? id[k] : 0x7fffffff, w = k < cnt ? id[k] : -1;
+    int v = k < cnt ? id[first + k] : 0x7fffffff, w = k < cnt ? id[first + k] : -1;
     v = __reduce_min_sync(0xffffffffu, v);
     w = __reduce_max_sync(0xffffffffu, w);
     if ((threadIdx.x & 31) == 0) { atomicMin(lohi, v); atomicMax(lohi + 1, w); }

@@ -114,9 +114,10 @@ int emdee_get_virials(emdee_system *sys, double *virials_N);
 int emdee_get_totals(emdee_system *sys, double *E, double *W, int64_t *npairs);
 
 /* Windows of the id-ordered host arrays (additive; a slab rank then moves only the rows of the atoms it holds over PCIe instead
- * of all N): [*id_first, *id_first + *count) is the smallest id window covering every atom this rank holds (owned + ghosts; all
- * N before the first emdee_bin of a decomposed system).  emdee_set_positions_range takes rows id_first.. of the 3xN array and
- * fails if the window misses an atom the rank holds; the getters fill the rows of atoms this rank OWNS and zero the rest. */
+ * of all N): [*id_first, *id_first + *count) is the smallest id window covering every atom this rank owns (all N before the
+ * first emdee_bin of a decomposed system).  emdee_set_positions_range takes rows id_first.. of the 3xN array and fails if the
+ * window misses an atom the rank owns (ghosts outside the window are refreshed from their owners by the next emdee_bin, which
+ * the call makes mandatory anyway); the getters fill the rows of the atoms this rank owns and zero the rest. */
 int emdee_get_local_id_range(emdee_system *sys, int64_t *id_first, int64_t *count);
 int emdee_set_positions_range(emdee_system *sys, int64_t id_first, int64_t count, const double *pos_3xcount);
 int emdee_get_forces_range(emdee_system *sys, int64_t id_first, int64_t count, double *forces_3xcount);

@@ -790,5 +790,6 @@ def test_slab_decomposition_multi_gpu():
         env = dict(os.environ, SLAB_N=str(n), SLAB_NDIV=str(ndiv))
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
                               "--master-addr", "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "slab_worker.py")],
-                             env=env, capture_output=True, text=True, timeout=900)
+                             env=env, capture_output=True, text=True, timeout=280)
+        print(out.stdout[-2500:])          # the SLAB_RESULT line (errors against the oracle) goes to the test log either way
         assert out.returncode == 0 and "SLAB_RESULT" in out.stdout, out.stdout[-3000:] + out.stderr[-3000:]

@@ -1,11 +1,11 @@
 # Multi-GPU pass: slab-decomposition parity test (unless SKIP_TEST=1) and the scaling bench at N = $1 [$2 ...]
 cd /root/repo
 mkdir -p gpurun_out
-[ "$SKIP_TEST" = 1 ] || EMDEE_DEBUG=1 timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "slab" --timeout 500 2>&1 | tail -25 > gpurun_out/slab_test.log
-[ "$SKIP_TEST" = 1 ] || { grep -o "SLAB_RESULT.*" gpurun_out/slab_test.log | cut -c1-1500; tail -3 gpurun_out/slab_test.log; }
+[ "$SKIP_TEST" = 1 ] || EMDEE_DEBUG=1 timeout 400 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -s -k "slab" --timeout 300 > gpurun_out/slab_test.log 2>&1
+[ "$SKIP_TEST" = 1 ] || { grep -o "SLAB_RESULT.*" gpurun_out/slab_test.log | cut -c1-1800; grep "Error\|error:" gpurun_out/slab_test.log | head -5; tail -3 gpurun_out/slab_test.log; }
 for n in "$@"; do
   if [ $n = 1 ]; then timeout 300 python bench.py --gpus 1 --no-cpu-baseline $BENCH_ARGS > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err
-  else EMDEE_DEBUG=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --no-cpu-baseline $BENCH_ARGS > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err; fi
+  else EMDEE_DEBUG=1 timeout 180 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --no-cpu-baseline $BENCH_ARGS > gpurun_out/scale_$n.json 2> gpurun_out/scale_$n.err; fi
   grep "force kernel mode\|slab step\|peer-mapped\|status" gpurun_out/scale_$n.err | sort | uniq -c | head -12
   python -c "
 import json
