@@ -557,22 +557,22 @@ def run_b200(args):
     s.set_positions(w["pos"])
     s.bin(args.ndiv)
     id0, cnt = s.local_id_range() if world > 1 else (0, N)
-    pos_h = torch.from_numpy(w["pos"][id0:id0 + cnt].copy()).pin_memory().numpy()
-    f_h = torch.empty((cnt, 3), dtype=torch.float64).pin_memory().numpy()
-    e_h = torch.empty(cnt, dtype=torch.float64).pin_memory().numpy()
-    w_h = torch.empty(cnt, dtype=torch.float64).pin_memory().numpy()
+    pos_h = torch.from_numpy(w["pos"].copy()).pin_memory().numpy()           # full id-ordered host arrays, pinned; a slab rank
+    f_h = torch.empty((N, 3), dtype=torch.float64).pin_memory().numpy()      # touches only its window's rows of them
+    e_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
+    w_h = torch.empty(N, dtype=torch.float64).pin_memory().numpy()
 
     def e2e_once():
         if world > 1:
-            s.set_positions_range(id0, pos_h)
+            s.set_positions_range(id0, cnt, pos_h)
         else:
             s.set_positions(pos_h)
         s.bin(args.ndiv)
         s.compute(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS)
         if world > 1:
-            s.forces_range(id0, f_h)
-            s.energies_range(id0, e_h)
-            s.virials_range(id0, w_h)
+            s.forces_range(id0, cnt, f_h)
+            s.energies_range(id0, cnt, e_h)
+            s.virials_range(id0, cnt, w_h)
         else:
             s.forces(f_h)
             s.energies(e_h)
@@ -590,7 +590,7 @@ def run_b200(args):
     e2e = {"value": pairs_e2e / e2e_t, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(24 * rows),
            "d2h_bytes_per_step": int(40 * rows), "ms_per_call": e2e_t * 1e3, "atom_evals_per_s": N / e2e_t,
            "call": ("set_positions(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> forces/energies/virials(host)" if world == 1 else
-                    "per rank, on the id window of the atoms it holds: set_positions_range(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> "
+                    "per rank, on the cyclic id window of the atoms it owns: set_positions_range(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> "
                     "forces/energies/virials_range(host); bytes are summed over ranks")}
 
     cpu = None

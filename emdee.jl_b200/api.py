@@ -210,28 +210,36 @@ class NonbondedSystem:
         return int(m.value)
 
     def local_id_range(self):
-        """(first id, count): the smallest window of global ids covering every atom this rank owns."""
+        """(first id, count): the smallest cyclic window of global ids -- first, first+1, ... (mod N) -- covering every atom this
+        rank owns."""
         a, n = C.c_int64(), C.c_int64()
         call("emdee_get_local_id_range", self._h, C.byref(a), C.byref(n))
         return int(a.value), int(n.value)
 
-    def set_positions_range(self, id_first, rows):
-        """Rows id_first.. of the (N, 3) position array (a slab rank uploads only the atoms it owns; bin() refreshes the ghosts)."""
-        p = np.ascontiguousarray(rows, dtype=np.float64)
-        if p.ndim != 2 or p.shape[1] != 3:
-            raise ValueError("rows must be (count, 3)")
-        call("emdee_set_positions_range", self._h, int(id_first), p.shape[0], _ptr(p))
+    def set_positions_range(self, id_first, count, positions):
+        """Upload only rows id_first, ... (mod N), `count` of them, of the full (N, 3) position array (a slab rank moves the
+        rows of the atoms it owns; bin() refreshes the ghosts)."""
+        p = _as_3xN(positions, "positions")
+        if p.shape[0] != self.N:
+            raise ValueError("positions must hold N atoms")
+        call("emdee_set_positions_range", self._h, int(id_first), int(count), _ptr(p))
 
-    def forces_range(self, id_first, out):
-        call("emdee_get_forces_range", self._h, int(id_first), out.shape[0], _ptr(out))
+    def _range_out(self, out, shape):
+        if not (isinstance(out, np.ndarray) and out.dtype == np.float64 and out.flags.c_contiguous and out.shape == shape):
+            raise ValueError("out must be a C-contiguous float64 array of shape %r (the full id-ordered array)" % (shape,))
         return out
 
-    def energies_range(self, id_first, out):
-        call("emdee_get_energies_range", self._h, int(id_first), out.shape[0], _ptr(out))
+    def forces_range(self, id_first, count, out):
+        """Write the window's rows of the full (N, 3) array `out` (forces of the atoms this rank owns); other rows are untouched."""
+        call("emdee_get_forces_range", self._h, int(id_first), int(count), _ptr(self._range_out(out, (self.N, 3))))
         return out
 
-    def virials_range(self, id_first, out):
-        call("emdee_get_virials_range", self._h, int(id_first), out.shape[0], _ptr(out))
+    def energies_range(self, id_first, count, out):
+        call("emdee_get_energies_range", self._h, int(id_first), int(count), _ptr(self._range_out(out, (self.N,))))
+        return out
+
+    def virials_range(self, id_first, count, out):
+        call("emdee_get_virials_range", self._h, int(id_first), int(count), _ptr(self._range_out(out, (self.N,))))
         return out
 
     def set_velocities(self, velocities):

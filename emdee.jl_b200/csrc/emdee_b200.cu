@@ -670,31 +670,69 @@ extern "C" int emdee_set_positions(emdee_system *s, const double *pos)
     return check_launch("set_positions");
 }
 
-// ---- windows of the id-ordered host arrays: a slab rank moves only the rows of the atoms it holds ----------------------------
+// ---- cyclic windows of the id-ordered host arrays: a slab rank moves only the rows of the atoms it owns ----------------------
+#define ID_BUCKETS 4096
 extern "C" int emdee_get_local_id_range(emdee_system *s, int64_t *id_first, int64_t *count)
 {
     SYS_ENTER(s, "emdee_get_local_id_range");
     if (!id_first || !count) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_local_id_range: null output");
     if (s->nown == s->N) { *id_first = 0; *count = s->N; return EMDEE_OK; }   // not decomposed (yet): every atom is here
-    EMDEE_TRY(ensure_tmp(s, 2 * sizeof(int)));
-    const int init[2] = {0x7fffffff, -1};
-    CUDA_TRY(cudaMemcpyAsync(s->tmp, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH_1D(c, k_id_range, s->nown, s->nlo, s->nown, A.id, reinterpret_cast<int *>(s->tmp));
-    int lohi[2];
-    CUDA_TRY(cudaMemcpyAsync(lohi, s->tmp, sizeof(lohi), cudaMemcpyDeviceToHost, c->stream));
+    // occupancy of ID_BUCKETS equal id ranges; the window is the complement of the longest cyclic run of empty ones
+    EMDEE_TRY(ensure_tmp(s, ID_BUCKETS));
+    CUDA_TRY(cudaMemsetAsync(s->tmp, 0, ID_BUCKETS, c->stream));
+    LAUNCH_1D(c, k_id_buckets, s->nown, s->nlo, s->nown, A.id, s->N, ID_BUCKETS, reinterpret_cast<unsigned char *>(s->tmp));
+    unsigned char occ[ID_BUCKETS];
+    CUDA_TRY(cudaMemcpyAsync(occ, s->tmp, ID_BUCKETS, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *id_first = lohi[0];
-    *count = (int64_t)lohi[1] - lohi[0] + 1;
-    return check_launch("k_id_range");
+    EMDEE_TRY(check_launch("k_id_buckets"));
+    int best_len = 0, best_start = 0, run = 0;
+    for (int k = 0; k < 2 * ID_BUCKETS; k++) {          // twice around: runs that wrap
+        if (!occ[k % ID_BUCKETS]) {
+            if (++run > best_len && run <= ID_BUCKETS) { best_len = run; best_start = k - run + 1; }
+        } else
+            run = 0;
+    }
+    if (best_len >= ID_BUCKETS) { *id_first = 0; *count = 0; return EMDEE_OK; }     // owns nothing
+    const int b0 = (best_start + best_len) % ID_BUCKETS, nb = ID_BUCKETS - best_len;   // occupied arc: buckets b0 .. b0 + nb - 1 (cyclic)
+    // bucket k holds ids [ceil(k N / B), ceil((k+1) N / B))
+    auto lo_of = [&](int64_t k) { return (k * s->N + ID_BUCKETS - 1) / ID_BUCKETS; };
+    const int64_t first = lo_of(b0);
+    int64_t end = lo_of((int64_t)b0 + nb);             // may exceed N: the window wraps
+    if (b0 + nb > ID_BUCKETS) end = s->N + lo_of((int64_t)b0 + nb - ID_BUCKETS);
+    *id_first = first;
+    *count = std::min<int64_t>(end - first, s->N);
+    return EMDEE_OK;
+}
+
+// rows [id_first, id_first + count) (mod N) of a full id-ordered host array <-> `count` contiguous rows of the device scratch
+static int window_copy(emdee_system *s, void *host_full, int64_t id_first, int64_t count, size_t row_bytes, bool to_device)
+{
+    emdee_ctx *c = s->ctx;
+    char *h = reinterpret_cast<char *>(host_full), *d = reinterpret_cast<char *>(s->tmp);
+    const int64_t n1 = std::min(count, s->N - id_first), n2 = count - n1;
+    if (to_device) {
+        CUDA_TRY(cudaMemcpyAsync(d, h + id_first * row_bytes, n1 * row_bytes, cudaMemcpyHostToDevice, c->stream));
+        if (n2 > 0) CUDA_TRY(cudaMemcpyAsync(d + n1 * row_bytes, h, n2 * row_bytes, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CUDA_TRY(cudaMemcpyAsync(h + id_first * row_bytes, d, n1 * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (n2 > 0) CUDA_TRY(cudaMemcpyAsync(h, d + n1 * row_bytes, n2 * row_bytes, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return EMDEE_OK;
+}
+static int window_check(emdee_system *s, const void *p, int64_t id_first, int64_t count, const char *what)
+{
+    if (!p || id_first < 0 || id_first >= s->N || count < 0 || count > s->N)
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: window of %lld rows from row %lld of %lld", what, (long long)count, (long long)id_first, (long long)s->N);
+    return EMDEE_OK;
 }
 
 extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int64_t count, const double *pos)
 {
     SYS_ENTER(s, "emdee_set_positions_range");
-    if (!pos || id_first < 0 || count < 0 || id_first + count > s->N)
-        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: rows [%lld, %lld) of %lld", (long long)id_first, (long long)(id_first + count), (long long)s->N);
-    EMDEE_TRY(upload(s, pos, sizeof(double) * 3 * count));
-    LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, s->nlo, s->nlo + s->nown, A.id, id_first, count, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
+    EMDEE_TRY(window_check(s, pos, id_first, count, "emdee_set_positions_range"));
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * std::max<int64_t>(count, 1)));
+    EMDEE_TRY(window_copy(s, const_cast<double *>(pos), id_first, count, 3 * sizeof(double), true));
+    LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, s->nlo, s->nlo + s->nown, A.id, id_first, count, s->N, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
     LAUNCH_1D(c, k_scale_positions, ntot, ntot, A.r[0], A.r[1], A.r[2], s->L, A.s[0], A.s[1], A.s[2]);
     int flag = 0;
     CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
@@ -714,11 +752,11 @@ static int get3_range(emdee_system *s, double *const src[3], int64_t id_first, i
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
-    if (!out || id_first < 0 || count < 0 || id_first + count > s->N) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: bad window", what);
-    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * count));
+    EMDEE_TRY(window_check(s, out, id_first, count, what));
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * 3 * count, c->stream));
-    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, src[0], src[1], src[2], s->tmp);
-    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * 3 * count, cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src[0], src[1], src[2], s->tmp);
+    EMDEE_TRY(window_copy(s, out, id_first, count, 3 * sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);
 }
@@ -726,11 +764,11 @@ static int get1_range(emdee_system *s, const double *src, int64_t id_first, int6
 {
     emdee_ctx *c = s->ctx;
     AtomArrays &A = s->A[s->cur];
-    if (!out || id_first < 0 || count < 0 || id_first + count > s->N) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: bad window", what);
-    EMDEE_TRY(ensure_tmp(s, sizeof(double) * count));
+    EMDEE_TRY(window_check(s, out, id_first, count, what));
+    EMDEE_TRY(ensure_tmp(s, sizeof(double) * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * count, c->stream));
-    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, src, s->tmp);
-    CUDA_TRY(cudaMemcpyAsync(out, s->tmp, sizeof(double) * count, cudaMemcpyDeviceToHost, c->stream));
+    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src, s->tmp);
+    EMDEE_TRY(window_copy(s, out, id_first, count, sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);
 }

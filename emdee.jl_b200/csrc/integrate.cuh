@@ -100,49 +100,55 @@ __global__ void k_get3(int64_t first, int64_t n, const int32_t *__restrict__ id,
     const int64_t g = id[i];
     out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
 }
-// the same for a window [id0, id0 + n) of the id-ordered host array (slab ranks move only the rows of the atoms they hold)
-// slots [own0, own1) are atoms the rank owns (the window must cover them); ghosts outside the window keep their values (the
-// next re-binning refreshes every ghost from its owner)
+// The same for a CYCLIC window of the id-ordered host array: rows id0, id0+1, ... (mod N), n of them, held contiguously in
+// window order on the device side of the transfer.  Slab ranks move only the rows of the atoms they own; the window is cyclic
+// because the periodic box makes the first and the last slab own a few atoms from the other end of the id order.
+// Slots [own0, own1) are atoms the rank owns (the window must cover them); ghosts outside the window keep their values (the
+// next re-binning refreshes every ghost from its owner).
+__device__ __forceinline__ int64_t window_row(int32_t id, int64_t id0, int64_t N)
+{
+    int64_t g = (int64_t)id - id0;
+    return g < 0 ? g + N : g;
+}
 __global__ void k_set3_range(int64_t first, int64_t cnt, int64_t own0, int64_t own1, const int32_t *__restrict__ id, int64_t id0, int64_t n,
-                             const double *__restrict__ in, double *__restrict__ d0, double *__restrict__ d1, double *__restrict__ d2,
-                             int *__restrict__ err)
+                             int64_t N, const double *__restrict__ in, double *__restrict__ d0, double *__restrict__ d1,
+                             double *__restrict__ d2, int *__restrict__ err)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
     const int64_t i = first + k;
-    const int64_t g = (int64_t)id[i] - id0;
-    if (g < 0 || g >= n) {
+    const int64_t g = window_row(id[i], id0, N);
+    if (g >= n) {
         if (i >= own0 && i < own1) atomicCAS(err, 0, 7);
         return;
     }
     d0[i] = in[3 * g]; d1[i] = in[3 * g + 1]; d2[i] = in[3 * g + 2];
 }
-__global__ void k_get3_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, const double *__restrict__ d0,
-                             const double *__restrict__ d1, const double *__restrict__ d2, double *__restrict__ out)
-{
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= cnt) return;
-    const int64_t i = first + k;
-    const int64_t g = (int64_t)id[i] - id0;
-    if (g < 0 || g >= n) return;
-    out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
-}
-__global__ void k_get1_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, const double *__restrict__ d,
+__global__ void k_get3_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, int64_t N,
+                             const double *__restrict__ d0, const double *__restrict__ d1, const double *__restrict__ d2,
                              double *__restrict__ out)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= cnt) return;
-    const int64_t g = (int64_t)id[first + k] - id0;
-    if (g >= 0 && g < n) out[g] = d[first + k];
+    const int64_t i = first + k;
+    const int64_t g = window_row(id[i], id0, N);
+    if (g >= n) return;
+    out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
 }
-// smallest and largest global id among slots [first, first + cnt)
-__global__ void k_id_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int *__restrict__ lohi)
+__global__ void k_get1_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, int64_t N,
+                             const double *__restrict__ d, double *__restrict__ out)
 {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int v = k < cnt ? id[first + k] : 0x7fffffff, w = k < cnt ? id[first + k] : -1;
-    v = __reduce_min_sync(0xffffffffu, v);
-    w = __reduce_max_sync(0xffffffffu, w);
-    if ((threadIdx.x & 31) == 0) { atomicMin(lohi, v); atomicMax(lohi + 1, w); }
+    if (k >= cnt) return;
+    const int64_t g = window_row(id[first + k], id0, N);
+    if (g < n) out[g] = d[first + k];
+}
+// which of `nbuckets` equal id ranges hold an atom of slots [first, first + cnt)
+__global__ void k_id_buckets(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t N, int nbuckets, unsigned char *__restrict__ occupied)
+{
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= cnt) return;
+    occupied[(int64_t)id[first + k] * nbuckets / N] = 1;
 }
 
 template <typename T>

@@ -113,16 +113,19 @@ int emdee_get_virials(emdee_system *sys, double *virials_N);
 /* sum of per-atom energies / virials and the number of pairs in the set (this rank's atoms). */
 int emdee_get_totals(emdee_system *sys, double *E, double *W, int64_t *npairs);
 
-/* Windows of the id-ordered host arrays (additive; a slab rank then moves only the rows of the atoms it holds over PCIe instead
- * of all N): [*id_first, *id_first + *count) is the smallest id window covering every atom this rank owns (all N before the
- * first emdee_bin of a decomposed system).  emdee_set_positions_range takes rows id_first.. of the 3xN array and fails if the
- * window misses an atom the rank owns (ghosts outside the window are refreshed from their owners by the next emdee_bin, which
- * the call makes mandatory anyway); the getters fill the rows of the atoms this rank owns and zero the rest. */
+/* Cyclic windows of the id-ordered host arrays (additive; a slab rank then moves only the rows of the atoms it owns over PCIe
+ * instead of all N): rows *id_first, *id_first + 1, ... (mod N), *count of them, are the smallest such window covering every
+ * atom this rank owns, to 1/4096 of N (all N before the first emdee_bin of a decomposed system; cyclic because the periodic box
+ * makes the first and last slab own a few atoms from the other end of the id order).  The *_range calls take the FULL 3xN / N
+ * host array and touch only the window's rows: emdee_set_positions_range uploads them and fails if the window misses an atom
+ * the rank owns (ghosts outside it are refreshed from their owners by the next emdee_bin, which the call makes mandatory
+ * anyway); the getters write the rows of the atoms this rank owns (zeros for other rows of the window) and leave the rest of
+ * the array alone. */
 int emdee_get_local_id_range(emdee_system *sys, int64_t *id_first, int64_t *count);
-int emdee_set_positions_range(emdee_system *sys, int64_t id_first, int64_t count, const double *pos_3xcount);
-int emdee_get_forces_range(emdee_system *sys, int64_t id_first, int64_t count, double *forces_3xcount);
-int emdee_get_energies_range(emdee_system *sys, int64_t id_first, int64_t count, double *energies_count);
-int emdee_get_virials_range(emdee_system *sys, int64_t id_first, int64_t count, double *virials_count);
+int emdee_set_positions_range(emdee_system *sys, int64_t id_first, int64_t count, const double *pos_3xN);
+int emdee_get_forces_range(emdee_system *sys, int64_t id_first, int64_t count, double *forces_3xN);
+int emdee_get_energies_range(emdee_system *sys, int64_t id_first, int64_t count, double *energies_N);
+int emdee_get_virials_range(emdee_system *sys, int64_t id_first, int64_t count, double *virials_N);
 
 /* Pair-set audit (the pair enumeration find_action_partners1! was heading to, src/cells.jl:224-297):
  * sorted (i<j) pairs for small N, or (count, sum hash, xor hash) with hash = splitmix64((i<<32)|j). */

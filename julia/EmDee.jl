@@ -237,11 +237,22 @@ function update_cells!(cells::Cells, r::Matrix{Float64}, L)
     return nothing
 end
 
-# Slab ranks (multi-GPU): move only the rows of the id-ordered host arrays that cover the atoms this rank holds
+# Slab ranks (multi-GPU): move only the rows of the full id-ordered host arrays that belong to atoms this rank owns -- a cyclic
+# window first, first+1, ... (mod N) of `count` rows; the arrays passed are the FULL 3xN / N arrays
 function local_id_range(s::NonbondedSystem)
     a = Ref{Int64}(0); n = Ref{Int64}(0)
     check(ccall((:emdee_get_local_id_range, libemdee), Cint, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), s.handle, a, n))
     return a[], n[]
+end
+set_positions_range!(s::NonbondedSystem, id_first::Integer, count::Integer, r::Matrix{Float64}) =
+    check(ccall((:emdee_set_positions_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, count, r))
+forces_range!(out::Matrix{Float64}, s::NonbondedSystem, id_first::Integer, count::Integer) =
+    check(ccall((:emdee_get_forces_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, count, out))
+energies_range!(out::Vector{Float64}, s::NonbondedSystem, id_first::Integer, count::Integer) =
+    check(ccall((:emdee_get_energies_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, count, out))
+virials_range!(out::Vector{Float64}, s::NonbondedSystem, id_first::Integer, count::Integer) =
+    check(ccall((:emdee_get_virials_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, count, out))
+
 end
 set_positions_range!(s::NonbondedSystem, id_first::Integer, rows::Matrix{Float64}) =
     check(ccall((:emdee_set_positions_range, libemdee), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Cdouble}), s.handle, id_first, size(rows, 2), rows))

@@ -624,9 +624,11 @@ def test_state_invalidation(em, oracle, dioxin_water):
     assert np.array_equal(s.forces(), f0)
     # id windows of the host arrays (what slab ranks use to move only their own rows): one GPU holds every atom
     assert s.local_id_range() == (0, N)
-    assert np.array_equal(s.forces_range(100, np.empty((50, 3))), f0[100:150])
+    buf = np.full((N, 3), 77.0)
+    s.forces_range(N - 10, 30, buf)                    # cyclic: rows N-10 .. N-1 and 0 .. 19 of the full array
+    assert np.array_equal(buf[N - 10:], f0[N - 10:]) and np.array_equal(buf[:20], f0[:20]) and np.all(buf[20:N - 10] == 77.0)
     with pytest.raises(em.EmDeeError):
-        s.set_positions_range(10, pos[10:N - 5])      # the window must cover every atom the rank holds
+        s.set_positions_range(10, N - 15, pos)         # the window must cover every atom the rank owns
     with pytest.raises(em.EmDeeError):
         s.energies()                                  # the last compute selected FORCES only
     # larger cutoff: the old grid / list would miss pairs
