@@ -1071,7 +1071,9 @@ static int choose_bricks(emdee_system *s)
                 // 1.31 ms for 11-12), plus ~2.5 % per staged cell per home cell for the producers' staging
                 const double groups = std::ceil(1.03 * home / 32.0);
                 const double fill = groups / (std::ceil(groups / FLP_NCONS) * FLP_NCONS);
-                const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
+                // bricks that stick out of the grid (a slab of 7 planes cut into layers of 2) stage a full halo for fewer home atoms
+                const double whole = ((double)g.M / (g.nbx * g.bx)) * ((double)g.M / (g.nby * g.by)) * ((double)g.nzhome / (g.nbz * g.bz));
+                const double score = 1e6 + 1000.0 * whole / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
                 if (score > best_score) {
                     best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
