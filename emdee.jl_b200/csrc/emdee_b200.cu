@@ -726,6 +726,20 @@ static int window_check(emdee_system *s, const void *p, int64_t id_first, int64_
     return EMDEE_OK;
 }
 
+// an owned atom outside the caller's window (device flag 7): the window is stale -- ownership changes at every re-binning
+static int window_flag(emdee_system *s, const char *what)
+{
+    emdee_ctx *c = s->ctx;
+    int flag = 0;
+    CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    if (flag == 7) {
+        CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: the window does not cover every atom this rank owns (ask emdee_get_local_id_range again after a re-binning)", what);
+    }
+    return EMDEE_OK;
+}
+
 extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int64_t count, const double *pos)
 {
     SYS_ENTER(s, "emdee_set_positions_range");
@@ -734,13 +748,7 @@ extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int6
     EMDEE_TRY(window_copy(s, const_cast<double *>(pos), id_first, count, 3 * sizeof(double), true));
     LAUNCH_1D(c, k_set3_range, ntot, 0, ntot, s->nlo, s->nlo + s->nown, A.id, id_first, count, s->N, s->tmp, A.r[0], A.r[1], A.r[2], s->err);
     LAUNCH_1D(c, k_scale_positions, ntot, ntot, A.r[0], A.r[1], A.r[2], s->L, A.s[0], A.s[1], A.s[2]);
-    int flag = 0;
-    CUDA_TRY(cudaMemcpyAsync(&flag, s->err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CUDA_TRY(cudaStreamSynchronize(c->stream));
-    if (flag == 7) {
-        CUDA_TRY(cudaMemsetAsync(s->err, 0, sizeof(int), c->stream));
-        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_set_positions_range: the window does not cover every atom this rank owns (emdee_get_local_id_range)");
-    }
+    EMDEE_TRY(window_flag(s, "emdee_set_positions_range"));
     s->has_pos = true;
     s->binned = false;
     s->forces_valid = false;
@@ -755,7 +763,8 @@ static int get3_range(emdee_system *s, double *const src[3], int64_t id_first, i
     EMDEE_TRY(window_check(s, out, id_first, count, what));
     EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * 3 * count, c->stream));
-    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src[0], src[1], src[2], s->tmp);
+    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src[0], src[1], src[2], s->tmp, s->err);
+    EMDEE_TRY(window_flag(s, what));
     EMDEE_TRY(window_copy(s, out, id_first, count, 3 * sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);
@@ -767,7 +776,8 @@ static int get1_range(emdee_system *s, const double *src, int64_t id_first, int6
     EMDEE_TRY(window_check(s, out, id_first, count, what));
     EMDEE_TRY(ensure_tmp(s, sizeof(double) * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * count, c->stream));
-    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src, s->tmp);
+    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src, s->tmp, s->err);
+    EMDEE_TRY(window_flag(s, what));
     EMDEE_TRY(window_copy(s, out, id_first, count, sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);
@@ -1071,9 +1081,9 @@ static int choose_bricks(emdee_system *s)
                 // 1.31 ms for 11-12), plus ~2.5 % per staged cell per home cell for the producers' staging
                 const double groups = std::ceil(1.03 * home / 32.0);
                 const double fill = groups / (std::ceil(groups / FLP_NCONS) * FLP_NCONS);
-                // bricks that stick out of the grid (a slab of 7 planes cut into layers of 2) stage a full halo for fewer home atoms
-                const double whole = ((double)g.M / (g.nbx * g.bx)) * ((double)g.M / (g.nby * g.by)) * ((double)g.nzhome / (g.nbz * g.bz));
-                const double score = 1e6 + 1000.0 * whole / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
+                // (a factor for bricks that stick out of the grid -- a slab of 7 planes cut into layers of 2 -- was tried at 8 GPUs: it
+                // picks 4x4x1 bricks there, 0.252 ms per launch against 0.240 ms for 4x2x2 with a half-filled last layer: not kept)
+                const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
                 if (score > best_score) {
                     best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;

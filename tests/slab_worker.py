@@ -92,22 +92,34 @@ def main():
     res["vv_list_pairs"] = [int(allsum(np.array([npl], dtype=np.int64))[0]), int(ref1["npairs"])]
     nloc2, _ = s.local_count()
     res["nlocal_sum_after"] = int(allsum(np.array([nloc2], dtype=np.int64))[0])
-    # id windows: every rank uploads only the rows of the atoms it holds and downloads the rows of the atoms it owns
+    # the same single point through the full-array calls (set_positions / forces / energies) ...
+    s.set_positions(p1)
+    s.bin(ndiv)
+    s.compute(em.CUTOFF, 7)
+    ff = allsum(s.forces()); ef = allsum(s.energies())
+    res["full_force_err"] = float(np.abs(ff - ref1["forces"]).max() / np.sqrt((ref1["forces"] ** 2).sum(1).mean()))
+    res["full_E_err"] = float(abs(ef.sum() - ref1["E"]) / abs(ref1["E"]))
+    # ... and through the id windows: every rank uploads only the rows of the atoms it owns and downloads those rows
     lo, cnt = s.local_id_range()
     res["id_window_rows_sum"] = int(allsum(np.array([cnt], dtype=np.int64))[0])
     s.set_positions_range(lo, cnt, p1)
     s.bin(ndiv)
     s.compute(em.CUTOFF, 7)
+    lo, cnt = s.local_id_range()         # ownership is that of the new binning
     fw = np.zeros((N, 3)); ew = np.zeros(N)
     s.forces_range(lo, cnt, fw)          # only the window's rows of the full arrays are written
     s.energies_range(lo, cnt, ew)
+    res["window"] = [int(lo), int(cnt)]
     fw = allsum(fw); ew = allsum(ew)
+    bad = np.nonzero(np.abs(fw - ref1["forces"]).max(axis=1) > 1e-6)[0]
+    res["window_bad_rows"] = [int(bad.size)] + bad[:8].tolist()
     res["window_force_err"] = float(np.abs(fw - ref1["forces"]).max() / np.sqrt((ref1["forces"] ** 2).sum(1).mean()))
     res["window_E_err"] = float(abs(ew.sum() - ref1["E"]) / abs(ref1["E"]))
     ok = (res["nlocal_sum"] == N and res["nlocal_sum_after"] == N and res["force_err"] <= 1e-9 and res["E_err"] <= 1e-10
           and res["W_err"] <= 1e-10 and res["pairs"][0] == res["pairs"][1] and res["digest_sum_ok"] and res["cell_index_ok"]
           and res["vv_pos_err"] <= 1e-10 and res["vv_vel_err"] <= 1e-9 and res["vv_force_err"] <= 1e-8
           and res["vv_force_err_same_positions"] <= 1e-9 and res["window_force_err"] <= 1e-9 and res["window_E_err"] <= 1e-10
+          and res["full_force_err"] <= 1e-9 and res["full_E_err"] <= 1e-10
           and res["id_window_rows_sum"] < 1.25 * N
           and abs(res["vv_list_pairs"][0] - res["vv_list_pairs"][1]) <= world)      # every rank halves its own ordered-pair count
     res["ok"] = bool(ok)
