@@ -9,6 +9,19 @@
 
 #define EMDEE_WARP 32
 
+// -DEMDEE_CHECKS=1: explicit bounds checks on the hand-rolled shared-memory structures of the list kernels (staged indices,
+// per-lane stacks and rows, task indices); a violation raises device flag 8, which the next getter / emdee_synchronize reports.
+// compute-sanitizer is not available on the GPU pool this library is developed on; the GPU tests are run against a library
+// built this way instead (tools/gpu_checked.sh).  Off by default: the checks cost instructions in the hot loops.
+#ifndef EMDEE_CHECKS
+#define EMDEE_CHECKS 0
+#endif
+#if EMDEE_CHECKS
+#define EMDEE_CHECK(cond, errptr) do { if (!(cond)) atomicCAS((errptr), 0, 8); } while (0)
+#else
+#define EMDEE_CHECK(cond, errptr) do { } while (0)
+#endif
+
 // ---- error handling: thread-local message + status code -------------------------------------
 void emdee_set_error(const char *fmt, ...);
 #define CUDA_TRY(expr)                                                                              \

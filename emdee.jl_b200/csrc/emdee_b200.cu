@@ -1979,6 +1979,7 @@ static int check_device_flag(emdee_system *s, const char *where)
         if (flag == 2) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: a brick overflowed its shared-memory staging area", where);
         if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its capacity (set EMDEE_LIST_CHUNKS higher or EMDEE_LIST=0)", where);
         if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
+        if (flag == 8) EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an internal bounds check of the list kernels failed (library built with -DEMDEE_CHECKS=1)", where);
         if (flag == 6) EMDEE_FAIL(EMDEE_ERR_NCCL, "%s: a neighbouring rank never published its boundary atoms (peer-mapped halo timed out after ~2 s)", where);
         if (flag == 7) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: a position window did not cover every atom this rank owns", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);

@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
         int cxi = R;
         while (cs[hrow * sxn + cxi + 1] <= me) cxi++;
         const int slot_i = gbase[hrow * sxn + cxi] + (me - cs[hrow * sxn + cxi]);
+        EMDEE_CHECK(me >= 1 && me < scal[1] && hr < nhy * nhz && cxi < sxn, a.err);
         const double2 q0 = pxy[me];
         const double pix = q0.x, piy = q0.y, piz = pz[me];
         const uint2 hme = ph[me];
@@ -304,7 +305,10 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
             const __half2 dxy = __hsub2(*reinterpret_cast<const __half2 *>(&hj.x), ixy);
             const __half2 dzw = __hsub2(*reinterpret_cast<const __half2 *>(&hj.y), izw);
             const __half2 s = __hfma2(dzw, dzw, __hmul2(dxy, dxy));
-            if (__hle(__hadd(__low2half(s), __high2half(s)), thr)) { *qp = (uint16_t)j; qp += BLOCK; cnt++; }
+            if (__hle(__hadd(__low2half(s), __high2half(s)), thr)) {
+                EMDEE_CHECK(cnt < FL_QCAP, a.err);
+                *qp = (uint16_t)j; qp += BLOCK; cnt++;
+            }
         };
 
         for (int c = 0; c < nchmax; c++) {
@@ -313,6 +317,7 @@ __global__ void __launch_bounds__(ILP == 8 ? 192 : FL_MAX_BLOCK, 2) k_force_list
             if (c + 2 + FL_AHEAD < nch) prefetch_l2(lp + (size_t)(c + 2 + FL_AHEAD) * 32);
             const unsigned j0 = e0.x & 0xffffu, j1 = e0.x >> 16, j2 = e0.y & 0xffffu, j3 = e0.y >> 16;
             const unsigned j4 = e0.z & 0xffffu, j5 = e0.z >> 16, j6 = e0.w & 0xffffu, j7 = e0.w >> 16;
+            EMDEE_CHECK((int)max(max(max(j0, j1), max(j2, j3)), max(max(j4, j5), max(j6, j7))) < scal[1], a.err);
             // the eight gathers are issued together, ahead of the stack stores they must not be reordered with
             const uint2 h0 = ph[j0], h1 = ph[j1], h2 = ph[j2], h3 = ph[j3], h4 = ph[j4], h5 = ph[j5], h6 = ph[j6], h7 = ph[j7];
             test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);

@@ -470,6 +470,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             const bool active = h < nh;
             const int hh = active ? h : (grp << 5);
             const int me = a.homeidx[((size_t)bid * a.gmax + grp) * 32 + (hh & 31)];
+            EMDEE_CHECK(me >= 1 && me < B.scal[1] && pre_n <= a.lcap8 * 8 && grp < a.gmax, a.err);
             const int slot_i = recipe[me].x;
             const double2 q0 = pxy[me];
             const double pix = q0.x, piy = q0.y, piz = pz[me];
@@ -534,7 +535,10 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 const __half2 dxy = __hsub2(*reinterpret_cast<const __half2 *>(&hj.x), ixy);
                 const __half2 dzw = __hsub2(*reinterpret_cast<const __half2 *>(&hj.y), izw);
                 const __half2 s = __hfma2(dzw, dzw, __hmul2(dxy, dxy));
-                if (__hle(__hadd(__low2half(s), __high2half(s)), thr)) { *qp = (uint16_t)j; qp += FLP_QS; cnt++; }
+                if (__hle(__hadd(__low2half(s), __high2half(s)), thr)) {
+                    EMDEE_CHECK(cnt < QCAP, a.err);
+                    *qp = (uint16_t)j; qp += FLP_QS; cnt++;
+                }
             };
 
             for (int c = 0; c < nchmax; c++) {
@@ -542,6 +546,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 if (c + 2 + FL_AHEAD < nch) prefetch_l2(lp + (size_t)(c + 2 + FL_AHEAD) * 32);
                 const unsigned j0 = e0.x & 0xffffu, j1 = e0.x >> 16, j2 = e0.y & 0xffffu, j3 = e0.y >> 16;
                 const unsigned j4 = e0.z & 0xffffu, j5 = e0.z >> 16, j6 = e0.w & 0xffffu, j7 = e0.w >> 16;
+                EMDEE_CHECK((int)max(max(max(j0, j1), max(j2, j3)), max(max(j4, j5), max(j6, j7))) < B.scal[1], a.err);
                 const uint2 h0 = ph[j0], h1 = ph[j1], h2 = ph[j2], h3 = ph[j3], h4 = ph[j4], h5 = ph[j5], h6 = ph[j6], h7 = ph[j7];
                 if (FUSE && c > 0) {
                     // pop ILP entries (an empty stack yields the dummy atom) and fetch their coordinates before anything is

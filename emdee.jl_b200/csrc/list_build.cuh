@@ -187,6 +187,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
             xb = a.xbase[slot_i]; xm = a.xmask[slot_i];
         }
         const int h = hstart[hr] + (me - cs[hrow * sxn + R]);
+        EMDEE_CHECK(hr < nhy * nhz && me < nstaged && a0 >= cs[hrow * sxn + R] && cxb < sxn, a.err);
         if ((h >> 5) >= a.gmax) { atomicCAS(a.err, 0, 5); break; }
         const size_t gs = (size_t)bid * a.gmax + (h >> 5);
         uint4 *lp = a.list8 + gs * a.lcap8 * 32 + (h & 31);
@@ -233,6 +234,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
             asm volatile("" ::: "memory");
         };
         auto push = [&](bool take, unsigned value) {
+            EMDEE_CHECK(!take || ((int)(wsh - row_sh) < 2 * LB_ROW_ENTRIES && (int)value >= 1 && (int)value <= nstaged), a.err);
             asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p st.shared.u16 [%0], %1; }" ::"r"(wsh), "h"((unsigned short)value), "r"((unsigned)take));
             wsh += take ? 2u : 0u;
         };
