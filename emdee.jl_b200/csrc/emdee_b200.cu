@@ -763,8 +763,8 @@ static int get3_range(emdee_system *s, double *const src[3], int64_t id_first, i
     EMDEE_TRY(window_check(s, out, id_first, count, what));
     EMDEE_TRY(ensure_tmp(s, sizeof(double) * 3 * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * 3 * count, c->stream));
-    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src[0], src[1], src[2], s->tmp, s->err);
-    EMDEE_TRY(window_flag(s, what));
+    LAUNCH_1D(c, k_get3_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src[0], src[1], src[2], s->tmp, c->nranks > 1 ? s->err : nullptr);
+    if (c->nranks > 1) EMDEE_TRY(window_flag(s, what));
     EMDEE_TRY(window_copy(s, out, id_first, count, 3 * sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);
@@ -776,8 +776,8 @@ static int get1_range(emdee_system *s, const double *src, int64_t id_first, int6
     EMDEE_TRY(window_check(s, out, id_first, count, what));
     EMDEE_TRY(ensure_tmp(s, sizeof(double) * std::max<int64_t>(count, 1)));
     CUDA_TRY(cudaMemsetAsync(s->tmp, 0, sizeof(double) * count, c->stream));
-    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src, s->tmp, s->err);
-    EMDEE_TRY(window_flag(s, what));
+    LAUNCH_1D(c, k_get1_range, s->nown, s->nlo, s->nown, A.id, id_first, count, s->N, src, s->tmp, c->nranks > 1 ? s->err : nullptr);
+    if (c->nranks > 1) EMDEE_TRY(window_flag(s, what));
     EMDEE_TRY(window_copy(s, out, id_first, count, sizeof(double), false));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     return check_launch(what);

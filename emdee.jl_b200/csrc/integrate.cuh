@@ -132,7 +132,10 @@ __global__ void k_get3_range(int64_t first, int64_t cnt, const int32_t *__restri
     if (k >= cnt) return;
     const int64_t i = first + k;
     const int64_t g = window_row(id[i], id0, N);
-    if (g >= n) { atomicCAS(err, 0, 7); return; }      // an owned atom outside the window: its row would be silently missing
+    if (g >= n) {      // slab rank (err != null): an owned atom outside the window means a stale window, its row would be silently missing
+        if (err) atomicCAS(err, 0, 7);
+        return;
+    }
     out[3 * g] = d0[i]; out[3 * g + 1] = d1[i]; out[3 * g + 2] = d2[i];
 }
 __global__ void k_get1_range(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t id0, int64_t n, int64_t N,
@@ -142,7 +145,7 @@ __global__ void k_get1_range(int64_t first, int64_t cnt, const int32_t *__restri
     if (k >= cnt) return;
     const int64_t g = window_row(id[first + k], id0, N);
     if (g < n) out[g] = d[first + k];
-    else atomicCAS(err, 0, 7);
+    else if (err) atomicCAS(err, 0, 7);
 }
 // which of `nbuckets` equal id ranges hold an atom of slots [first, first + cnt)
 __global__ void k_id_buckets(int64_t first, int64_t cnt, const int32_t *__restrict__ id, int64_t N, int nbuckets, unsigned char *__restrict__ occupied)

@@ -120,8 +120,8 @@ int emdee_get_totals(emdee_system *sys, double *E, double *W, int64_t *npairs);
  * host array and touch only the window's rows: emdee_set_positions_range uploads them and fails if the window misses an atom
  * the rank owns (ghosts outside it are refreshed from their owners by the next emdee_bin, which the call makes mandatory
  * anyway); the getters write the rows of the atoms this rank owns (zeros for other rows of the window), leave the rest of
- * the array alone, and fail likewise if an owned atom lies outside the window -- ownership changes at every emdee_bin, so ask
- * for the window again after it. */
+ * the array alone, and on a slab rank fail likewise if an owned atom lies outside the window -- ownership changes at every
+ * emdee_bin, so ask for the window again after it (one GPU owns every atom: any window of rows may be read there). */
 int emdee_get_local_id_range(emdee_system *sys, int64_t *id_first, int64_t *count);
 int emdee_set_positions_range(emdee_system *sys, int64_t id_first, int64_t count, const double *pos_3xN);
 int emdee_get_forces_range(emdee_system *sys, int64_t id_first, int64_t count, double *forces_3xN);

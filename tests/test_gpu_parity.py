@@ -788,6 +788,9 @@ def test_slab_decomposition_multi_gpu():
         cases.append((4, 2, 16))
     if ngpu >= 8:
         cases.append((8, 1, 40))              # N = 256,000: M = 22 planes over 8 ranks
+    only = os.environ.get("SLAB_WORLDS")      # e.g. SLAB_WORLDS=8: run that case alone (an 8-GPU box is charged 8x)
+    if only:
+        cases = [c for c in cases if str(c[0]) in only.split(",")]
     for world, ndiv, n in cases:
         env = dict(os.environ, SLAB_N=str(n), SLAB_NDIV=str(ndiv))
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
