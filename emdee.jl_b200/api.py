@@ -350,7 +350,7 @@ class NonbondedSystem:
         o = np.zeros(8, dtype=np.int32)
         call("emdee_get_step_config", self._h, _ptr(o))
         return dict(brick=(int(o[0]), int(o[1]), int(o[2])), brick_capacity=int(o[3]), pair_list=bool(o[4]),
-                    persistent=bool(o[5]), fused_vv=bool(o[6]), list_chunks=int(o[7]))
+                    persistent=bool(o[5] & 1), tma=bool(o[5] & 2), fused_vv=bool(o[6]), list_chunks=int(o[7]))
 
     def scale_velocities(self, factor):
         call("emdee_scale_velocities", self._h, float(factor))

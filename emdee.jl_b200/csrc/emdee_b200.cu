@@ -194,6 +194,12 @@ struct emdee_system {
     // Newton's third law inside the brick (EMDEE_N3=1, fused velocity-Verlet steps only): the list then holds every pair of
     // two home atoms once; the other list kernels need the full list, so the flavour of the valid list is tracked
     bool want_n3 = false, list_n3 = false, build_n3 = false;
+    // TMA staging of the persistent kernel (opt-in, EMDEE_TMA=1; the default is the recipe gathers, which measure faster:
+    // profiles/README.md): per-brick segment table written by k_list_build, raw ring sized from the longest staged row
+    bool want_tma = false, fl_tma = false;
+    int4 *seg = nullptr;
+    int64_t seg_cap_total = 0;
+    int segcap = 0, raw_rows = 0, rawlen = 0, fc_rowmax = 0, pre_rowmax = 0;
     size_t fc_smem_budget = 0;
     size_t fc_smem = 0;
     double2 *ljtab = nullptr;                 // pair table of the LJ parameter classes
@@ -432,7 +438,7 @@ static int alloc_atoms(AtomArrays &A, int64_t cap)
 {
     for (int c = 0; c < 3; c++) {
         EMDEE_TRY(dev_alloc(&A.r[c], cap));
-        EMDEE_TRY(dev_alloc(&A.s[c], cap));
+        EMDEE_TRY(dev_alloc(&A.s[c], cap + 2));       // bulk copies round a row up to an even number of slots
         EMDEE_TRY(dev_alloc(&A.v[c], cap));
         EMDEE_TRY(dev_alloc(&A.rb[c], cap));
     }
@@ -469,6 +475,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_FUSE")) s->fl_fuse = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_FUSE_VV")) s->fuse_vv = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_N3")) s->want_n3 = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_TMA")) s->want_tma = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -488,7 +495,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->digest, 16));        // [0..3] audit digest + pair counter, [8..15] role timers of FLP_TIMING builds
     A(dev_alloc(&s->err, 1));
     A(dev_alloc(&s->maxpop, 1));
-    A(dev_alloc(&s->brick_max, 1));
+    A(dev_alloc(&s->brick_max, 2));         // staged atoms of the fullest brick, atoms of the longest staged row
     if (c->nranks > 1 && st == EMDEE_OK) {
         for (int b = 0; b < 2; b++)
             for (int k = 0; k < 3; k++) dev_free(s->A[b].s[k]);
@@ -556,6 +563,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     for (int k = 0; k < 4; k++) dev_free(s->migbuf[k]);
     for (int k = 0; k < 4; k++) dev_free(s->ghostbuf[k]);
     dev_free(s->pairs14);
+    dev_free(s->seg);
     delete s;
     return EMDEE_OK;
 }
@@ -915,18 +923,22 @@ __global__ void k_brick_max(GridDesc g, const int32_t *__restrict__ cell_start, 
     const int M = g.M, R = g.R;
     const int hx0 = bxi * g.bx, hy0 = byi * g.by, hz0 = g.zhome0 + bzi * g.bz;
     const int nhx = min(g.bx, M - hx0), nhy = min(g.by, M - hy0), nhz = min(g.bz, g.zhome0 + g.nzhome - hz0);
-    int total = 0;
+    int total = 0, rowmax = 0;
     for (int cz = 0; cz < nhz + 2 * R; cz++)
         for (int cy = 0; cy < nhy + 2 * R; cy++) {
             int lz = hz0 - R + cz;
             if (g.zwrap) lz = wrap_mod(lz, M);
             const int gy = wrap_mod(hy0 - R + cy, M);
+            int row = 0;
             for (int cx = 0; cx < nhx + 2 * R; cx++) {
                 const int lc = wrap_mod(hx0 - R + cx, M) + M * (gy + M * lz);
-                total += cell_start[lc + 1] - cell_start[lc];
+                row += cell_start[lc + 1] - cell_start[lc];
             }
+            total += row;
+            rowmax = max(rowmax, row);
         }
     atomicMax(out, total);
+    atomicMax(out + 1, rowmax);        // longest staged (y, z) row: sizes the raw ring of the TMA staging
 }
 
 static int exclusive_scan(emdee_system *s, int32_t *data, int64_t n, int32_t *maxval)
@@ -950,17 +962,18 @@ static int exclusive_scan(emdee_system *s, int32_t *data, int64_t n, int32_t *ma
 //   blocks/SM(shared memory, registers) x min(warps per block, warp tasks per brick).
 // The staged-atom capacity is the exact maximum over all bricks (k_brick_max), so a launch never
 // overflows.  The previous choice is kept across re-binnings while it still fits.
-static int brick_capacity(emdee_system *s, int *cap_out)
+static int brick_capacity(emdee_system *s, int *cap_out, int *rowmax_out)
 {
     emdee_ctx *c = s->ctx;
     GridDesc &g = s->g;
-    CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
+    CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, 2 * sizeof(int), c->stream));
     const int nb = g.nbx * g.nby * g.nbz;
     LAUNCH_1D(c, k_brick_max, (int64_t)nb, g, s->cell_start, s->brick_max);
-    int mx = 0;
-    CUDA_TRY(cudaMemcpyAsync(&mx, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    int mx[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(mx, s->brick_max, sizeof(mx), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
-    *cap_out = std::max(64, (mx + 4) & ~3);
+    *cap_out = std::max(64, (mx[0] + 4) & ~3);
+    *rowmax_out = mx[1];
     return check_launch("k_brick_max");
 }
 static void set_brick_shape(emdee_system *s, const int sh[3])
@@ -1010,8 +1023,9 @@ static int choose_bricks(emdee_system *s)
         }
         return 0;
     };
-    auto finish = [&](int cap, int block, int lblock) -> int {
+    auto finish = [&](int cap, int block, int lblock, int rowmax) -> int {
         s->fc_cap = cap;
+        s->fc_rowmax = rowmax;
         // 32-atom groups per brick from the densest cell, with head-room so that density fluctuations between
         // re-binnings do not resize the pair list
         const int gmax = (g.bx * g.by * g.bz * (std::max(maxpop, 1) + 8) + 31) / 32 + 1;
@@ -1023,6 +1037,20 @@ static int choose_bricks(emdee_system *s)
         s->fl_block = lblock;
         s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
         s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin;
+        // TMA staging: the x image of a staged atom is resolved against its segment's centre, so a segment must span less than
+        // half the box; the raw ring (two groups of whole rows) must fit behind the stacks
+        s->fl_tma = false;
+        if (s->fl_persistent && s->want_tma && !s->want_n3 && 2 * (g.bx + 2 * R + 1) <= g.M && rowmax > 0) {
+            const int nrows = (g.by + 2 * R) * (g.bz + 2 * R), rowpad = (rowmax + 5) & ~1;
+            const size_t base = flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) + 2 * (size_t)(2 * nrows) * sizeof(int4) + 64;
+            if (base < c->smem_optin) {
+                const int r = (int)std::min<size_t>((c->smem_optin - base) / (2 * 3 * sizeof(double) * (size_t)rowpad), (size_t)nrows);
+                if (r >= 1 && (int64_t)r * rowpad < 65536) {
+                    s->fl_tma = true;
+                    s->segcap = 2 * nrows; s->raw_rows = r; s->rawlen = r * rowpad;
+                }
+            }
+        }
         s->fc_typed = typed;
         s->fc_nblocks = g.nbx * g.nby * g.nbz;
         return EMDEE_OK;
@@ -1031,12 +1059,12 @@ static int choose_bricks(emdee_system *s)
     // (one tiny kernel + sync per re-binning)
     if (s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK") && std::fabs(per_cell - s->fc_per_cell) <= 0.08 * s->fc_per_cell && R == s->fc_R) {
         set_brick_shape(s, s->fc_shape);
-        int cap = s->pre_cap;              // (a slab re-binning measured it for this shape before its one synchronisation)
-        if (!s->pre_valid) EMDEE_TRY(brick_capacity(s, &cap));
+        int cap = s->pre_cap, rowmax = s->pre_rowmax;      // (a slab re-binning measured them for this shape before its one synchronisation)
+        if (!s->pre_valid) EMDEE_TRY(brick_capacity(s, &cap, &rowmax));
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const size_t need = listed ? fl_smem_bytes(cap, ncs, s->fl_block, std::max(s->ntypes, 1)) : fc_smem_bytes(cap, ncs, s->fc_block, typed);
         if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin)
-            return finish(cap, s->fc_block, s->fl_block);
+            return finish(cap, s->fc_block, s->fl_block, rowmax);
     }
     // shapes in units of ndiv cells (a cell edge is (rc + skin)/ndiv), so the candidates keep their physical size
     static const int base_shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {7, 2, 2}, {5, 3, 2}, {6, 2, 2}, {4, 3, 2}, {5, 2, 2}, {3, 3, 2}, {8, 2, 1}, {4, 4, 1},
@@ -1054,7 +1082,7 @@ static int choose_bricks(emdee_system *s)
     if (const char *e = getenv("EMDEE_BLOCK")) forced_block = atoi(e);
     if (const char *e = getenv("EMDEE_LBLOCK")) forced_lblock = atoi(e);
     double best_score = -1;
-    int best_shape[3] = {0, 0, 0}, best_block = 0, best_lblock = 192, best_cap = 0;
+    int best_shape[3] = {0, 0, 0}, best_block = 0, best_lblock = 192, best_cap = 0, best_rowmax = 0;
     size_t best_budget = 0;
     const int nshape = forced[0] > 0 ? 1 : nshapes_all;
     int prev[3] = {-1, -1, -1};
@@ -1065,8 +1093,8 @@ static int choose_bricks(emdee_system *s)
         if (std::max(g.bx, std::max(g.by, g.bz)) + 2 * R > 32) continue;       // ctab / ccoord hold 32 cells per dimension
         if (g.bx == prev[0] && g.by == prev[1] && g.bz == prev[2]) continue;   // clipped to the same shape as the previous one
         prev[0] = g.bx; prev[1] = g.by; prev[2] = g.bz;
-        int cap = 0;
-        EMDEE_TRY(brick_capacity(s, &cap));
+        int cap = 0, rowmax = 0;
+        EMDEE_TRY(brick_capacity(s, &cap, &rowmax));
         if (cap > 65534) continue;
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const double home = per_cell * g.bx * g.by * g.bz;
@@ -1085,7 +1113,7 @@ static int choose_bricks(emdee_system *s)
                 // picks 4x4x1 bricks there, 0.252 ms per launch against 0.240 ms for 4x2x2 with a half-filled last layer: not kept)
                 const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
                 if (score > best_score) {
-                    best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap;
+                    best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap; best_rowmax = rowmax;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
                     best_budget = c->smem_optin;
                 }
@@ -1107,7 +1135,7 @@ static int choose_bricks(emdee_system *s)
                 const double active = std::min(16.0, resident * nw * busy);
                 const double score = active * 1000.0 + 100.0 * std::min(resident, 3) + 2.0 * (g.bx * g.by * g.bz);
                 if (score > best_score) {
-                    best_score = score; best_block = cblock; best_lblock = lblock; best_cap = cap;
+                    best_score = score; best_block = cblock; best_lblock = lblock; best_cap = cap; best_rowmax = rowmax;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
                     best_budget = per_sm / resident - 1024;
                 }
@@ -1128,7 +1156,7 @@ static int choose_bricks(emdee_system *s)
             // the halo staged per home atom drops from 9x to 5x), then fewer idle warps
             const double score = active * 1000.0 + 2.0 * (g.bx * g.by * g.bz) - 0.1 * resident * (block / 32);
             if (score > best_score) {
-                best_score = score; best_block = block; best_cap = cap;
+                best_score = score; best_block = block; best_cap = cap; best_rowmax = rowmax;
                 best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
                 best_budget = per_sm / resident - 1024;
             }
@@ -1143,7 +1171,7 @@ static int choose_bricks(emdee_system *s)
     s->fc_per_cell = per_cell;
     s->fc_R = R;
     s->fc_smem_budget = std::min(best_budget, c->smem_optin);
-    return finish(best_cap, best_block, best_lblock);
+    return finish(best_cap, best_block, best_lblock, best_rowmax);
 }
 
 static int do_bin(emdee_system *s, int ndiv)
@@ -1383,14 +1411,14 @@ static int do_bin_slab(emdee_system *s, int ndiv)
         CUDA_TRY(cudaMemcpyAsync(&marks[k], s->cell_start + mark_idx[k], sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
     // read back in the same synchronisation: the densest cell, the staged-atom capacity of the previous brick shape (what
     // choose_bricks needs when it keeps that shape), and the largest displacement of the interval that ends here
-    int pre_maxpop = 0, pre_brickmax = 0;
+    int pre_maxpop = 0, pre_brickmax[2] = {0, 0};
     unsigned dmax_bits = 0;
     const bool pre = s->fc_shape[0] > 0 && !getenv("EMDEE_BRICK");
     if (pre) {
         set_brick_shape(s, s->fc_shape);
-        CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, sizeof(int), c->stream));
+        CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, 2 * sizeof(int), c->stream));
         LAUNCH_1D(c, k_brick_max, (int64_t)(g.nbx * g.nby * g.nbz), g, s->cell_start, s->brick_max);
-        CUDA_TRY(cudaMemcpyAsync(&pre_brickmax, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(pre_brickmax, s->brick_max, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     }
     CUDA_TRY(cudaMemcpyAsync(&pre_maxpop, s->maxpop, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     if (!first_time) {
@@ -1401,7 +1429,8 @@ static int do_bin_slab(emdee_system *s, int ndiv)
     REBIN_PHASE(1)       // ghost-plane populations, scan, marks
     s->pre_valid = pre;
     s->pre_maxpop = pre_maxpop;
-    s->pre_cap = std::max(64, (pre_brickmax + 4) & ~3);
+    s->pre_cap = std::max(64, (pre_brickmax[0] + 4) & ~3);
+    s->pre_rowmax = pre_brickmax[1];
     if (!first_time && s->skin > 0) {
         float d2;
         memcpy(&d2, &dmax_bits, 4);
@@ -1630,11 +1659,17 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
 {
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
     const bool n3 = !COUNT && !EW && s->vv_mode != 0 && s->list_n3;
+    bool tma = s->fl_tma && a.seg != nullptr && !n3;      // the stepping variants and the single-point F/E/W variant have a TMA form
     if (!COUNT && !EW && s->vv_mode != 0) {
         if (n3) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, true>;
+        else if (tma) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, false, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, false, true>;
         else kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
-    }
-    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, n3 ? s->fc_gmax : 0);
+    } else if (tma && !COUNT && EW && s->fl_fuse)
+        kern = k_force_list_p<MULTI, false, 2, true, true, false, false, false, true>;
+    else
+        tma = false;
+    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, n3 ? s->fc_gmax : 0) +
+                        (tma ? flp_tma_bytes(s->segcap, s->rawlen) : 0);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
     // registers of its SM, so NCCL could not start before the first block retires otherwise)
@@ -1848,6 +1883,18 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
             EMDEE_TRY(dev_alloc(&s->brickhdr, (size_t)2 * s->hdr_cap));
         }
         a.recipe = s->recipe; a.homeidx = s->homeidx; a.brickhdr = s->brickhdr; a.rcap = s->fc_cap + 1;
+        if (s->fl_tma) {
+            const int64_t sneed = (int64_t)s->fc_nblocks * s->segcap;
+            if (sneed > s->seg_cap_total) {
+                dev_free(s->seg);
+                s->seg_cap_total = sneed + sneed / 8;
+                EMDEE_TRY(dev_alloc(&s->seg, (size_t)s->seg_cap_total));
+            }
+            a.seg = s->seg; a.segcap = s->segcap; a.raw_rows = s->raw_rows; a.rawlen = s->rawlen;
+            if (mode == 1 && getenv("EMDEE_DEBUG"))
+                fprintf(stderr, "[emdee] TMA staging: %d segments per brick, raw ring of 2 x %d rows x %d atoms (longest row %d)\n", s->segcap,
+                        s->raw_rows, s->rawlen / std::max(1, s->raw_rows), s->fc_rowmax);
+        }
         // lanes of a group without a home atom must read "no entries"
         if (mode == 1) CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
     }
@@ -1980,6 +2027,7 @@ static int check_device_flag(emdee_system *s, const char *where)
         if (flag == 5) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: the pair list overflowed its capacity (set EMDEE_LIST_CHUNKS higher or EMDEE_LIST=0)", where);
         if (flag == 4) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "%s: migration list overflow", where);
         if (flag == 8) EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an internal bounds check of the list kernels failed (library built with -DEMDEE_CHECKS=1)", where);
+        if (flag == 9) EMDEE_FAIL(EMDEE_ERR_CUDA, "%s: a bulk copy of the staging path never completed", where);
         if (flag == 6) EMDEE_FAIL(EMDEE_ERR_NCCL, "%s: a neighbouring rank never published its boundary atoms (peer-mapped halo timed out after ~2 s)", where);
         if (flag == 7) EMDEE_FAIL(EMDEE_ERR_INVALID, "%s: a position window did not cover every atom this rank owns", where);
         EMDEE_FAIL(EMDEE_ERR_STATE, "%s: an atom left the slab's cell range", where);
@@ -2264,7 +2312,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         // (first half-kick, drift, s = r/L into the second buffer) for every atom as soon as its force is known.
         // k_vv only starts the first step of the call.
         for (int k = 0; k < 3; k++)
-            if (!s->s_alt[k]) EMDEE_TRY(dev_alloc(&s->s_alt[k], (size_t)s->cap));
+            if (!s->s_alt[k]) EMDEE_TRY(dev_alloc(&s->s_alt[k], (size_t)s->cap + 2));
         bool drifted = false;
         const char *ue = getenv("EMDEE_DEBUG_UNFUSE_AT");
         const int64_t unfuse_at = ue ? atoll(ue) : -1;
@@ -2405,7 +2453,7 @@ extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
     out[2] = s->grid_ok ? s->g.bz : 0;
     out[3] = s->grid_ok ? s->fc_cap : 0;
     out[4] = listed ? 1 : 0;
-    out[5] = listed && s->fl_persistent ? 1 : 0;
+    out[5] = listed && s->fl_persistent ? (1 | (s->fl_tma ? 2 : 0)) : 0;      // bit 1: staging by bulk asynchronous copies (EMDEE_TMA=1)
     out[6] = listed && s->fl_persistent && s->fuse_vv && s->n14 == 0 && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
     out[7] = s->lcap8;
     return EMDEE_OK;

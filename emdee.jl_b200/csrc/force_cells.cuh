@@ -107,6 +107,12 @@ struct CellArgs {
     unsigned long long wait_epoch;    // ghosts of this launch are complete when the flags reach this value (0: already complete)
     unsigned long long publish_epoch; // value I raise after my boundary atoms are advanced (0: nothing is published)
     int *p2p_done;                    // [0] lower-side bricks advanced, [1] upper-side (zeroed per launch)
+    // TMA staging of the persistent kernel: segment table written by k_list_build -- per brick, two entries per staged (y, z) row
+    // (the part before and behind the periodic seam): {first slot rounded down to even, atoms | misalignment << 16,
+    // staged index + 1 of the first atom | offset in the raw group << 16, first staged cell x | cells << 8 | cy << 16 | cz << 24}
+    int4 *seg;
+    int segcap;                       // entries per brick
+    int raw_rows, rawlen;             // rows per raw group, doubles per coordinate array of a group
 };
 
 // Brick handled by launch index i (a launch covers one or two contiguous ranges of bricks).

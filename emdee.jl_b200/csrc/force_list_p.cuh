@@ -29,6 +29,12 @@
 #ifndef FLP_NPROD
 #define FLP_NPROD 4
 #endif
+#ifndef FLP_MBAR
+#define FLP_MBAR 1           // hand-over of the staging buffers by mbarriers (0: named barriers, every consumer warp waits for the slowest)
+#endif
+#ifndef FLP_CARRY
+#define FLP_CARRY 0          // a warp's first task of the NEXT brick is claimed (and its list head requested) before the final drain
+#endif                       // of its last task in this one, when that buffer is already full
 #define FLP_NCONS (FLP_THREADS / 32 - FLP_NPROD)
 #define FLP_QS (FLP_NCONS * 32)          // row stride of the consumers' stacks
 
@@ -54,7 +60,8 @@ __host__ __device__ inline int flp_qcap(int nbuf) { return nbuf >= 3 ? 24 : FL_Q
 __host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf, int n3_groups = 0)
 {
     return nbuf * flp_buf_bytes(cap, ncs_max, ntypes, n3_groups) + (size_t)ntypes * ntypes * sizeof(double2) +
-           (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t);
+           (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t) +
+           128;     // (head-room for the kernel's static shared memory -- barriers, brick claims -- which counts against the same limit)
 }
 
 // -DFLP_TIMING=1: per-role cycle counters (clock64) accumulated into a.timing[8]: producers' wait for an empty buffer,
@@ -62,10 +69,22 @@ __host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntype
 #ifndef FLP_TIMING
 #define FLP_TIMING 0
 #endif
+__device__ __forceinline__ long long flp_clock() { long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory"); return t; }
 #if FLP_TIMING
-#define FLP_T(var) const long long var = clock64()
+// BAR.SYNC does not block at issue on sm_100 (the block is deferred to the next instruction that touches barrier-protected
+// state), so a clock read right behind a barrier measures nothing: FLP_TB reads a word of shared memory first
+__device__ __forceinline__ long long flp_clock_after(const volatile int *protected_word)
+{
+    const int v = *protected_word;
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(v) : "memory");
+    return t;
+}
+#define FLP_T(var) const long long var = flp_clock()
+#define FLP_TB(var, word) const long long var = flp_clock_after(word)
 #define FLP_TACC(slot, expr) do { if (lane == 0) tacc[slot] += (expr); } while (0)
 #else
+#define FLP_TB(var, word)
 #define FLP_T(var)
 #define FLP_TACC(slot, expr)
 #endif
@@ -81,6 +100,74 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// ---- bulk asynchronous copies (TMA, cp.async.bulk) completing on an mbarrier: the staging path of the TMA variant ----------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// (bounded: a copy that never completes -- a fault, a byte count that does not add up -- raises device flag 9 instead of hanging)
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity, int *err)
+{
+    unsigned done;
+    int spins = 0;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (!done && ++spins > (1 << 20)) { atomicCAS(err, 0, 9); break; }
+    } while (!done);
+}
+// ---- hand-over of the staging buffers by mbarriers: full[b] counts the producer threads, empty[b] the consumer threads -------
+// (named barriers made every consumer warp wait for the slowest one at each brick boundary: bar.sync needs all of them to arrive;
+// with an mbarrier a warp that is done with brick k goes on to brick k+1 as soon as that buffer is full, one brick of slack)
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded by time (~4 s: boundary bricks of a slab may wait ~2 s for a neighbour's flag before they are staged): device flag 9
+__device__ __forceinline__ bool mbar_wait_long(unsigned long long *bar, unsigned parity, int *err)
+{
+    unsigned done;
+    int spins = 0;
+    long long t0 = 0;
+    for (;;) {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (done) return true;
+        if ((++spins & 1023) == 0) {
+            long long t; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t)::"memory");
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > (1ll << 33)) { atomicCAS(err, 0, 9); return false; }
+        }
+    }
+}
+__device__ __forceinline__ bool mbar_test(unsigned long long *bar, unsigned parity)      // has that phase completed? (no waiting)
+{
+    unsigned done;
+    asm volatile("{ .reg .pred p; mbarrier.test_wait.parity.acquire.cta.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return done != 0;
+}
+// `bytes` (a multiple of 16) from 16-byte aligned global memory to 16-byte aligned shared memory; completion is counted on `bar`
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// shared memory of the TMA variant behind the stacks: two segment tables (this brick's, the next one's) and a ring of two raw
+// row groups (three coordinate arrays each) that the bulk copies fill
+__host__ __device__ inline size_t flp_tma_bytes(int segcap, int rawlen)
+{
+    return 2 * (size_t)segcap * sizeof(int4) + 2 * 3 * (size_t)rawlen * sizeof(double) + 32;
 }
 
 struct BrickBuf {
@@ -128,7 +215,13 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // N3: the list holds every pair of two home atoms once (k_list_build<.., N3>); the evaluating lane adds the reaction to the
 // partner's accumulator in shared memory (FP64 compare-and-swap loops), home atoms' own sums go to the same accumulators at the
 // end of a warp task, and the producers write a brick's forces out once its consumers have released the buffer.
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false>
+// TMA: the producers stage a brick from bulk asynchronous copies instead of per-atom gathers.  After the (cell, id) sort every
+// (y, z) row of the brick's cell block is one contiguous slot range of the coordinate arrays (two at the periodic seam), so a
+// row is three cp.async.bulk copies (x, y, z) that one lane issues and an mbarrier counts; k_list_build leaves the segment
+// table of every brick behind.  Row groups are copied into a two-slot ring of raw scaled coordinates ahead of time -- also
+// across bricks, before the consumers have released the buffer -- and what remains on the hand-over's critical path is the
+// shared-to-shared pass into the brick's frame (FP64 + FP16 copies).  No staging recipe is read.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false, bool TMA = false>
 __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
@@ -141,8 +234,25 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     uint16_t *qguard = reinterpret_cast<uint16_t *>(ljt + a.ntypes * a.ntypes);
     uint16_t *queue = qguard + FLP_QS;
     __shared__ int claimed[2];                 // the producers' next brick (double-buffered over the brick parity)
+    __shared__ __align__(8) unsigned long long tma_bar[2];      // one mbarrier per slot of the raw ring (TMA variant)
+    __shared__ __align__(8) unsigned long long hand_bar[2 * NBUF];   // full[b] = hand_bar[b], empty[b] = hand_bar[NBUF + b]
+    // TMA variant: segment tables and raw ring behind the stacks
+    int4 *segs = reinterpret_cast<int4 *>(
+        smem_raw + ((reinterpret_cast<unsigned char *>(queue + (size_t)QCAP * FLP_QS) - smem_raw + 15) & ~(size_t)15));
+    double *rawring = reinterpret_cast<double *>(segs + 2 * (TMA ? a.segcap : 0));
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        if (TMA) { mbar_init(&tma_bar[0], FLP_NPROD); mbar_init(&tma_bar[1], FLP_NPROD); }
+        for (int q = 0; q < NBUF; q++) { mbar_init(&hand_bar[q], FLP_NPROD * 32); mbar_init(&hand_bar[NBUF + q], FLP_NCONS * 32); }
+        mbar_fence_init();
+    }
+    // fill number n of a buffer (n = k / NBUF): the consumers wait for phase n of full[b], the producers for phase n of empty[b]
+    // before fill n + 1; every thread of the arriving side arrives (release), every waiting thread polls (acquire)
+    auto full_arrive = [&](int b_) { if (FLP_MBAR) mbar_arrive(&hand_bar[b_]); else bar_arrive(1 + b_, FLP_THREADS); };
+    auto full_wait = [&](int b_, int fill) { return FLP_MBAR ? mbar_wait_long(&hand_bar[b_], fill & 1, a.err) : (bar_sync(1 + b_, FLP_THREADS), true); };
+    auto empty_arrive = [&](int b_) { if (FLP_MBAR) mbar_arrive(&hand_bar[NBUF + b_]); else bar_arrive(1 + NBUF + b_, FLP_THREADS); };
+    auto empty_wait = [&](int b_, int fill) { return FLP_MBAR ? mbar_wait_long(&hand_bar[NBUF + b_], fill & 1, a.err) : (bar_sync(1 + NBUF + b_, FLP_THREADS), true); };
     for (int t = tid; t < a.ntypes * a.ntypes; t += FLP_THREADS) ljt[t] = a.ljtab[t];
     if (tid < FLP_QS) qguard[tid] = 0;
     if (N3)
@@ -153,7 +263,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     __syncthreads();
 #if FLP_TIMING
     long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    const long long t_begin = clock64();
+    const long long t_begin = flp_clock();
 #endif
 
     if (warp < FLP_NPROD) {
@@ -259,48 +369,93 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         bool seen_lo = !(VV && P2P && a.wait_epoch != 0), seen_hi = seen_lo;
         auto wait_flag = [&](const unsigned long long *f) {
             if (tid == 0) {
-                const long long t0 = clock64();
+                const long long t0 = flp_clock();
                 while (ld_acquire_sys(f) < a.wait_epoch) {
                     __nanosleep(64);
-                    if (clock64() - t0 > (1ll << 32)) { atomicCAS(a.err, 0, 6); break; }      // ~2 s: the neighbour never published
+                    if (flp_clock() - t0 > (1ll << 32)) { atomicCAS(a.err, 0, 6); break; }      // ~2 s: the neighbour never published
                 }
                 __threadfence_system();
             }
             bar_sync(1 + 2 * NBUF, PN);
         };
+        // ---- TMA variant: row groups of a brick travel global -> raw ring by bulk copies, issued one group ahead ----------
+        unsigned gq = 0, gw = 0;                    // row groups issued / consumed so far (the same in every producer thread)
+        auto flags_for = [&](int vbid) {            // P2P: ghosts this brick reads must be complete before they are copied
+            if (VV && P2P) {
+                const int bzi = vbid / (g.nbx * g.nby);
+                if (!seen_lo && bzi < a.p2p_lo_layers) { wait_flag(a.flag_from_lo); seen_lo = true; if (TMA) fence_proxy_async(); }
+                if (!seen_hi && bzi >= a.p2p_hi_layer0) { wait_flag(a.flag_from_hi); seen_hi = true; if (TMA) fence_proxy_async(); }
+            }
+        };
+        auto seg_load = [&](int sb, int vbid) {
+            for (int t = tid; t < a.segcap; t += PN) segs[sb * a.segcap + t] = a.seg[(size_t)vbid * a.segcap + t];
+        };
+        // every producer warp issues the copies of the segments it will transform itself (segment t belongs to warp t mod NPROD):
+        // cp.async.bulk runs on the uniform datapath, one copy at a time per warp, so four warps issue four at a time
+        auto group_issue = [&](int sb, int vnrows, int gi) {
+            const int slot = gq & 1;
+            const int s0 = 2 * gi * a.raw_rows, s1 = min(2 * vnrows, 2 * (gi + 1) * a.raw_rows);
+            double *rw = rawring + (size_t)slot * 3 * a.rawlen;
+            unsigned bytes = 0;
+            for (int t = s0 + warp + FLP_NPROD * lane; t < s1; t += FLP_NPROD * 32) {
+                const int4 e = segs[sb * a.segcap + t];
+                const int n = e.y & 0xffff;
+                if (n) bytes += 24u * (unsigned)(((e.y >> 16) + n + 1) & ~1);
+            }
+            bytes = __reduce_add_sync(0xffffffffu, bytes);
+            if (lane == 0) mbar_expect_tx(&tma_bar[slot], bytes);       // (one arrival per producer warp completes the phase)
+            __syncwarp();
+            for (int t = s0 + warp + FLP_NPROD * lane; t < s1; t += FLP_NPROD * 32) {
+                const int4 e = segs[sb * a.segcap + t];
+                const int n = e.y & 0xffff;
+                if (!n) continue;
+                const unsigned nb8 = 8u * (unsigned)(((e.y >> 16) + n + 1) & ~1), ro = (unsigned)e.z >> 16;
+                bulk_g2s(rw + ro, a.sx + e.x, nb8, &tma_bar[slot]);
+                bulk_g2s(rw + a.rawlen + ro, a.sy + e.x, nb8, &tma_bar[slot]);
+                bulk_g2s(rw + 2 * a.rawlen + ro, a.sz + e.x, nb8, &tma_bar[slot]);
+            }
+            gq++;
+        };
+        if (TMA && brick < nbricks) {
+            const int bid0 = FC_BRICK_OF(a, brick);
+            seg_load(0, bid0);
+            bar_sync(1 + 2 * NBUF, PN);
+            flags_for(bid0);
+            group_issue(0, brick_geom(g, bid0).nrows, 0);
+        }
         for (int k = 0;; k++) {
             const int b = k % NBUF;
             const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
             if (brick >= nbricks) {
                 FLP_T(tw0);
-                if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);
-                FLP_TACC(0, clock64() - tw0);
+                if (k >= NBUF && !empty_wait(b, k / NBUF - 1)) return;
+                FLP_TACC(0, flp_clock() - tw0);
                 if (N3 && held_bid[b] >= 0) flush_forces(B, held_bid[b], held_nh[b]);
                 if (tid == 0) B.scal[4] = -1;
                 __threadfence_block();
-                bar_arrive(1 + b, FLP_THREADS);
+                full_arrive(b);
                 if (VV) {
                     // the atoms of the brick just released, then (after its release) those of the brick in the other buffer
                     FLP_T(ta0);
                     if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);
-                    FLP_TACC(2, clock64() - ta0);
+                    FLP_TACC(2, flp_clock() - ta0);
 #pragma unroll
                     for (int q = 1; q < NBUF; q++) {
                         const int ob = (k + q) % NBUF;
                         if (held_bid[ob] >= 0) {
                             FLP_T(tw1);
-                            bar_sync(1 + NBUF + ob, FLP_THREADS);
+                            if (!empty_wait(ob, (k - NBUF + q) / NBUF)) return;      // (its last fill was step k - NBUF + q)
                             FLP_T(ta1);
                             if (N3) flush_forces(brick_buf(smem_raw + ob * bufsz, a.cap, a.ncs_max, MULTI), held_bid[ob], held_nh[ob]);
                             advance_atoms(held_bid[ob], held_nh[ob]);
                             FLP_TACC(0, ta1 - tw1);
-                            FLP_TACC(2, clock64() - ta1);
+                            FLP_TACC(2, flp_clock() - ta1);
                         }
                     }
                 }
 #if FLP_TIMING
                 if (warp == 0 && lane == 0) {
-                    tacc[3] = clock64() - t_begin;         // producers' total
+                    tacc[3] = flp_clock() - t_begin;         // producers' total
                     for (int q = 0; q < 4; q++) atomicAdd(a.timing + q, (unsigned long long)tacc[q]);
                     atomicAdd(a.timing + 6, (unsigned long long)k);
                 }
@@ -353,14 +508,12 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     if (MULTI) B.ptyp[i] = (uint8_t)a.type[rc[u].x];
                 }
             };
-            if (VV && P2P) {
-                const int bzi = bid / (g.nbx * g.nby);
-                if (!seen_lo && bzi < a.p2p_lo_layers) { wait_flag(a.flag_from_lo); seen_lo = true; }
-                if (!seen_hi && bzi >= a.p2p_hi_layer0) { wait_flag(a.flag_from_hi); seen_hi = true; }
+            if (!TMA) {
+                flags_for(bid);
+                // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
+                // time, and the staging latency that follows the hand-over is what the consumers then wait for
+                load_batch(1 + tid);
             }
-            // the first batch is requested BEFORE the buffer is free: the producers wait for the consumers ~40 % of the
-            // time, and the staging latency that follows the hand-over is what the consumers then wait for
-            load_batch(1 + tid);
             if (tid == 0) claimed[k & 1] = gridDim.x + atomicAdd(a.brick_counter, 1);
             bar_sync(1 + 2 * NBUF, PN);        // producers only; ids 1..NBUF are full[], NBUF+1..2*NBUF empty[]
             const int nb = claimed[k & 1];
@@ -370,8 +523,11 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     const int nbid = FC_BRICK_OF(a, nb);
                     hdr_n1 = a.brickhdr[2 * nbid];
                     hdr_nh = a.brickhdr[2 * nbid + 1];
-                    const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
-                    for (int t = tid * 128; t < a.rcap * 8; t += PN * 128) prefetch_l2(nr + t);
+                    if (TMA) seg_load((k + 1) & 1, nbid);
+                    else {
+                        const unsigned char *nr = reinterpret_cast<const unsigned char *>(a.recipe + (size_t)nbid * a.rcap);
+                        for (int t = tid * 128; t < a.rcap * 8; t += PN * 128) prefetch_l2(nr + t);
+                    }
                 }
             }
             {   // the consumers claim this brick's tasks dynamically: bring every group's entry counts and first chunks into L2
@@ -384,8 +540,8 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
             }
             FLP_T(tw2);
-            if (k >= NBUF) bar_sync(1 + NBUF + b, FLP_THREADS);       // empty[b]: the consumers are done with this buffer
-            FLP_T(ts0);
+            if (k >= NBUF && !empty_wait(b, k / NBUF - 1)) return;    // empty[b]: the consumers are done with this buffer
+            FLP_TB(ts0, B.scal + 3);
             FLP_TACC(0, ts0 - tw2);
             if (N3 && held_bid[b] >= 0) flush_forces(B, held_bid[b], held_nh[b]);
             if (tid == 0) {
@@ -400,20 +556,76 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 B.scal[3] = 0;              // task cursor
                 B.scal[4] = brick;
             }
-            store_batch(1 + tid);
-            for (int i0 = 1 + tid + U * PN; i0 < n1; i0 += U * PN) {
-                load_batch(i0);
-                store_batch(i0);
+            if (TMA) {
+                bar_sync(1 + 2 * NBUF, PN);         // the next brick's segment table is complete
+                const int ngr = (bg.nrows + a.raw_rows - 1) / a.raw_rows;
+                const int sb = k & 1;
+                for (int gi = 0; gi < ngr; gi++) {
+                    // one group ahead: the next group of this brick, or the first one of the next brick (its buffer need not be free)
+                    if (gi + 1 < ngr) group_issue(sb, bg.nrows, gi + 1);
+                    else if (nb < nbricks) {
+                        const int nbid = FC_BRICK_OF(a, nb);
+                        flags_for(nbid);
+                        group_issue((k + 1) & 1, brick_geom(g, nbid).nrows, 0);
+                    }
+                    const int slot = gw & 1;
+                    mbar_wait(&tma_bar[slot], (gw >> 1) & 1, a.err);
+                    gw++;
+                    const double *rw = rawring + (size_t)slot * 3 * a.rawlen;
+                    const int s0 = 2 * gi * a.raw_rows, s1 = min(2 * bg.nrows, 2 * (gi + 1) * a.raw_rows);
+                    for (int t = s0 + warp; t < s1; t += FLP_NPROD) {
+                        const int4 e = segs[sb * a.segcap + t];
+                        const int n = e.y & 0xffff;
+                        if (!n) continue;
+                        const int mis = e.y >> 16, st0 = e.z & 0xffff, ro = (int)((unsigned)e.z >> 16) + mis;
+                        // image nearest to the segment's centre in x (a segment spans less than half the box: checked by the
+                        // host) and to the row's cell in y and z
+                        const double cxc = ((double)(ux0 + (e.w & 255)) + 0.5 * ((e.w >> 8) & 255)) * invM,
+                                     cyc = ((double)(uy0 + ((e.w >> 16) & 255)) + 0.5) * invM, czc = ((double)(uz0 + (int)((unsigned)e.w >> 24)) + 0.5) * invM;
+                        const double ox = cxc - bcx, oy = cyc - bcy, oz = czc - bcz;
+                        constexpr int TU = 4;                  // atoms per lane in flight (the chain load -> image -> store is pure latency)
+                        const int nlim = min(n, n1 - st0);
+                        for (int r0 = lane; r0 < nlim; r0 += 32 * TU) {
+                            double vx[TU], vy[TU], vz[TU];
+#pragma unroll
+                            for (int u = 0; u < TU; u++) {
+                                const int q = ro + min(r0 + 32 * u, nlim - 1);
+                                vx[u] = rw[q]; vy[u] = rw[a.rawlen + q]; vz[u] = rw[2 * a.rawlen + q];
+                            }
+#pragma unroll
+                            for (int u = 0; u < TU; u++) {
+                                const int r = r0 + 32 * u;
+                                if (r >= nlim) break;
+                                const int i = st0 + r;
+                                double dx = vx[u] - cxc, dy = vy[u] - cyc, dz = vz[u] - czc;
+                                dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);
+                                const double px = a.L * (dx + ox), py = a.L * (dy + oy), pzv = a.L * (dz + oz);
+                                B.pxy[i] = make_double2(px, py);
+                                B.pz[i] = pzv;
+                                const __half2 hxy = __floats2half2_rn((float)px, (float)py), hz0h = __floats2half2_rn((float)pzv, 0.0f);
+                                B.ph[i] = make_uint2(*reinterpret_cast<const unsigned *>(&hxy), *reinterpret_cast<const unsigned *>(&hz0h));
+                                if (MULTI) B.ptyp[i] = (uint8_t)a.type[e.x + mis + r];
+                            }
+                        }
+                    }
+                    bar_sync(1 + 2 * NBUF, PN);     // this ring slot may be overwritten by the group after next
+                }
+            } else {
+                store_batch(1 + tid);
+                for (int i0 = 1 + tid + U * PN; i0 < n1; i0 += U * PN) {
+                    load_batch(i0);
+                    store_batch(i0);
+                }
             }
             __threadfence_block();
-            bar_arrive(1 + b, FLP_THREADS);                           // full[b]
+            full_arrive(b);                                           // full[b]
             FLP_T(ta2);
             FLP_TACC(1, ta2 - ts0);
             if (VV) {
                 if (held_bid[b] >= 0) advance_atoms(held_bid[b], held_nh[b]);     // released before this staging started
                 held_bid[b] = bid; held_nh[b] = nh;
             }
-            FLP_TACC(2, clock64() - ta2);
+            FLP_TACC(2, flp_clock() - ta2);
             brick = nb;
         }
         return;
@@ -438,13 +650,16 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         for (int k = 2; k < 2 + FL_AHEAD; k++) prefetch_l2(a.list8 + (gs * a.lcap8 + k) * 32 + lane);
     };
 
+    int carry = -1;                   // FLP_CARRY: the task already claimed in the brick this warp enters next
     for (int k = 0;; k++) {
         const int b = k % NBUF;
         const BrickBuf B = brick_buf(smem_raw + b * bufsz, a.cap, a.ncs_max, MULTI);
         FLP_T(tc0);
-        bar_sync(1 + b, FLP_THREADS);                                 // full[b]
-        FLP_TACC(4, clock64() - tc0);
+        if (!full_wait(b, k / NBUF)) break;                           // full[b]
         const int brick = B.scal[4];
+#if FLP_TIMING
+        FLP_TACC(4, flp_clock_after(B.scal + 4) - tc0);
+#endif
         if (brick < 0) break;
         const int bid = FC_BRICK_OF(a, brick);
         const double2 *pxy = B.pxy;
@@ -460,10 +675,13 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         const int ntask = min(ngroups, a.gmax);
         // tasks are claimed from the buffer's cursor; the first claim of a brick finds the list head in L2 (the producers
         // prefetched it), later ones are requested one task ahead
-        int grp = 0;
-        if (lane == 0) grp = atomicAdd(&B.scal[3], 1);
-        grp = __shfl_sync(0xffffffffu, grp, 0);
-        if (grp < ntask) request(bid, grp);
+        int grp = carry;
+        if (!(FLP_CARRY && FLP_MBAR) || carry < 0) {
+            if (lane == 0) grp = atomicAdd(&B.scal[3], 1);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+            if (grp < ntask) request(bid, grp);
+        }
+        carry = -1;
 
         while (grp < ntask) {
             const int h = (grp << 5) + lane;
@@ -486,12 +704,6 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             const uint4 *lp = a.list8 + ((size_t)bid * a.gmax + grp) * a.lcap8 * 32 + lane;
             uint4 e0 = 0 < nch ? pre0 : zero4;
             uint4 e1 = 1 < nch ? pre1 : zero4;
-            // claim the next task (in this brick, else this warp's first task of the next brick) and request its head
-            int ngrp = 0;
-            if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
-            ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
-            if (ngrp < ntask) request(bid, ngrp);
-
             int cnt = 0;
             uint16_t *qp = queue + ctid;
             unsigned tmin = 0xffffffffu;
@@ -572,6 +784,22 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 const int over = __reduce_max_sync(0xffffffffu, cnt) - (QCAP - 8);
                 if (over > 0) drain((max(over, FL_MINPOP) + ILP - 1) & ~(ILP - 1));
             }
+            // claim this warp's next task of the brick and request its list head; the final drain hides the round trip.  (Claimed
+            // at the START of a task, the first warps to reach a brick took two tasks each and left none for the others -- with the
+            // mbarrier hand-over the warps arrive one by one -- so half the warps worked on each buffer and nothing was staged ahead.)
+            int ngrp = 0;
+            if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
+            ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
+            if (ngrp < ntask) request(bid, ngrp);
+            else if (FLP_CARRY && FLP_MBAR && mbar_test(&hand_bar[(k + 1) % NBUF], ((k + 1) / NBUF) & 1)) {
+                const BrickBuf Bn = brick_buf(smem_raw + ((k + 1) % NBUF) * bufsz, a.cap, a.ncs_max, MULTI);
+                const int nbrick = Bn.scal[4];
+                if (nbrick >= 0) {
+                    if (lane == 0) carry = atomicAdd(&Bn.scal[3], 1);
+                    carry = __shfl_sync(0xffffffffu, carry, 0);
+                    if (carry < min((Bn.scal[0] + 31) >> 5, a.gmax)) request(FC_BRICK_OF(a, nbrick), carry);
+                }
+            }
             drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
 
             if (N3 && tmin <= 2u) {
@@ -621,7 +849,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             grp = ngrp;
         }
         if (VV || N3) __threadfence_block();                          // the producers read this brick's forces after empty[b]
-        bar_arrive(1 + NBUF + b, FLP_THREADS);                        // empty[b]
+        empty_arrive(b);                                              // empty[b]
     }
     if (COUNT) {
         for (int o = 16; o > 0; o >>= 1) npair += __shfl_xor_sync(0xffffffffu, npair, o);
@@ -630,7 +858,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 #if FLP_TIMING
     if (lane == 0) {
         atomicAdd(a.timing + 4, (unsigned long long)tacc[4]);
-        atomicAdd(a.timing + 5, (unsigned long long)(clock64() - t_begin));      // consumers' total, summed over warps
+        atomicAdd(a.timing + 5, (unsigned long long)(flp_clock() - t_begin));      // consumers' total, summed over warps
     }
 #endif
 }

@@ -138,6 +138,36 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         }
         if (idx + 1 < a.rcap) recipe[idx + 1] = make_int2(slot, code);
     });
+    if (a.seg) {
+        // segment table for the TMA staging of k_force_list_p: every staged (y, z) row is one contiguous slot range, two at the
+        // periodic seam in x; bulk copies need 16-byte alignment, so a segment starts at the even slot at or below its first
+        // atom and covers an even number of slots.  One thread per raw group lays the group's segments out in the raw arrays.
+        const int nrows = bg.nrows, ngroups = (nrows + a.raw_rows - 1) / a.raw_rows;
+        int4 *seg = a.seg + (size_t)bid * a.segcap;
+        for (int gi = tid; gi < ngroups; gi += blockDim.x) {
+            int off = 0;
+            for (int row = gi * a.raw_rows; row < min(nrows, (gi + 1) * a.raw_rows); row++) {
+                int seam = sxn;                                   // first staged cell behind the seam (global x = 0), if any
+                for (int cx = 1; cx < sxn; cx++)
+                    if (wrap_mod(bg.hx0 - R + cx, g.M) == 0) { seam = cx; break; }
+                const int cy = row % syn, cz = row / syn;
+                for (int part = 0; part < 2; part++) {
+                    const int c0 = part ? seam : 0, c1 = part ? sxn : seam;
+                    int4 e = make_int4(0, 0, 0, 0);
+                    if (c0 < c1) {
+                        const int t0 = row * sxn + c0;
+                        const int n = cs[row * sxn + c1] - cs[t0], g0 = gbase[t0], mis = g0 & 1;
+                        if (n > 0 && 2 * row + part < a.segcap) {
+                            e = make_int4(g0 - mis, n | (mis << 16), (cs[t0] + 1) | (off << 16), c0 | ((c1 - c0) << 8) | (cy << 16) | (cz << 24));
+                            off += (mis + n + 1) & ~1;
+                        }
+                    }
+                    if (2 * row + part < a.segcap) seg[2 * row + part] = e;
+                }
+            }
+            if (off > a.rawlen) atomicCAS(a.err, 0, 2);           // (the host sized the ring from the longest row of any brick)
+        }
+    }
     {   // header and home list (home atom h -> staged index + 1)
         const int nh = hstart[nhy * nhz];
         if (tid == 0) { a.brickhdr[2 * bid] = nstaged + 1; a.brickhdr[2 * bid + 1] = nh; }

@@ -342,7 +342,7 @@ def test_velocity_verlet(em, oracle, fuse_vv, monkeypatch):
     s.close()
 
 
-@pytest.mark.parametrize("variant", ["persistent", "fused_vv", "n3", "block_per_brick", "ndiv2", "no_list"])
+@pytest.mark.parametrize("variant", ["persistent", "fused_vv", "n3", "tma", "block_per_brick", "ndiv2", "no_list"])
 def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     """The stepping path (pair list built on the re-binning step, walked by k_force_list_p afterwards): after
     steps that only walked the list, forces and the evaluated pair count equal the oracle's at the same
@@ -350,14 +350,15 @@ def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     so the count is the sharp check.  Variants: the persistent kernel (default), the block-per-brick kernel
     it falls back to when two staging buffers do not fit, cells of half the edge (ndiv = 2), and stepping
     without a list (window scan on every step)."""
-    monkeypatch.setenv("EMDEE_FUSE_VV", "1" if variant in ("fused_vv", "n3") else "0")
+    monkeypatch.setenv("EMDEE_FUSE_VV", "1" if variant in ("fused_vv", "n3", "tma") else "0")
     monkeypatch.setenv("EMDEE_N3", "1" if variant == "n3" else "0")       # Newton's third law inside the brick (fused steps only)
+    monkeypatch.setenv("EMDEE_TMA", "1" if variant == "tma" else "0")     # staging by bulk asynchronous copies (cp.async.bulk + mbarrier)
     if variant == "block_per_brick":
         monkeypatch.setenv("EMDEE_PERSIST", "0")
     if variant == "no_list":
         monkeypatch.setenv("EMDEE_LIST", "0")
     ndiv = 2 if variant == "ndiv2" else 1
-    pos, L = em.workloads.fcc_lattice(16)
+    pos, L = em.workloads.fcc_lattice(24 if variant == "tma" else 16)     # (a bulk-copied row must span less than half the box)
     N = pos.shape[0]
     atoms = em.workloads.lj_fluid_atoms(N)
     s = make_system(em, pos, L, 2.5, 2.0, atoms)
@@ -366,6 +367,7 @@ def test_pair_list_stepping_audit(em, oracle, variant, monkeypatch):
     s.set_skin(0.4)
     s.bin(ndiv)
     s.compute(em.CUTOFF, em.FORCES)
+    assert s.step_config()["tma"] == (variant == "tma")
     for nsteps in (1, 3):                       # 1: the build step itself; 3 more: list walks
         s.vv_step(0.005, nsteps, rebin_every=5)
         s.synchronize()
