@@ -568,15 +568,13 @@ def run_b200(args):
         else:
             s.set_positions(pos_h)
         s.bin(args.ndiv)
-        s.compute(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS)
         if world > 1:
+            s.compute(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS)
             s.forces_range(id0, cnt, f_h)
             s.energies_range(id0, cnt, e_h)
             s.virials_range(id0, cnt, w_h)
-        else:
-            s.forces(f_h)
-            s.energies(e_h)
-            s.virials(w_h)
+        else:     # the reference's own call shape: compute_nonbonded!(forces, energies, virials, ...) fills three host arrays
+            s.compute_into(em.CUTOFF, em.FORCES | em.ENERGIES | em.VIRIALS, f_h, e_h, w_h)
 
     e2e_once()
     pairs_e2e = allsum(float(s.pair_set_digest()[0]))
@@ -589,7 +587,7 @@ def run_b200(args):
     rows = allsum(float(cnt))
     e2e = {"value": pairs_e2e / e2e_t, "unit": "pair-interactions/s", "h2d_bytes_per_step": int(24 * rows),
            "d2h_bytes_per_step": int(40 * rows), "ms_per_call": e2e_t * 1e3, "atom_evals_per_s": N / e2e_t,
-           "call": ("set_positions(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> forces/energies/virials(host)" if world == 1 else
+           "call": ("set_positions(host) -> bin -> compute_nonbonded_into(CUTOFF, F|E|V, forces, energies, virials: host)" if world == 1 else
                     "per rank, on the cyclic id window of the atoms it owns: set_positions_range(host) -> bin -> compute_nonbonded(CUTOFF, F|E|V) -> "
                     "forces/energies/virials_range(host); bytes are summed over ranks")}
 

@@ -286,6 +286,15 @@ class NonbondedSystem:
     def compute(self, mode=CUTOFF, bitmask=FORCES | ENERGIES | VIRIALS):
         call("emdee_compute_nonbonded", self._h, int(mode), int(bitmask))
 
+    def compute_into(self, mode, bitmask, forces=None, energies=None, virials=None):
+        """compute_nonbonded!(forces, energies, virials, ...) with the reference's output arguments (src/nonbonded.jl:109-120):
+        the evaluation and the transfer of the selected outputs into caller-owned id-ordered host arrays as ONE call
+        (emdee_compute_nonbonded_into: on one GPU the rows of a finished chunk of z planes travel while the next chunk computes)."""
+        f = _out_view(forces, self.N, 3, "forces") if bitmask & FORCES else None
+        e = _out_view(energies, self.N, 1, "energies") if bitmask & ENERGIES else None
+        w = _out_view(virials, self.N, 1, "virials") if bitmask & VIRIALS else None
+        call("emdee_compute_nonbonded_into", self._h, int(mode), int(bitmask), _ptr(f), _ptr(e), _ptr(w))
+
     def vv_step(self, dt, nsteps, rebin_every=1):
         """nsteps velocity-Verlet steps; rebin_every > 0: re-bin at that cadence, 0: never, < 0 (with a skin):
         adaptively, when an atom has moved more than skin/2 since the last binning."""
@@ -444,13 +453,7 @@ def compute_nonbonded_(forces, energies, virials, positions, L, tiles, model, at
             s.set_tiles(tiles)
         else:
             s.bin(ndiv)
-        s.compute(mode, bitmask)
-        if bitmask & FORCES:
-            s.forces(_out_view(forces, N, 3, "forces"))
-        if bitmask & ENERGIES:
-            s.energies(_out_view(energies, N, 1, "energies"))
-        if bitmask & VIRIALS:
-            s.virials(_out_view(virials, N, 1, "virials"))
+        s.compute_into(mode, bitmask, forces, energies, virials)
     finally:
         s.close()
     return None

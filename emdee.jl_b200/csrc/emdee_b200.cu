@@ -6,6 +6,8 @@
 #include <cstring>
 #include <algorithm>
 #include <cmath>
+#include <utility>
+#include <vector>
 
 #include "common.cuh"
 #include "binning.cuh"
@@ -100,6 +102,9 @@ struct emdee_ctx {
     ncclComm_t comm = nullptr;
     cudaStream_t comm_stream = nullptr;
     cudaEvent_t ev_compute = nullptr, ev_comm = nullptr;
+    // emdee_compute_nonbonded_into: results leave for the host on their own stream, chunk by chunk, behind the compute stream
+    cudaStream_t copy_stream = nullptr;
+    std::vector<cudaEvent_t> chunk_events;
 };
 
 struct emdee_system {
@@ -234,6 +239,8 @@ struct emdee_system {
     // scratch for host transfers
     double *tmp = nullptr;
     size_t tmp_bytes = 0;
+    // run_cells on a range of brick layers (emdee_compute_nonbonded_into evaluates the box in chunks of z layers); 0 layers: all
+    int range_first = 0, range_count = 0;
 };
 
 #define LAUNCH_1D(ctx, kernel, n, ...)                                                        \
@@ -331,6 +338,8 @@ extern "C" int emdee_destroy(emdee_ctx *c)
     if (c->ev_compute) cudaEventDestroy(c->ev_compute);
     if (c->ev_comm) cudaEventDestroy(c->ev_comm);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (cudaEvent_t e : c->chunk_events) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return EMDEE_OK;
@@ -1896,7 +1905,8 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
                         s->raw_rows, s->rawlen / std::max(1, s->raw_rows), s->fc_rowmax);
         }
         // lanes of a group without a home atom must read "no entries"
-        if (mode == 1) CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
+        if (mode == 1 && (s->range_count == 0 || s->range_first == 0))
+            CUDA_TRY(cudaMemsetAsync(s->list_n, 0, (size_t)slots * 32 * sizeof(uint16_t), c->stream));
     }
     const bool F = (bitmask & EMDEE_FORCES) != 0;
     const bool EW = (bitmask & (EMDEE_ENERGIES | EMDEE_VIRIALS)) != 0;
@@ -1919,6 +1929,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     // launch order: interior layers first, then (one launch over two ranges) the layers that read ghost planes
     int ranges[2][3] = {{0, s->fc_nblocks, 0}, {0, 0, 0}};       // {first brick, bricks of the first range, bricks of the second range}
     int second_first = 0;
+    if (s->range_count > 0) { ranges[0][0] = s->range_first * layer; ranges[0][1] = s->range_count * layer; }
     if (halo && c->nranks > 1) {
         CUDA_TRY(cudaEventRecord(c->ev_compute, c->stream));
         CUDA_TRY(cudaStreamWaitEvent(c->comm_stream, c->ev_compute, 0));
@@ -2128,6 +2139,108 @@ extern "C" int emdee_get_virials(emdee_system *s, double *out)
     if (!(s->last_bitmask & EMDEE_VIRIALS)) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_get_virials: the last compute did not select VIRIALS");
     EMDEE_TRY(check_device_flag(s, "emdee_get_virials"));
     return get1(s, s->vir, out, "emdee_get_virials");
+}
+
+// compute_nonbonded!(forces, energies, virials, ...) with HOST output arrays (src/nonbonded.jl:122-155): the evaluation of
+// emdee_compute_nonbonded followed by the getters of the selected outputs, as one call.  On one GPU with a cell grid and the
+// list kernels the box is evaluated in chunks of brick layers (z planes): list build and force kernel of chunk k+1 run while the
+// rows of chunk k travel to the host on a second stream.  The host arrays are id-ordered, a chunk's atoms are whatever the
+// binning put into its planes: their rows are found as occupied id buckets (runs of buckets = one copy each).  Where ids run
+// with z (lattices, most structure files) a chunk is one or two runs; if the buckets of all chunks add up to much more than N
+// rows (ids uncorrelated with position) the call falls back to one evaluation and three whole-array copies.
+#define INTO_BUCKETS 2048
+extern "C" int emdee_compute_nonbonded_into(emdee_system *s, int mode, int bitmask, double *forces, double *energies, double *virials)
+{
+    SYS_ENTER(s, "emdee_compute_nonbonded_into");
+    if ((bitmask & 7) == 0 || (bitmask & ~7)) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded_into: bitmask %d must combine FORCES|ENERGIES|VIRIALS", bitmask);
+    if (((bitmask & EMDEE_FORCES) && !forces) || ((bitmask & EMDEE_ENERGIES) && !energies) || ((bitmask & EMDEE_VIRIALS) && !virials))
+        EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_compute_nonbonded_into: null array for a selected output");
+    const GridDesc &g = s->g;
+    const char *pe = getenv("EMDEE_PIPE");
+    int want_chunks = pe ? atoi(pe) : 8;
+    const bool fast = want_chunks > 1 && mode == EMDEE_CUTOFF && c->nranks == 1 && s->has_model && s->has_atoms && s->has_pos && s->binned &&
+                      s->grid_ok && single_point_list(s) && (s->n14 == 0 || s->scale14 == 1.0) && g.zwrap && g.nbz >= 4 &&
+                      (s->ntypes > 0) == s->fc_typed && s->N >= 65536;
+    std::vector<std::pair<int64_t, int64_t>> runs[CHUNKS_MAX];      // per chunk: {first row, rows}
+    ChunkPlan plan = {};
+    int layer_bound[CHUNKS_MAX + 1];
+    bool piped = fast;
+    if (piped) {
+        const int nchunks = std::min(std::min(want_chunks, CHUNKS_MAX), g.nbz / 2);
+        plan.nchunks = nchunks;
+        for (int k = 0; k <= nchunks; k++) {
+            layer_bound[k] = (int)((int64_t)g.nbz * k / nchunks);
+            plan.cell_bound[k] = std::min(layer_bound[k] * g.bz, g.M) * g.M * g.M;
+        }
+        // rows of every chunk as runs of occupied id buckets (one small kernel, one read-back)
+        EMDEE_TRY(ensure_tmp(s, sizeof(double) * 5 * s->N + (size_t)CHUNKS_MAX * INTO_BUCKETS));
+        unsigned char *occ_d = reinterpret_cast<unsigned char *>(s->tmp + 5 * s->N);
+        CUDA_TRY(cudaMemsetAsync(occ_d, 0, (size_t)nchunks * INTO_BUCKETS, c->stream));
+        LAUNCH_1D(c, k_chunk_id_buckets, s->N, s->N, plan, s->cell_start, A.id, s->N, INTO_BUCKETS, occ_d);
+        std::vector<unsigned char> occ((size_t)nchunks * INTO_BUCKETS);
+        CUDA_TRY(cudaMemcpyAsync(occ.data(), occ_d, occ.size(), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        EMDEE_TRY(check_launch("k_chunk_id_buckets"));
+        auto lo_of = [&](int64_t b) { return (b * s->N + INTO_BUCKETS - 1) / INTO_BUCKETS; };     // bucket b holds ids [lo_of(b), lo_of(b + 1))
+        int64_t total = 0;
+        for (int k = 0; k < nchunks; k++) {
+            const unsigned char *o = occ.data() + (size_t)k * INTO_BUCKETS;
+            for (int b = 0; b < INTO_BUCKETS;) {
+                if (!o[b]) { b++; continue; }
+                int e = b;
+                while (e < INTO_BUCKETS && o[e]) e++;
+                runs[k].push_back({lo_of(b), lo_of(e) - lo_of(b)});
+                total += lo_of(e) - lo_of(b);
+                b = e;
+            }
+        }
+        if (total > s->N + s->N / 2) piped = false;      // ids do not run with z: every chunk would copy most of the arrays
+    }
+    if (!piped) {
+        EMDEE_TRY(emdee_compute_nonbonded(s, mode, bitmask));
+        if (bitmask & EMDEE_FORCES) EMDEE_TRY(emdee_get_forces(s, forces));
+        if (bitmask & EMDEE_ENERGIES) EMDEE_TRY(emdee_get_energies(s, energies));
+        if (bitmask & EMDEE_VIRIALS) EMDEE_TRY(emdee_get_virials(s, virials));
+        return EMDEE_OK;
+    }
+    if (!c->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    while ((int)c->chunk_events.size() < plan.nchunks) {
+        cudaEvent_t e;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c->chunk_events.push_back(e);
+    }
+    double *tF = (bitmask & EMDEE_FORCES) ? s->tmp : nullptr, *tE = (bitmask & EMDEE_ENERGIES) ? s->tmp + 3 * s->N : nullptr,
+           *tW = (bitmask & EMDEE_VIRIALS) ? s->tmp + 4 * s->N : nullptr;
+    const bool build = !s->list_valid || s->list_n3;      // (a half list left by Newton's-third-law stepping is rebuilt in full form)
+    s->build_n3 = false;
+    int rc_ = EMDEE_OK;
+    for (int k = 0; k < plan.nchunks && rc_ == EMDEE_OK; k++) {
+        s->range_first = layer_bound[k];
+        s->range_count = layer_bound[k + 1] - layer_bound[k];
+        if (build) rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 1);
+        if (rc_ == EMDEE_OK) rc_ = run_cells(s, bitmask, false, nullptr, 0, false, 2);
+        if (rc_ != EMDEE_OK) break;
+        const int64_t est = std::max<int64_t>(1024, s->N / plan.nchunks);
+        k_get_chunk<<<(unsigned)ceil_div64(est, 256), 256, 0, c->stream>>>(s->cell_start, plan.cell_bound[k], plan.cell_bound[k + 1], A.id, s->f[0], s->f[1],
+                                                                           s->f[2], s->en, s->vir, tF, tE, tW);
+        c->launches++;
+        CUDA_TRY(cudaEventRecord(c->chunk_events[k], c->stream));
+        CUDA_TRY(cudaStreamWaitEvent(c->copy_stream, c->chunk_events[k], 0));
+        for (const auto &r : runs[k]) {
+            if (tF) CUDA_TRY(cudaMemcpyAsync(forces + 3 * r.first, tF + 3 * r.first, sizeof(double) * 3 * r.second, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (tE) CUDA_TRY(cudaMemcpyAsync(energies + r.first, tE + r.first, sizeof(double) * r.second, cudaMemcpyDeviceToHost, c->copy_stream));
+            if (tW) CUDA_TRY(cudaMemcpyAsync(virials + r.first, tW + r.first, sizeof(double) * r.second, cudaMemcpyDeviceToHost, c->copy_stream));
+        }
+    }
+    s->range_first = 0; s->range_count = 0;
+    if (rc_ != EMDEE_OK) { cudaStreamSynchronize(c->copy_stream); return rc_; }
+    if (build) s->list_valid = true;
+    s->last_mode = mode;
+    s->last_bitmask = bitmask;
+    s->forces_valid = (bitmask & EMDEE_FORCES) != 0;
+    CUDA_TRY(cudaStreamSynchronize(c->copy_stream));
+    EMDEE_TRY(check_launch("emdee_compute_nonbonded_into"));
+    return check_device_flag(s, "emdee_compute_nonbonded_into");      // (a list or brick overflow invalidates what was copied)
 }
 
 extern "C" int emdee_get_forces_range(emdee_system *s, int64_t id_first, int64_t count, double *out)
@@ -2574,10 +2687,7 @@ extern "C" int emdee_compute_nonbonded_host(int64_t N, const double *pos, double
     if (st == EMDEE_OK) st = emdee_set_positions(s, pos);
     if (st == EMDEE_OK && tiles) st = emdee_set_tiles(s, tiles, ntiles);
     if (st == EMDEE_OK && mode == EMDEE_CUTOFF) st = emdee_bin(s, ndiv);
-    if (st == EMDEE_OK) st = emdee_compute_nonbonded(s, mode, bitmask);
-    if (st == EMDEE_OK && (bitmask & EMDEE_FORCES)) st = emdee_get_forces(s, forces);
-    if (st == EMDEE_OK && (bitmask & EMDEE_ENERGIES)) st = emdee_get_energies(s, energies);
-    if (st == EMDEE_OK && (bitmask & EMDEE_VIRIALS)) st = emdee_get_virials(s, virials);
+    if (st == EMDEE_OK) st = emdee_compute_nonbonded_into(s, mode, bitmask, forces, energies, virials);
     emdee_system_destroy(s);
     emdee_destroy(c);
     return st;

@@ -29,6 +29,9 @@
 #ifndef FLP_NPROD
 #define FLP_NPROD 4
 #endif
+#ifndef FLP_ADV_W
+#define FLP_ADV_W 3          // atoms per producer thread in flight in the fused integrator
+#endif
 #ifndef FLP_MBAR
 #define FLP_MBAR 1           // hand-over of the staging buffers by mbarriers (0: named barriers, every consumer warp waits for the slowest)
 #endif
@@ -287,7 +290,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             unsigned dmax = 0;
             const bool push = VV && P2P && a.publish_epoch != 0 && a.vv_mode == 2;
             const long long peer_lo_first = push ? a.peer_info[0] : 0;       // the lower neighbour's first upper-ghost slot
-            constexpr int W = 3;                 // atoms per thread in flight: the chain home index -> slot -> data is pure latency
+            constexpr int W = FLP_ADV_W;         // atoms per thread in flight: the chain home index -> slot -> data is pure latency
             for (int h00 = 0; h00 < vnh; h00 += W * PN) {
                 int slot[W];
                 bool ok[W];

@@ -155,6 +155,41 @@ __global__ void k_id_buckets(int64_t first, int64_t cnt, const int32_t *__restri
     occupied[(int64_t)id[first + k] * nbuckets / N] = 1;
 }
 
+// ---- results of a single-point evaluation leaving in chunks of z planes (emdee_compute_nonbonded_into) ---------------------------
+// A chunk is the slot range of the cells [cell_bound[k], cell_bound[k + 1]) (z is the slowest digit of the cell index, so a range of
+// planes is one contiguous slot range); its atoms' rows of the id-ordered arrays are marked in `nbuckets` equal id ranges.
+#define CHUNKS_MAX 32
+struct ChunkPlan {
+    int nchunks;
+    int cell_bound[CHUNKS_MAX + 1];
+};
+__global__ void k_chunk_id_buckets(int64_t n, ChunkPlan plan, const int32_t *__restrict__ cell_start, const int32_t *__restrict__ id,
+                                   int64_t N, int nbuckets, unsigned char *__restrict__ occupied)
+{
+    __shared__ int bound[CHUNKS_MAX + 1];
+    if (threadIdx.x <= plan.nchunks) bound[threadIdx.x] = cell_start[plan.cell_bound[threadIdx.x]];
+    __syncthreads();
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = 0;
+    while (k + 1 < plan.nchunks && i >= bound[k + 1]) k++;
+    occupied[(int64_t)k * nbuckets + (int64_t)id[i] * nbuckets / N] = 1;
+}
+// slot order -> id order for the atoms of cells [c0, c1): forces as N x 3 rows, energies, virials (null: not wanted)
+__global__ void k_get_chunk(const int32_t *__restrict__ cell_start, int c0, int c1, const int32_t *__restrict__ id,
+                            const double *__restrict__ f0, const double *__restrict__ f1, const double *__restrict__ f2,
+                            const double *__restrict__ en, const double *__restrict__ vir, double *__restrict__ outF,
+                            double *__restrict__ outE, double *__restrict__ outW)
+{
+    const int64_t first = cell_start[c0], n = cell_start[c1] - first;
+    for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = first + k, g = id[i];
+        if (outF) { outF[3 * g] = f0[i]; outF[3 * g + 1] = f1[i]; outF[3 * g + 2] = f2[i]; }
+        if (outE) outE[g] = en[i];
+        if (outW) outW[g] = vir[i];
+    }
+}
+
 template <typename T>
 __global__ void k_set1(int64_t first, int64_t n, const int32_t *__restrict__ id, const T *__restrict__ in,
                        int stride, int off, T *__restrict__ d)

@@ -104,6 +104,12 @@ int emdee_get_cell_order(emdee_system *sys, int32_t *perm_N, int32_t *cell_start
  * mode EMDEE_CUTOFF needs emdee_bin first; EMDEE_ALLPAIRS_REFERENCE uses the tile list set by
  * emdee_set_tiles (default: nonbonded_computation_tiles(N), src/nonbonded.jl:18-26). */
 int emdee_compute_nonbonded(emdee_system *sys, int mode, int bitmask);
+/* The same evaluation with the reference's output arguments: compute_nonbonded!(forces, energies, virials, ...) fills three
+ * HOST arrays in id order (src/nonbonded.jl:122-155; forces N rows of 3, row-major).  Equivalent to emdee_compute_nonbonded
+ * followed by emdee_get_forces / _energies / _virials for the outputs `bitmask` selects (the other pointers may be NULL), but on
+ * one GPU the box is evaluated in chunks of z planes and the rows of a finished chunk travel to the host while the next chunk
+ * computes (falls back to the plain sequence when atom ids do not run with z, or EMDEE_PIPE=0).  Synchronous. */
+int emdee_compute_nonbonded_into(emdee_system *sys, int mode, int bitmask, double *forces_Nx3, double *energies_N, double *virials_N);
 int emdee_set_tiles(emdee_system *sys, const int32_t *tiles_2xT, int64_t ntiles);
 int emdee_get_positions(emdee_system *sys, double *pos_3xN);
 int emdee_get_velocities(emdee_system *sys, double *vel_3xN);

@@ -116,6 +116,12 @@ bin!(s::NonbondedSystem, ndiv::Integer=2) =
     check(ccall((:emdee_bin, libemdee), Cint, (Ptr{Cvoid}, Cint), s.handle, ndiv))
 compute!(s::NonbondedSystem, mode::Integer, bitmask::Integer) =
     check(ccall((:emdee_compute_nonbonded, libemdee), Cint, (Ptr{Cvoid}, Cint, Cint), s.handle, mode, bitmask))
+# the reference's call shape on a device-resident system: evaluation + the selected outputs into host arrays, as one call
+# (on one GPU the rows of a finished chunk of z planes travel to the host while the next chunk computes)
+compute_into!(forces::Matrix{Float64}, energies::Vector{Float64}, virials::Vector{Float64}, s::NonbondedSystem,
+              mode::Integer, bitmask::Integer) =
+    check(ccall((:emdee_compute_nonbonded_into, libemdee), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Cdouble}, Ptr{Cdouble}, Ptr{Cdouble}),
+                s.handle, mode, bitmask, forces, energies, virials))
 get_forces!(out::Matrix{Float64}, s::NonbondedSystem) =
     check(ccall((:emdee_get_forces, libemdee), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.handle, out))
 get_energies!(out::Vector{Float64}, s::NonbondedSystem) =

@@ -207,6 +207,48 @@ def test_cutoff_fcc(em, oracle, n, ndiv):
     s.close()
 
 
+@pytest.mark.parametrize("ids", ["with_z", "shuffled"])
+def test_compute_into_host_arrays(em, oracle, ids, monkeypatch):
+    """compute_nonbonded!(forces, energies, virials, ...) with host output arrays as one call (emdee_compute_nonbonded_into):
+    chunks of z planes are evaluated and copied out one behind the other when ids run with z, the plain sequence runs when
+    they do not -- both against the oracle and bit for bit against compute + getters; then a subset of the outputs on a valid
+    list, and the pipeline switched off."""
+    pos, L = em.workloads.fcc_lattice(28)                # N = 87,808: M = 18 planes of edge 2.5, 9 brick layers
+    N = pos.shape[0]
+    if ids == "shuffled":
+        pos = pos[np.random.default_rng(5).permutation(N)]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    ref = oracle.cutoff_cells(pos, L, 2.5, 2.0, atoms, ndiv=1, fast=True)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(1)
+    f = np.full((N, 3), np.nan); e = np.full(N, np.nan); w = np.full(N, np.nan)
+    n0 = s.ctx.launch_count()
+    s.compute_into(em.CUTOFF, 7, f, e, w)
+    launches = s.ctx.launch_count() - n0
+    assert (launches >= 3 * 4) == (ids == "with_z"), launches       # build + forces + un-permute per chunk, or three launches in all
+    check_efw((f, e, w), (ref["forces"], ref["energies"], ref["virials"]), "compute_into vs oracle")
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    E, W, _ = s.totals(pairs=False)
+    assert abs(E - ref["E"]) <= E_TOL * abs(ref["E"]) and abs(W - ref["W"]) <= E_TOL * abs(ref["W"])
+    # the list is valid now: forces only, into a Fortran-ordered 3 x N array; energies and virials are left alone
+    fF = np.zeros((3, N), order="F"); e2 = e.copy()
+    s.compute_into(em.CUTOFF, em.FORCES, fF, None, None)
+    assert np.array_equal(fF.T, f) and np.array_equal(e2, e)
+    with pytest.raises((em.EmDeeError, TypeError)):
+        s.compute_into(em.CUTOFF, em.FORCES | em.ENERGIES, fF, None, None)      # a selected output without an array
+    s.close()
+    # the plain sequence gives the same bits
+    monkeypatch.setenv("EMDEE_PIPE", "0")
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.bin(1)
+    f1 = np.zeros((N, 3)); e1 = np.zeros(N); w1 = np.zeros(N)
+    s.compute_into(em.CUTOFF, 7, f1, e1, w1)
+    assert np.array_equal(f1, f) and np.array_equal(e1, e) and np.array_equal(w1, w)
+    s.compute(em.CUTOFF, 7)
+    assert np.array_equal(s.forces(), f) and np.array_equal(s.energies(), e) and np.array_equal(s.virials(), w)
+    s.close()
+
+
 def test_config1_both_modes(em, oracle):
     """Config 1 checked in ALLPAIRS_REFERENCE mode as well."""
     pos, L = em.workloads.fcc_lattice(10)
