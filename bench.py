@@ -477,6 +477,7 @@ def run_b200(args):
     s.vv_step(args.dt, args.warmup, args.rebin_every)
     barrier()
     launches0 = ctx.launch_count()
+    sc0 = s.step_counters()
     s.profile_begin()
     sampler.mark()
     wall0 = time.perf_counter()
@@ -487,6 +488,8 @@ def run_b200(args):
     wall = time.perf_counter() - wall0
     sampler.mark()
     force_ms, force_launches = s.profile_end()
+    sc1 = s.step_counters()
+    list_modes = {k: sc1[k] - sc0[k] for k in ("walk", "prune", "replay")}     # stepping launches by list mode (two-level list)
     kinds = [s.profile_kind(k) for k in range(3)]          # (ms, launches): window scan, list build, list walk
     dom = 2 if kinds[2][1] > 0 else 0                       # the stepping kernel; systems that cannot use a list scan windows
     dom_ms, dom_launches = kinds[dom]
@@ -518,7 +521,8 @@ def run_b200(args):
     step_bytes = nloc * (force_bytes + BYTES_VV) + nloc * BYTES_REBIN * rebins / args.steps
     traffic = None
     try:      # DRAM bytes per launch of the dominant kernel from the committed ncu capture (same workload, 1 GPU)
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        prof = json.load(open(tp if os.path.exists(tp) else os.path.join(ROOT, "profiles", "r1_traffic.json")))
         if world == 1 and prof.get("workload") == args.workload and dom == 2:
             traffic = prof["dram_bytes_per_launch"]
     except (OSError, ValueError, KeyError):
@@ -530,7 +534,8 @@ def run_b200(args):
         "flops_per_pair": FLOPS_PER_PAIR, "pairs_per_launch": pairs_local, "ms_per_launch": force_ms_per_launch,
         "launches_timed": dom_launches, "kernel_share_of_step": dom_ms / ms if ms > 0 else None,
         "kernel_also_does": ("the velocity-Verlet kick and drift of the step (fused into the producer warps; EMDEE_FUSE_VV=0 "
-                             "runs them as k_vv and the force kernel alone takes 1.22 ms)") if dom == 2 and cfg["fused_vv"] else None,
+                             "runs them as k_vv)") if dom == 2 and cfg["fused_vv"] else None,
+        "launches_by_list_mode": list_modes,
         "force_kernels_share_of_step": force_ms / ms if ms > 0 else None,
         "list_build": {"kernel": "k_list_build", "ms_per_launch": build_ms_per_launch, "launches_timed": kinds[1][1],
                        "share_of_step": kinds[1][0] / ms if ms > 0 else None},

@@ -77,6 +77,7 @@ SIGNATURES = {
     "emdee_get_cell_order": [_p, _p, _p],
     "emdee_compute_nonbonded": [_p, _i, _i],
     "emdee_compute_nonbonded_into": [_p, _i, _i, _p, _p, _p],
+    "emdee_get_step_counters": [_p, _p],
     "emdee_set_tiles": [_p, _p, _i64],
     "emdee_get_positions": [_p, _p],
     "emdee_get_velocities": [_p, _p],

@@ -361,6 +361,13 @@ class NonbondedSystem:
         return dict(brick=(int(o[0]), int(o[1]), int(o[2])), brick_capacity=int(o[3]), pair_list=bool(o[4]),
                     persistent=bool(o[5] & 1), tma=bool(o[5] & 2), fused_vv=bool(o[6]), list_chunks=int(o[7]))
 
+    def step_counters(self):
+        """Counters of the fused stepping loop: re-binnings, and stepping launches by list mode (full walk, prune, replay of the
+        inner list)."""
+        o = np.zeros(4, dtype=np.int64)
+        call("emdee_get_step_counters", self._h, _ptr(o))
+        return dict(rebins=int(o[0]), walk=int(o[1]), prune=int(o[2]), replay=int(o[3]))
+
     def scale_velocities(self, factor):
         call("emdee_scale_velocities", self._h, float(factor))
 

@@ -202,6 +202,18 @@ struct emdee_system {
     // TMA staging of the persistent kernel (opt-in, EMDEE_TMA=1; the default is the recipe gathers, which measure faster:
     // profiles/README.md): per-brick segment table written by k_list_build, raw ring sized from the longest staged row
     bool want_tma = false, fl_tma = false;
+    // two-level list of the fused stepping kernel (k_force_list_p<..., LM>): inner list logged by a prune step, replayed after it
+    uint4 *inner8 = nullptr;
+    int *inner_n = nullptr;
+    int64_t inner_slots = 0;
+    int inner_lcap8 = 0;
+    double skin2 = 0.0;                       // inner skin (EMDEE_SKIN2, e.g. 0.12; 0: off -- the default: measured, it does not pay at the
+                                              // bench's state point: a replay launch takes 1.10 ms, a prune launch 1.39 ms, a plain walk 1.19 ms)
+    int lm = 0;                               // mode of the next stepping launch: 0 plain walk, 1 prune, 2 replay
+    uint64_t list_gen = 0, inner_gen = 0;     // the inner list is a subset of the list of generation inner_gen
+    int steps_since_prune = 0;
+    bool inner_at_current = false;            // the last stepping launch pruned or replayed at the positions the system still has
+    int64_t counters[4] = {0, 0, 0, 0};       // re-binnings, stepping launches: plain, prune, replay (emdee_get_step_counters)
     int4 *seg = nullptr;
     int64_t seg_cap_total = 0;
     int segcap = 0, raw_rows = 0, rawlen = 0, fc_rowmax = 0, pre_rowmax = 0;
@@ -485,6 +497,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_FUSE_VV")) s->fuse_vv = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_N3")) s->want_n3 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_TMA")) s->want_tma = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_SKIN2")) s->skin2 = std::max(0.0, atof(e));
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -499,7 +512,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     A(dev_alloc(&s->slot_of_id, N));
     A(dev_alloc(&s->order, s->cap));
     A(dev_alloc(&s->src_of_new, s->cap));
-    A(dev_alloc(&s->maxd2, 2));
+    A(dev_alloc(&s->maxd2, 4));              // [0] since the binning, [1] its max over ranks, [2] largest step since the last prune step
     A(dev_alloc(&s->brick_counter, 4));      // [0] brick cursor of the persistent kernel, [1], [2] boundary bricks advanced (peer halos)
     A(dev_alloc(&s->digest, 16));        // [0..3] audit digest + pair counter, [8..15] role timers of FLP_TIMING builds
     A(dev_alloc(&s->err, 1));
@@ -562,6 +575,7 @@ extern "C" int emdee_system_destroy(emdee_system *s)
     dev_free(s->slot_of_id); dev_free(s->order); dev_free(s->src_of_new);
     dev_free(s->count); dev_free(s->cell_start); dev_free(s->fill); dev_free(s->block_sum);
     dev_free(s->ljtab); dev_free(s->digest); dev_free(s->maxd2); dev_free(s->brick_counter);
+    dev_free(s->inner8); dev_free(s->inner_n);
     for (int k = 0; k < 3; k++) dev_free(s->s_alt[k]);
     dev_free(s->err); dev_free(s->maxpop); dev_free(s->brick_max); dev_free(s->tiles); dev_free(s->tmp);
     for (int k = 0; k < 5; k++) dev_free(s->aud[k]);
@@ -682,6 +696,7 @@ extern "C" int emdee_set_positions(emdee_system *s, const double *pos)
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     s->has_pos = true;
     s->binned = false;        // cells must be rebuilt (update_cells!, src/cells.jl:196)
+    s->inner_at_current = false;
     s->forces_valid = false;
     s->kick_pending = false;
     return check_launch("set_positions");
@@ -768,6 +783,7 @@ extern "C" int emdee_set_positions_range(emdee_system *s, int64_t id_first, int6
     EMDEE_TRY(window_flag(s, "emdee_set_positions_range"));
     s->has_pos = true;
     s->binned = false;
+    s->inner_at_current = false;
     s->forces_valid = false;
     s->kick_pending = false;
     return check_launch("set_positions_range");
@@ -1186,6 +1202,7 @@ static int choose_bricks(emdee_system *s)
 static int do_bin(emdee_system *s, int ndiv)
 {
     emdee_ctx *c = s->ctx;
+    s->inner_at_current = false;
     AtomArrays &A = s->A[s->cur];
     // cells_per_dimension(L, cutoff, ndiv) = floor(Int32, ndiv*L/cutoff), src/cells.jl:36 (cutoff + skin here)
     const double Mf = std::floor((double)ndiv * s->L / (s->cutoff + s->skin));
@@ -1672,8 +1689,13 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
     if (!COUNT && !EW && s->vv_mode != 0) {
         if (n3) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, true>;
         else if (tma) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, false, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, false, true>;
+        else if (s->lm == 1 && !s->p2p_launch) kern = k_force_list_p<MULTI, false, 2, false, true, true, false, false, false, 1>;
+        else if (s->lm == 2 && !s->p2p_launch) kern = k_force_list_p<MULTI, false, 2, false, true, true, false, false, false, 2>;
         else kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
-    } else if (tma && !COUNT && EW && s->fl_fuse)
+        s->counters[(n3 || tma || s->p2p_launch) ? 1 : 1 + s->lm]++;
+    } else if (COUNT && !EW && s->lm == 2)       // the audit counts through the inner list when the stepping kernel would replay it
+        { kern = k_force_list_p<MULTI, true, 2, false, true, false, false, false, false, 2>; tma = false; }
+    else if (tma && !COUNT && EW && s->fl_fuse)
         kern = k_force_list_p<MULTI, false, 2, true, true, false, false, false, true>;
     else
         tma = false;
@@ -1694,6 +1716,7 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
         for (int k = 0; k < 3; k++) { ac.vv_v[k] = A.v[k]; ac.vv_r[k] = A.r[k]; ac.vv_snew[k] = s->s_alt[k]; ac.vv_rb[k] = A.rb[k]; }
         ac.vv_mass = A.mass;
         ac.vv_maxd2 = s->vv_track ? s->maxd2 : nullptr;
+        ac.vv_maxstep = s->vv_track ? s->maxd2 + 2 : nullptr;
         ac.vv_check_skin = s->vv_check_skin;
         if (s->p2p_launch) {
             emdee_ctx *c = s->ctx;
@@ -1857,6 +1880,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         auto thr16 = [&](double rcut) { return fp16_threshold(hext, rcut); };
         a.rc2h = thr16(s->cutoff);
         a.rl2h = thr16(s->cutoff + s->skin);
+        a.rp2h = thr16(s->cutoff + std::min(s->skin2, s->skin));
     }
     if (mode != 0) {
         if (audit) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: the pair-list kernels do not audit");
@@ -1892,6 +1916,16 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
             EMDEE_TRY(dev_alloc(&s->brickhdr, (size_t)2 * s->hdr_cap));
         }
         a.recipe = s->recipe; a.homeidx = s->homeidx; a.brickhdr = s->brickhdr; a.rcap = s->fc_cap + 1;
+        if ((mode == 2 || mode == 3) && s->lm != 0) {
+            if (s->inner_slots < s->list_slots || s->inner_lcap8 != s->lcap8) {
+                if (s->lm == 2) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: no inner list to replay");
+                dev_free(s->inner8); dev_free(s->inner_n);
+                s->inner_slots = s->list_slots; s->inner_lcap8 = s->lcap8;
+                EMDEE_TRY(dev_alloc(&s->inner8, (size_t)s->inner_slots * s->lcap8 * 32));
+                EMDEE_TRY(dev_alloc(&s->inner_n, (size_t)s->inner_slots));
+            }
+            a.inner8 = s->inner8; a.inner_n = s->inner_n;
+        }
         if (s->fl_tma) {
             const int64_t sneed = (int64_t)s->fc_nblocks * s->segcap;
             if (sneed > s->seg_cap_total) {
@@ -1976,7 +2010,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         }
     }
     if (pe1) CUDA_TRY(cudaEventRecord(pe1, c->stream));
-    if (mode == 1) { s->list_n3 = s->build_n3; s->build_n3 = false; }
+    if (mode == 1) { s->list_n3 = s->build_n3; s->build_n3 = false; s->list_gen++; }
     return EMDEE_OK;
 }
 
@@ -2370,7 +2404,11 @@ extern "C" int emdee_list_pair_count(emdee_system *s, int64_t *npairs)
     if (!list_capable(s)) return EMDEE_OK;
     if (!s->list_valid) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_list_pair_count: no valid pair list (call emdee_vv_step first)");
     CUDA_TRY(cudaMemsetAsync(s->digest, 0, 4 * sizeof(unsigned long long), c->stream));
-    EMDEE_TRY(run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 3));
+    // (what the stepping kernel walked last: the inner list if the last launch pruned into it or replayed it at these positions)
+    s->lm = s->inner_at_current && s->inner_gen != 0 && s->inner_gen == s->list_gen && s->fl_persistent ? 2 : 0;
+    const int rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 3);
+    s->lm = 0;
+    EMDEE_TRY(rc_);
     unsigned long long n = 0;
     CUDA_TRY(cudaMemcpyAsync(&n, s->digest, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -2427,6 +2465,14 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
         for (int k = 0; k < 3; k++)
             if (!s->s_alt[k]) EMDEE_TRY(dev_alloc(&s->s_alt[k], (size_t)s->cap + 2));
         bool drifted = false;
+        // two-level list: with the per-step read-back of the adaptive re-binning the host also knows the largest step any atom has
+        // taken since the last prune step, so it can let the kernel replay the inner list while no atom can have moved skin2 / 2
+        // (steps since the prune x largest step), and ask for a new prune step otherwise.  The first step of a call drifts in
+        // k_vv (not tracked): it prunes.
+        const bool inner_ok = adaptive1 && c->nranks == 1 && s->skin2 > 0 && s->skin2 < s->skin && !s->want_n3 && !s->want_tma;
+        s->inner_gen = 0;
+        s->inner_at_current = false;
+        float step2max = 0.0f;
         const char *ue = getenv("EMDEE_DEBUG_UNFUSE_AT");
         const int64_t unfuse_at = ue ? atoll(ue) : -1;
         for (int64_t st = 0; st < nsteps; st++) {
@@ -2438,16 +2484,17 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 s->ghost_state = 1;        // slab: the neighbours' atoms moved too
             }
             if (adaptive1 && !rebin) {
-                unsigned bits = 0;
-                CUDA_TRY(cudaMemcpyAsync(&bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
+                unsigned bits[3] = {0, 0, 0};
+                CUDA_TRY(cudaMemcpyAsync(bits, s->maxd2, sizeof(bits), cudaMemcpyDeviceToHost, c->stream));
                 CUDA_TRY(cudaStreamSynchronize(c->stream));
                 float d2max;
-                memcpy(&d2max, &bits, 4);
+                memcpy(&d2max, &bits[0], 4);
+                memcpy(&step2max, &bits[2], 4);
                 rebin = (double)d2max > 0.25 * s->skin * s->skin;
             }
             s->kick_pending = false;
             s->steps_since_bin++;
-            if (rebin) EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv));      // (a slab re-binning also refreshes the ghosts)
+            if (rebin) { EMDEE_TRY(c->nranks > 1 ? do_bin_slab(s, s->ndiv) : do_bin(s, s->ndiv)); s->counters[0]++; }      // (a slab re-binning also refreshes the ghosts)
             if (!(list_capable(s) && s->fl_persistent) || (rebin && st > 0 && st == unfuse_at)) {
                 // the re-binning chose bricks whose two staging buffers no longer fit (denser cells): this step's atoms are
                 // already kicked, drifted and re-binned, so evaluate its forces with the generic path and carry on there
@@ -2475,10 +2522,26 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 s->epoch++;
                 s->p2p_publish = (!last && !next_rebin) ? s->epoch : 0;     // a re-binning exchanges the ghosts itself
             }
+            s->lm = 0;
+            if (inner_ok && !s->list_n3 && !s->fl_tma) {
+                const bool have = s->inner_gen != 0 && s->inner_gen == s->list_gen && s->steps_since_prune >= 1;
+                const double moved = (double)s->steps_since_prune * std::sqrt((double)step2max) * (1.0 + 1e-6);
+                s->lm = have && moved <= 0.5 * s->skin2 ? 2 : 1;
+                if (const char *e = getenv("EMDEE_DEBUG_LM")) {      // timing experiments only: 2 replays a stale inner list (wrong forces), 1 prunes on every step
+                    if (atoi(e) == 2 && have) s->lm = 2;
+                    if (atoi(e) == 1) s->lm = 1;
+                }
+                if (s->lm == 1) CUDA_TRY(cudaMemsetAsync(s->maxd2 + 2, 0, sizeof(unsigned), c->stream));
+            }
+            const int lm_ = s->lm;
             const int rc_ = run_cells(s, EMDEE_FORCES, false, nullptr, 0, false, 2);
             s->vv_mode = 0;
             s->p2p_launch = false;
+            s->lm = 0;
             EMDEE_TRY(rc_);
+            if (lm_ == 1) { s->inner_gen = s->list_gen; s->steps_since_prune = 0; }
+            if (lm_ != 0 && !last) s->steps_since_prune++;
+            s->inner_at_current = lm_ != 0 && last;
             if (slab_fused) s->ghost_state = s->p2p_publish ? 2 : (last ? 0 : 1);
             if (!last) {
                 AtomArrays &Ac = s->A[s->cur];
@@ -2553,6 +2616,14 @@ extern "C" int emdee_scale_velocities(emdee_system *s, double factor)
     if (s->kick_pending) EMDEE_FAIL(EMDEE_ERR_STATE, "emdee_scale_velocities: a half-kick is pending (call between emdee_vv_step calls)");
     LAUNCH_1D(c, k_scale3, s->nown, s->nlo, s->nown, factor, A.v[0], A.v[1], A.v[2]);
     return check_launch("k_scale3");
+}
+
+extern "C" int emdee_get_step_counters(emdee_system *s, int64_t out[4])
+{
+    SYS_ENTER(s, "emdee_get_step_counters");
+    if (!out) EMDEE_FAIL(EMDEE_ERR_INVALID, "emdee_get_step_counters: null output");
+    for (int k = 0; k < 4; k++) out[k] = s->counters[k];
+    return EMDEE_OK;
 }
 
 extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])

@@ -76,6 +76,12 @@ struct CellArgs {
     LJFast fast;
     float rc2h;                       // k_force_list: FP16 pre-cull threshold (conservative, set by the host)
     float rl2h;                       // k_list_build: FP16 threshold of the list, (rc + skin)^2 + rounding bound
+    // two-level list of k_force_list_p (LM): the inner list of a warp task -- the rows a prune step drained, in the layout of list8
+    // (chunk c of lane l: inner8[((brick*gmax + group)*lcap8 + c)*32 + l]) -- its chunks per task, the prune step's FP16 threshold
+    uint4 *inner8;
+    int *inner_n;
+    float rp2h;
+    unsigned *vv_maxstep;             // fused integrator: max over atoms of |r(n+1) - r(n)|^2 (float bits; the host resets it at a prune step)
     // staging recipe, written by k_list_build and valid until the next re-binning (the persistent kernel stages from it
     // instead of rebuilding the cell table on every step):
     int2 *recipe;                     // recipe[brick*rcap + i], i = staged index + 1: {global slot, cx | cy<<8 | cz<<16}

@@ -224,10 +224,18 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // table of every brick behind.  Row groups are copied into a two-slot ring of raw scaled coordinates ahead of time -- also
 // across bricks, before the consumers have released the buffer -- and what remains on the hand-over's critical path is the
 // shared-to-shared pass into the brick's frame (FP64 + FP16 copies).  No staging recipe is read.
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false, bool TMA = false>
+// LM (two-level list, GROMACS calls it dynamic pruning): the list built at a re-binning holds every pair inside rc + skin (~85
+// entries per atom at skin 0.45, 54 of them inside rc), and walking it costs an FP16 test per entry on every step.  LM = 1 (a
+// "prune" step) walks it with the FP16 threshold of rc + skin2 (skin2 << skin) and logs every stack entry it drains -- the
+// survivors, in drain order, padded with dummies where a lane's stack ran dry -- as the INNER list of the warp task: the same
+// number of rows for every lane, so it is written as coalesced 16-byte chunks.  LM = 2 replays that log on the following steps:
+// no FP16 test, no stack, one gather and the pair arithmetic per row.  The host switches back to LM = 1 before an atom can have
+// moved skin2 / 2 since the prune step (emdee_vv_step), so the evaluated pair set stays the oracle's on every step.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false, bool TMA = false, int LM = 0>
 __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
+    static_assert(LM == 0 || (ILP == 4 && FUSE && !N3 && !EW && (LM == 2 || !COUNT)), "the two-level list is a variant of the fused stepping kernel");
     constexpr int QCAP = NBUF >= 3 ? 24 : FL_QCAP;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
@@ -287,7 +295,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         for (int q = 0; q < NBUF; q++) { held_bid[q] = -1; held_nh[q] = 0; }
         auto advance_atoms = [&](int vbid, int vnh) {
             const int2 *vrecipe = a.recipe + (size_t)vbid * a.rcap;
-            unsigned dmax = 0;
+            unsigned dmax = 0, smax = 0;
             const bool push = VV && P2P && a.publish_epoch != 0 && a.vv_mode == 2;
             const long long peer_lo_first = push ? a.peer_info[0] : 0;       // the lower neighbour's first upper-ghost slot
             constexpr int W = FLP_ADV_W;         // atoms per thread in flight: the chain home index -> slot -> data is pure latency
@@ -314,7 +322,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 for (int u = 0; u < W; u++) {
                     if (!ok[u]) continue;
                     const double hk = __ddiv_rn(0.5 * a.vv_dt, mass[u]);
-                    double d2 = 0;
+                    double d2 = 0, v2 = 0;
 #pragma unroll
                     for (int c3 = 0; c3 < 3; c3++) {
                         double v = __fma_rn(hk, f3[u][c3], v3[u][c3]);                // second half-kick of this step
@@ -331,16 +339,22 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                             }
                             const double d = r - rb3[u][c3];
                             d2 = fma(d, d, d2);
+                            v2 = fma(v, v, v2);
                         }
                         a.vv_v[c3][slot[u]] = v;
                     }
                     if (a.vv_mode == 2 && a.vv_check_skin && d2 > a.vv_half_skin2) atomicCAS(a.err, 0, 3);
                     dmax = max(dmax, __float_as_uint(__double2float_ru(d2)));
+                    smax = max(smax, __float_as_uint(__double2float_ru(v2 * a.vv_dt * a.vv_dt)));
                 }
             }
             if (a.vv_mode == 2 && a.vv_maxd2) {
                 dmax = __reduce_max_sync(0xffffffffu, dmax);
                 if (lane == 0 && dmax > *a.vv_maxd2) atomicMax(a.vv_maxd2, dmax);
+            }
+            if (a.vv_mode == 2 && a.vv_maxstep) {      // this step's drift: what the two-level list's prune cadence is decided on
+                smax = __reduce_max_sync(0xffffffffu, smax);
+                if (lane == 0 && smax > *a.vv_maxstep) atomicMax(a.vv_maxstep, smax);
             }
             if (push) {
                 // publish: when every brick holding atoms a neighbour needs has been advanced, raise that neighbour's flag
@@ -538,6 +552,11 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 for (int t = tid; t < ng * 8; t += PN) {      // 2 chunks x 512 B = 8 lines of 128 B per group
                     const size_t gs = (size_t)bid * a.gmax + (t >> 3);
                     const int part = t & 7;
+                    if (LM == 2) {
+                        if (part == 0 && (t >> 3) % 32 == 0) prefetch_l2(a.inner_n + gs);
+                        prefetch_l2(reinterpret_cast<const unsigned char *>(a.inner8 + gs * a.lcap8 * 32) + part * 128);
+                        continue;
+                    }
                     if (part == 0) prefetch_l2(a.list_n + gs * 32);
                     prefetch_l2(reinterpret_cast<const unsigned char *>(a.list8 + gs * a.lcap8 * 32) + part * 128);
                 }
@@ -636,7 +655,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 
     // ================================ consumers ================================
     const int ctid = tid - FLP_NPROD * 32;
-    const __half thr = __float2half_ru(a.rc2h);
+    const __half thr = __float2half_ru(LM == 1 ? a.rp2h : a.rc2h);      // (a prune step keeps what lies inside rc + skin2)
     const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
     unsigned long long npair = 0;
     double sig2_0 = 0, tt_0 = 0;
@@ -646,6 +665,14 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
     // entry count and first two chunks of (brick, group) into registers, the following chunks into L2
     auto request = [&](int bid_, int grp_) {
         const size_t gs = (size_t)bid_ * a.gmax + grp_;
+        if (LM == 2) {          // the inner list: chunks per task (the same for every lane), first two chunks
+            pre_n = a.inner_n[gs];
+            pre0 = a.inner8[gs * a.lcap8 * 32 + lane];
+            pre1 = a.inner8[(gs * a.lcap8 + 1) * 32 + lane];
+#pragma unroll
+            for (int k = 2; k < 2 + FL_AHEAD; k++) prefetch_l2(a.inner8 + (gs * a.lcap8 + k) * 32 + lane);
+            return;
+        }
         pre_n = a.list_n[gs * 32 + lane];
         pre0 = a.list8[gs * a.lcap8 * 32 + lane];
         pre1 = a.list8[(gs * a.lcap8 + 1) * 32 + lane];
@@ -701,10 +728,12 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             if (MULTI) ljrow = ljt + (int)ptyp[me] * a.ntypes;
             double fx = 0, fy = 0, fz = 0, e = 0, w = 0;
 
-            const int nent = pre_n;
-            const int nch = (nent + 7) >> 3;
-            const int nchmax = __reduce_max_sync(0xffffffffu, nch);
-            const uint4 *lp = a.list8 + ((size_t)bid * a.gmax + grp) * a.lcap8 * 32 + lane;
+            const size_t gs_task = (size_t)bid * a.gmax + grp;
+            // LM 2: pre_n counts the CHUNKS of the task's inner list (one count per task); else the entries of this lane's list
+            int nent = LM == 2 ? 0 : pre_n;
+            const int nch = LM == 2 ? pre_n : (nent + 7) >> 3;
+            const int nchmax = LM == 2 ? nch : __reduce_max_sync(0xffffffffu, nch);
+            const uint4 *lp = a.list8 + gs_task * a.lcap8 * 32 + lane;
             uint4 e0 = 0 < nch ? pre0 : zero4;
             uint4 e1 = 1 < nch ? pre1 : zero4;
             int cnt = 0;
@@ -737,11 +766,30 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             auto pair_eval = [&](int idx) {
                 const int j = queue[max(idx, -1) * FLP_QS + ctid];
                 pair_math(j, pxy[j], pz[j]);
+                return j;
+            };
+            // LM 1: the log of drained entries, four per call (the same number of calls in every lane); two calls make a chunk
+            uint4 lg = zero4;
+            bool lhalf = false;
+            int lchunk = 0;
+            uint4 *ip = LM == 1 ? a.inner8 + gs_task * a.lcap8 * 32 + lane : nullptr;
+            auto log4 = [&](int j0, int j1, int j2, int j3) {
+                const unsigned w0 = (unsigned)j0 | ((unsigned)j1 << 16), w1 = (unsigned)j2 | ((unsigned)j3 << 16);
+                if (!lhalf) { lg.x = w0; lg.y = w1; }
+                else {
+                    lg.z = w0; lg.w = w1;
+                    if (lchunk < a.lcap8) ip[(size_t)lchunk * 32] = lg;
+                    else atomicCAS(a.err, 0, 5);
+                    lchunk++;
+                }
+                lhalf = !lhalf;
             };
             auto drain = [&](int depth) {
                 for (int kk = 0; kk < depth; kk += ILP) {
+                    int jj[ILP];
 #pragma unroll
-                    for (int u = 1; u <= ILP; u++) pair_eval(cnt - u - kk);
+                    for (int u = 1; u <= ILP; u++) jj[u - 1] = pair_eval(cnt - u - kk);
+                    if (LM == 1) log4(jj[0], jj[1 % ILP], jj[2 % ILP], jj[3 % ILP]);
                 }
                 cnt = max(cnt - depth, 0);
                 qp = queue + cnt * FLP_QS + ctid;
@@ -756,7 +804,40 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
             };
 
-            for (int c = 0; c < nchmax; c++) {
+            int ngrp = 0;
+            if (LM == 2) {
+                // replay of the inner list: every row is a pair to evaluate (or the dummy atom); two groups of four per chunk
+                const uint4 *lp2 = a.inner8 + gs_task * a.lcap8 * 32 + lane;
+                const int claim_at = max(nch - 3, 0);       // this warp's next task is claimed (and its head requested) near the end
+                ngrp = ntask;
+                for (int c = 0; c < nch; c++) {
+                    const uint4 e2 = c + 2 < nch ? lp2[(size_t)(c + 2) * 32] : zero4;
+                    if (c + 2 + FL_AHEAD < nch) prefetch_l2(lp2 + (size_t)(c + 2 + FL_AHEAD) * 32);
+                    if (c == claim_at) {
+                        if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
+                        ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
+                        if (ngrp < ntask) request(bid, ngrp);
+                    }
+                    const unsigned q[8] = {e0.x & 0xffffu, e0.x >> 16, e0.y & 0xffffu, e0.y >> 16, e0.z & 0xffffu, e0.z >> 16, e0.w & 0xffffu, e0.w >> 16};
+                    EMDEE_CHECK((int)max(max(max(q[0], q[1]), max(q[2], q[3])), max(max(q[4], q[5]), max(q[6], q[7]))) < B.scal[1], a.err);
+#pragma unroll
+                    for (int hq = 0; hq < 8; hq += 4) {
+                        double2 jxy[4];
+                        double jz[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) { jxy[u] = pxy[q[hq + u]]; jz[u] = pz[q[hq + u]]; }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) pair_math((int)q[hq + u], jxy[u], jz[u]);
+                    }
+                    e0 = e1; e1 = e2;
+                }
+                if (nch == 0) {      // (a task without rows still has to claim)
+                    if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
+                    ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
+                    if (ngrp < ntask) request(bid, ngrp);
+                }
+            }
+            for (int c = 0; LM != 2 && c < nchmax; c++) {
                 const uint4 e2 = c + 2 < nch ? lp[(size_t)(c + 2) * 32] : zero4;
                 if (c + 2 + FL_AHEAD < nch) prefetch_l2(lp + (size_t)(c + 2 + FL_AHEAD) * 32);
                 const unsigned j0 = e0.x & 0xffffu, j1 = e0.x >> 16, j2 = e0.y & 0xffffu, j3 = e0.y >> 16;
@@ -779,6 +860,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
 #pragma unroll
                     for (int u = 0; u < ILP; u++) pair_math(pj[u], pxyj[u], pzj[u]);
+                    if (LM == 1) log4(pj[0], pj[1 % ILP], pj[2 % ILP], pj[3 % ILP]);
                 } else {
                     test(j0, h0); test(j1, h1); test(j2, h2); test(j3, h3);
                     test(j4, h4); test(j5, h5); test(j6, h6); test(j7, h7);
@@ -790,10 +872,12 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
             // claim this warp's next task of the brick and request its list head; the final drain hides the round trip.  (Claimed
             // at the START of a task, the first warps to reach a brick took two tasks each and left none for the others -- with the
             // mbarrier hand-over the warps arrive one by one -- so half the warps worked on each buffer and nothing was staged ahead.)
-            int ngrp = 0;
-            if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
-            ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
-            if (ngrp < ntask) request(bid, ngrp);
+            if (LM != 2) {
+                if (lane == 0) ngrp = atomicAdd(&B.scal[3], 1);
+                ngrp = __shfl_sync(0xffffffffu, ngrp, 0);
+            }
+            if (LM == 2) {}
+            else if (ngrp < ntask) request(bid, ngrp);
             else if (FLP_CARRY && FLP_MBAR && mbar_test(&hand_bar[(k + 1) % NBUF], ((k + 1) / NBUF) & 1)) {
                 const BrickBuf Bn = brick_buf(smem_raw + ((k + 1) % NBUF) * bufsz, a.cap, a.ncs_max, MULTI);
                 const int nbrick = Bn.scal[4];
@@ -803,7 +887,16 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                     if (carry < min((Bn.scal[0] + 31) >> 5, a.gmax)) request(FC_BRICK_OF(a, nbrick), carry);
                 }
             }
-            drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
+            if (LM != 2) drain((__reduce_max_sync(0xffffffffu, cnt) + ILP - 1) & ~(ILP - 1));
+            if (LM == 1) {      // the last chunk of the log, padded with dummies; rows of the task's inner list
+                if (lhalf) {
+                    lg.z = 0u; lg.w = 0u;
+                    if (lchunk < a.lcap8) ip[(size_t)lchunk * 32] = lg;
+                    else atomicCAS(a.err, 0, 5);
+                    lchunk++;
+                }
+                if (lane == 0) a.inner_n[gs_task] = min(lchunk, a.lcap8);
+            }
 
             if (N3 && tmin <= 2u) {
                 // pairs within 3e-6 of rc2 were left out by the hot loop (both sides): add the ones the oracle's decision keeps
@@ -831,6 +924,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
             }
             if (!N3 && tmin <= 2u) {     // this lane met a pair within 3e-6 of rc2: redo its list with the oracle's decision
+                if (LM == 2) nent = a.list_n[gs_task * 32 + lane];      // (the list of the last re-binning: a superset of the inner list)
                 LaneRedo rd;
                 rd.pxy = pxy; rd.pz = pz; rd.ptyp = ptyp; rd.ljt = ljt; rd.cs = nullptr; rd.gbase = nullptr; rd.recipe = recipe;
                 rd.ncs = 0; rd.ntypes = a.ntypes; rd.me = me; rd.slot_i = slot_i; rd.nent = nent;

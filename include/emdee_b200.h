@@ -152,6 +152,11 @@ int emdee_fp16_threshold(const double half_extent[3], double rcut, float *thresh
  * (0: never; < 0 with a skin: adaptively, on the first step on which an atom has moved more than skin/2 since the
  * last binning -- one 4-byte read-back per step, and a max over ranks in a slab decomposition).  Needs model, atoms, masses, velocities, one emdee_bin and one emdee_compute_nonbonded. */
 int emdee_vv_step(emdee_system *sys, double dt, int64_t nsteps, int rebin_every);
+/* Host-only counters of the fused stepping loop since the system was created: re-binnings, and stepping launches that walked
+ * the pair list in full, pruned it into the inner list (two-level list: the entries inside rc + skin2; opt-in with EMDEE_SKIN2=<skin2>, e.g. 0.12;
+ * off by default), or replayed the inner list.  The inner list is used by one-GPU runs with adaptive re-binning
+ * (rebin_every < 0): the per-step read-back tells the host when an atom may have moved skin2 / 2 since the last prune step. */
+int emdee_get_step_counters(emdee_system *sys, int64_t out[4]);
 int emdee_kinetic_energy(emdee_system *sys, double *K);
 /* v *= factor for every atom this rank owns: the device half of a velocity-rescaling thermostat (the reference has
  * none); the host computes the factor from emdee_kinetic_energy between emdee_vv_step calls. */

@@ -249,6 +249,41 @@ def test_compute_into_host_arrays(em, oracle, ids, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("skin2", ["0.12", "0.03", "0"])
+def test_two_level_list(em, oracle, skin2, monkeypatch):
+    """Two-level list of the fused stepping kernel (one GPU, adaptive re-binning): a prune step logs the list entries inside
+    rc + skin2 as the inner list, the following steps replay it until an atom may have moved skin2 / 2.  After a run that ended
+    on a replayed (or just pruned) inner list the evaluated pair count -- counted THROUGH the inner list -- and the forces equal
+    the oracle's at the same positions; skin2 = 0.03 prunes on almost every step, 0 (the library's default) leaves the second level off."""
+    monkeypatch.setenv("EMDEE_SKIN2", skin2)
+    pos, L = em.workloads.fcc_lattice(20)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 2.5, 2.0, atoms)
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_masses(np.ones(N))
+    s.set_skin(0.45)
+    s.bin(1)
+    s.compute(em.CUTOFF, em.FORCES)
+    c0 = s.step_counters()
+    for nsteps in (2, 3, 4, 26):                     # calls ending at different places of the prune / replay / re-binning cycle
+        s.vv_step(0.005, nsteps, rebin_every=-1)
+        s.synchronize()
+        ref = oracle.cutoff_cells(s.positions(), L, 2.5, 2.0, atoms, ndiv=1, bitmask=1, fast=True)
+        assert s.list_pair_count() == ref["npairs"], nsteps
+        assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"]), nsteps
+    c1 = s.step_counters()
+    walk, prune, replay = (c1[k] - c0[k] for k in ("walk", "prune", "replay"))
+    assert walk + prune + replay == 35 and c1["rebins"] - c0["rebins"] >= 2
+    if skin2 == "0":
+        assert prune == 0 and replay == 0
+    elif skin2 == "0.03":
+        assert walk == 0 and prune > replay
+    else:
+        assert walk == 0 and replay >= 15 and prune >= 8, (walk, prune, replay)
+    s.close()
+
+
 def test_config1_both_modes(em, oracle):
     """Config 1 checked in ALLPAIRS_REFERENCE mode as well."""
     pos, L = em.workloads.fcc_lattice(10)
