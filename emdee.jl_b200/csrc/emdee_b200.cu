@@ -180,6 +180,10 @@ struct emdee_system {
     int fl_block = 192;                       // block size of k_force_list
     bool fl_ilp8 = true;
     bool fl_persistent = false, want_persistent = true;   // k_force_list_p when two staging buffers fit in shared memory
+    // staged-atom capacity, stack depth and staging mode of the list kernels: with compaction (dense cells: the 27 cells around a
+    // one-cell brick do not fit twice) k_list_build keeps only the atoms within rc + skin of the home box, see CellArgs::compact
+    int fl_cap = 0, fl_qcap = FL_QCAP;
+    bool fl_compact = false, want_compact = true;
     bool fl_fuse = true;                                  // walk and drain share a basic block
     int reserve_sms = 0, nccl_sms = 4;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS).
                                                           // With bricks claimed dynamically every SM is busy until the launch ends, so NCCL's kernel would
@@ -498,6 +502,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_N3")) s->want_n3 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_TMA")) s->want_tma = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_SKIN2")) s->skin2 = std::max(0.0, atof(e));
+    if (const char *e = getenv("EMDEE_COMPACT")) s->want_compact = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -1001,6 +1006,31 @@ static int brick_capacity(emdee_system *s, int *cap_out, int *rowmax_out)
     *rowmax_out = mx[1];
     return check_launch("k_brick_max");
 }
+// the same for compacted staging: atoms within rc + skin of a brick's home box, largest count over all bricks
+static int brick_capacity_compact(emdee_system *s, int *cap_out)
+{
+    emdee_ctx *c = s->ctx;
+    GridDesc &g = s->g;
+    AtomArrays &A = s->A[s->cur];
+    CellArgs a = {};
+    a.g = g;
+    a.cell_start = s->cell_start;
+    a.sx = A.s[0]; a.sy = A.s[1]; a.sz = A.s[2];
+    a.L = s->L;
+    a.cell_edge = s->L / g.M;
+    const double rl = s->cutoff + s->skin;
+    a.keep2 = rl * rl * (1.0 + 1e-6);
+    a.block_split = 0x7fffffff; a.block_split2 = 0x7fffffff;
+    CUDA_TRY(cudaMemsetAsync(s->brick_max, 0, 2 * sizeof(int), c->stream));
+    const int nb = g.nbx * g.nby * g.nbz;
+    k_brick_keep_max<<<nb, 256, 0, c->stream>>>(a, s->brick_max);
+    c->launches++;
+    int mx = 0;
+    CUDA_TRY(cudaMemcpyAsync(&mx, s->brick_max, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *cap_out = mx >= (1 << 30) ? 1 << 30 : std::max(64, (mx + 4) & ~3);
+    return check_launch("k_brick_keep_max");
+}
 static void set_brick_shape(emdee_system *s, const int sh[3])
 {
     GridDesc &g = s->g;
@@ -1048,8 +1078,31 @@ static int choose_bricks(emdee_system *s)
         }
         return 0;
     };
-    auto finish = [&](int cap, int block, int lblock, int rowmax) -> int {
+    // Do two staging buffers of the persistent list kernel fit?  As they are; or, as a last resort (allow_compact: no brick shape
+    // fits otherwise -- dense cells), with shallower per-lane stacks, then (one GPU, no TMA / Newton's-third-law variant) with
+    // only the atoms within rc + skin of the home box staged.
+    struct ListFit { bool ok; int cap, qcap; bool compact; };
+    auto list_fit = [&](int cap_full, int ncs, bool allow_compact, ListFit *out) -> int {
+        const int nt = std::max(s->ntypes, 1);
+        *out = ListFit{false, cap_full, FL_QCAP, false};
+        if (!s->want_persistent) return EMDEE_OK;
+        for (int q : {FL_QCAP, FLP_QCAP_SMALL})
+            if ((q == FL_QCAP || allow_compact) && flp_smem_bytes(cap_full, ncs, nt, 2, 0, q) <= c->smem_optin) {
+                *out = ListFit{true, cap_full, q, false};
+                return EMDEE_OK;
+            }
+        if (!allow_compact || !s->want_compact || c->nranks != 1 || s->want_tma || s->want_n3 || ncs > FC_MAX_NCS_SMALL) return EMDEE_OK;
+        int ccap = 0;
+        EMDEE_TRY(brick_capacity_compact(s, &ccap));
+        for (int q : {FL_QCAP, FLP_QCAP_SMALL})
+            if (ccap < 65534 && flp_smem_bytes(ccap, ncs, nt, 2, 0, q) <= c->smem_optin) { *out = ListFit{true, ccap, q, true}; return EMDEE_OK; }
+        return EMDEE_OK;
+    };
+    auto finish = [&](int cap, int block, int lblock, int rowmax, ListFit lf) -> int {
         s->fc_cap = cap;
+        s->fl_cap = lf.ok ? lf.cap : cap;
+        s->fl_qcap = lf.ok ? lf.qcap : FL_QCAP;
+        s->fl_compact = lf.ok && lf.compact;
         s->fc_rowmax = rowmax;
         // 32-atom groups per brick from the densest cell, with head-room so that density fluctuations between
         // re-binnings do not resize the pair list
@@ -1061,11 +1114,11 @@ static int choose_bricks(emdee_system *s)
         s->fc_smem = fc_smem_bytes(cap, s->fc_ncs, block, typed);
         s->fl_block = lblock;
         s->fl_smem = fl_smem_bytes(cap, s->fc_ncs, lblock, std::max(s->ntypes, 1));
-        s->fl_persistent = s->want_persistent && flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin;
+        s->fl_persistent = lf.ok;
         // TMA staging: the x image of a staged atom is resolved against its segment's centre, so a segment must span less than
         // half the box; the raw ring (two groups of whole rows) must fit behind the stacks
         s->fl_tma = false;
-        if (s->fl_persistent && s->want_tma && !s->want_n3 && 2 * (g.bx + 2 * R + 1) <= g.M && rowmax > 0) {
+        if (s->fl_persistent && !s->fl_compact && s->fl_qcap == FL_QCAP && s->want_tma && !s->want_n3 && 2 * (g.bx + 2 * R + 1) <= g.M && rowmax > 0) {
             const int nrows = (g.by + 2 * R) * (g.bz + 2 * R), rowpad = (rowmax + 5) & ~1;
             const size_t base = flp_smem_bytes(cap, s->fc_ncs, std::max(s->ntypes, 1), 2) + 2 * (size_t)(2 * nrows) * sizeof(int4) + 64;
             if (base < c->smem_optin) {
@@ -1088,8 +1141,11 @@ static int choose_bricks(emdee_system *s)
         if (!s->pre_valid) EMDEE_TRY(brick_capacity(s, &cap, &rowmax));
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const size_t need = listed ? fl_smem_bytes(cap, ncs, s->fl_block, std::max(s->ntypes, 1)) : fc_smem_bytes(cap, ncs, s->fc_block, typed);
-        if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin)
-            return finish(cap, s->fc_block, s->fl_block, rowmax);
+        ListFit lf = {false, cap, FL_QCAP, false};
+        if (listed) EMDEE_TRY(list_fit(cap, ncs, s->fl_compact || s->fl_qcap != FL_QCAP, &lf));
+        if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin &&
+            (!listed || (lf.ok == s->fl_persistent && lf.compact == s->fl_compact && lf.qcap == s->fl_qcap)))
+            return finish(cap, s->fc_block, s->fl_block, rowmax, lf);
     }
     // shapes in units of ndiv cells (a cell edge is (rc + skin)/ndiv), so the candidates keep their physical size
     static const int base_shapes[][3] = {{8, 2, 2}, {4, 4, 2}, {7, 2, 2}, {5, 3, 2}, {6, 2, 2}, {4, 3, 2}, {5, 2, 2}, {3, 3, 2}, {8, 2, 1}, {4, 4, 1},
@@ -1110,6 +1166,10 @@ static int choose_bricks(emdee_system *s)
     int best_shape[3] = {0, 0, 0}, best_block = 0, best_lblock = 192, best_cap = 0, best_rowmax = 0;
     size_t best_budget = 0;
     const int nshape = forced[0] > 0 ? 1 : nshapes_all;
+    ListFit best_lf = {false, 0, FL_QCAP, false};
+    // second pass (dense cells): no shape fits the persistent kernel as it is -- allow shallower stacks and compacted staging
+    for (int pass = 0; pass < 2; pass++) {
+    if (pass == 1 && (!listed || !s->want_persistent || best_lf.ok)) break;
     int prev[3] = {-1, -1, -1};
     for (int k = 0; k < nshape; k++) {
         const int *sh = forced[0] > 0 ? forced : shapes[k];
@@ -1127,7 +1187,10 @@ static int choose_bricks(emdee_system *s)
             // the stepping kernel decides, as long as k_force_cells (single-point evaluations) fits too
             const int cblock = cells_block(cap, ncs, forced_block);
             if (!cblock) continue;
-            if (s->want_persistent && flp_smem_bytes(cap, ncs, std::max(s->ntypes, 1), 2) <= c->smem_optin) {
+            ListFit lf;
+            EMDEE_TRY(list_fit(cap, ncs, pass == 1, &lf));
+            if (pass == 1 && !lf.ok) continue;
+            if (lf.ok) {
                 // persistent kernel (two staging buffers).  Cost model per home atom, fitted to B200 measurements
                 // (4x2x2 / 3x2x2 / 4x3x2 / 5x2x2 bricks at skins 0.35-0.5): the consumers' time is 1 / fill, where a brick period
                 // lasts ceil(groups / consumer warps) warp-task times (13 groups on 12 consumers: 1.55 ms per launch against
@@ -1136,8 +1199,9 @@ static int choose_bricks(emdee_system *s)
                 const double fill = groups / (std::ceil(groups / FLP_NCONS) * FLP_NCONS);
                 // (a factor for bricks that stick out of the grid -- a slab of 7 planes cut into layers of 2 -- was tried at 8 GPUs: it
                 // picks 4x4x1 bricks there, 0.252 ms per launch against 0.240 ms for 4x2x2 with a half-filled last layer: not kept)
-                const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) + 1.0 / fill);
+                const double score = 1e6 + 1000.0 / (0.025 * ncs / (g.bx * g.by * g.bz) * ((double)lf.cap / cap) + 1.0 / fill);
                 if (score > best_score) {
+                    best_lf = lf;
                     best_score = score; best_block = cblock; best_lblock = 192; best_cap = cap; best_rowmax = rowmax;
                     best_shape[0] = g.bx; best_shape[1] = g.by; best_shape[2] = g.bz;
                     best_budget = c->smem_optin;
@@ -1187,16 +1251,18 @@ static int choose_bricks(emdee_system *s)
             }
         }
     }
+    }
     if (best_score < 0) EMDEE_FAIL(EMDEE_ERR_CAPACITY, "emdee_bin: no brick shape fits shared memory (cells too populated); use a larger ndiv");
     set_brick_shape(s, best_shape);
     if (getenv("EMDEE_DEBUG"))
-        fprintf(stderr, "[emdee] bricks %dx%dx%d block %d list-block %d cap %d (full search, per_cell %.1f, maxpop %d, listed %d)\n", best_shape[0],
-                best_shape[1], best_shape[2], best_block, best_lblock, best_cap, per_cell, maxpop, (int)listed);
+        fprintf(stderr, "[emdee] bricks %dx%dx%d block %d list-block %d cap %d (full search, per_cell %.1f, maxpop %d, listed %d; persistent %d: cap %d, stack %d, compacted %d)\n",
+                best_shape[0], best_shape[1], best_shape[2], best_block, best_lblock, best_cap, per_cell, maxpop, (int)listed, (int)best_lf.ok, best_lf.cap, best_lf.qcap,
+                (int)best_lf.compact);
     for (int k = 0; k < 3; k++) s->fc_shape[k] = best_shape[k];
     s->fc_per_cell = per_cell;
     s->fc_R = R;
     s->fc_smem_budget = std::min(best_budget, c->smem_optin);
-    return finish(best_cap, best_block, best_lblock, best_rowmax);
+    return finish(best_cap, best_block, best_lblock, best_rowmax, best_lf);
 }
 
 static int do_bin(emdee_system *s, int ndiv)
@@ -1665,7 +1731,7 @@ static int launch_build_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
     auto kern = s->build_n3 ? k_list_build<EXCL, true> : k_list_build<EXCL, false>;
-    const size_t smem = lb_smem_bytes(s->fc_cap, s->fc_ncs, LB_MAX_BLOCK, EXCL);
+    const size_t smem = lb_smem_bytes(a.cap, s->fc_ncs, LB_MAX_BLOCK, EXCL);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nblocks, LB_MAX_BLOCK, smem, s->ctx->stream>>>(a);
     s->ctx->launches++;
@@ -1699,7 +1765,7 @@ static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool s
         kern = k_force_list_p<MULTI, false, 2, true, true, false, false, false, true>;
     else
         tma = false;
-    const size_t smem = flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, n3 ? s->fc_gmax : 0) +
+    const size_t smem = flp_smem_bytes(a.cap, s->fc_ncs, std::max(s->ntypes, 1), 2, n3 ? s->fc_gmax : 0, s->fl_qcap) +
                         (tma ? flp_tma_bytes(s->segcap, s->rawlen) : 0);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // while a halo exchange is in flight the persistent blocks leave a few SMs to NCCL's kernel (each block holds all
@@ -1810,7 +1876,7 @@ extern "C" int emdee_fp16_threshold(const double half_extent[3], double rcut, fl
 // bits, and the accumulators fit next to the two staging buffers
 static bool n3_usable(const emdee_system *s)
 {
-    return s->want_n3 && s->fl_persistent && s->fc_gmax * 32 < 2047 &&
+    return s->want_n3 && s->fl_persistent && !s->fl_compact && s->fl_qcap == FL_QCAP && s->fc_gmax * 32 < 2047 &&
            flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, s->fc_gmax) <= s->ctx->smem_optin;
 }
 
@@ -1863,7 +1929,14 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
         const double rl = s->cutoff + s->skin;
         a.rl2f = (float)(rl * rl * (1.0 + 1e-4) + 64.0 * 1.2e-7 * cmax2);
     }
-    a.cap = s->fc_cap;
+    // staged-atom capacity: the list kernels of a persistent configuration may stage a compacted brick (fl_cap < fc_cap)
+    a.cap = (mode != 0 && s->fl_persistent) ? s->fl_cap : s->fc_cap;
+    a.qcap = s->fl_qcap;
+    a.compact = (mode != 0 && s->fl_persistent && s->fl_compact) ? 1 : 0;
+    {
+        const double rl = s->cutoff + s->skin;
+        a.keep2 = rl * rl * (1.0 + 1e-6);
+    }
     a.ncs_max = s->fc_ncs;
     a.err = s->err;
     a.list8 = s->list8; a.list_n = s->list_n; a.gmax = s->fc_gmax; a.lcap8 = s->lcap8;
@@ -1904,7 +1977,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
             EMDEE_TRY(dev_alloc(&s->list_n, (size_t)s->list_slots * 32));
             a.list8 = s->list8; a.list_n = s->list_n;
         }
-        const int64_t rneed = (int64_t)s->fc_nblocks * (s->fc_cap + 1);
+        const int64_t rneed = (int64_t)s->fc_nblocks * (a.cap + 1);
         if (rneed > s->recipe_cap) {
             dev_free(s->recipe);
             s->recipe_cap = rneed + rneed / 8;
@@ -1915,7 +1988,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
             s->hdr_cap = s->fc_nblocks + s->fc_nblocks / 4;
             EMDEE_TRY(dev_alloc(&s->brickhdr, (size_t)2 * s->hdr_cap));
         }
-        a.recipe = s->recipe; a.homeidx = s->homeidx; a.brickhdr = s->brickhdr; a.rcap = s->fc_cap + 1;
+        a.recipe = s->recipe; a.homeidx = s->homeidx; a.brickhdr = s->brickhdr; a.rcap = a.cap + 1;
         if ((mode == 2 || mode == 3) && s->lm != 0) {
             if (s->inner_slots < s->list_slots || s->inner_lcap8 != s->lcap8) {
                 if (s->lm == 2) EMDEE_FAIL(EMDEE_ERR_STATE, "run_cells: no inner list to replay");
@@ -2635,9 +2708,11 @@ extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
     out[0] = s->grid_ok ? s->g.bx : 0;
     out[1] = s->grid_ok ? s->g.by : 0;
     out[2] = s->grid_ok ? s->g.bz : 0;
-    out[3] = s->grid_ok ? s->fc_cap : 0;
+    out[3] = s->grid_ok ? s->fc_cap : 0;      // (full staging; a compacted persistent configuration stages fl_cap atoms)
     out[4] = listed ? 1 : 0;
-    out[5] = listed && s->fl_persistent ? (1 | (s->fl_tma ? 2 : 0)) : 0;      // bit 1: staging by bulk asynchronous copies (EMDEE_TMA=1)
+    // bit 1: staging by bulk asynchronous copies (EMDEE_TMA=1); bit 2: compacted staging (dense cells); bit 3: shallow stacks
+    out[5] = listed && s->fl_persistent ? (1 | (s->fl_tma ? 2 : 0) | (s->fl_compact ? 4 : 0) | (s->fl_qcap != FL_QCAP ? 8 : 0)) : 0;
+    if (listed && s->fl_persistent) out[3] = s->fl_cap;
     out[6] = listed && s->fl_persistent && s->fuse_vv && s->n14 == 0 && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
     out[7] = s->lcap8;
     return EMDEE_OK;

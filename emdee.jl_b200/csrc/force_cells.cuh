@@ -39,6 +39,7 @@
 #define FC_MAX_HOMEROWS 64  // by*bz of the largest supported brick
 #define FC_MAX_TYPES 16     // LJ parameter classes held as a pair table in shared memory
 
+#define FC_MAX_NCS_SMALL 512   // staged cells of the bricks k_brick_keep_max handles (static tables)
 #define FC_DIMTAB 96         // 3 x 32 doubles: a staged dimension has at most 32 cells
 
 #define FC_MAX_BLOCK 384     // launch bound: 12 warps, up to 170 registers per thread
@@ -81,6 +82,12 @@ struct CellArgs {
     uint4 *inner8;
     int *inner_n;
     float rp2h;
+    int qcap;                         // per-lane stack entries of k_force_list_p
+    // compacted staging (dense cells): k_list_build keeps only the staged atoms within rc + skin of the brick's home box
+    // (about 76 % of the 27 cells around a one-cell brick) and numbers them in staging order; the recipe it writes lists those
+    // atoms only, so k_force_list_p stages the compacted brick without knowing about it
+    int compact;
+    double keep2;                     // (rc + skin)^2 with a margin for rounding
     unsigned *vv_maxstep;             // fused integrator: max over atoms of |r(n+1) - r(n)|^2 (float bits; the host resets it at a prune step)
     // staging recipe, written by k_list_build and valid until the next re-binning (the persistent kernel stages from it
     // instead of rebuilding the cell table on every step):

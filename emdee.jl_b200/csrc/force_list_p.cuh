@@ -59,11 +59,11 @@ __host__ __device__ inline size_t flp_buf_bytes(int cap, int ncs_max, int ntypes
 }
 // nbuf staging buffers; the per-lane stacks shrink to 24 entries when three buffers are wanted (a brick period is
 // set by its slowest warp task, a third buffer lets the other warps run ahead instead of waiting for it)
-__host__ __device__ inline int flp_qcap(int nbuf) { return nbuf >= 3 ? 24 : FL_QCAP; }
-__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf, int n3_groups = 0)
+#define FLP_QCAP_SMALL 24     // stack depth the host falls back to when two buffers do not fit next to FL_QCAP entries per lane
+__host__ __device__ inline size_t flp_smem_bytes(int cap, int ncs_max, int ntypes, int nbuf, int n3_groups = 0, int qcap = FL_QCAP)
 {
     return nbuf * flp_buf_bytes(cap, ncs_max, ntypes, n3_groups) + (size_t)ntypes * ntypes * sizeof(double2) +
-           (size_t)(flp_qcap(nbuf) + 1) * FLP_QS * sizeof(uint16_t) +
+           (size_t)(qcap + 1) * FLP_QS * sizeof(uint16_t) +
            128;     // (head-room for the kernel's static shared memory -- barriers, brick claims -- which counts against the same limit)
 }
 
@@ -236,7 +236,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
     static_assert(LM == 0 || (ILP == 4 && FUSE && !N3 && !EW && (LM == 2 || !COUNT)), "the two-level list is a variant of the fused stepping kernel");
-    constexpr int QCAP = NBUF >= 3 ? 24 : FL_QCAP;
+    const int QCAP = a.qcap;          // per-lane stack entries (FL_QCAP; FLP_QCAP_SMALL where shared memory is short: dense cells)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap1 = a.cap + 1;

@@ -39,9 +39,66 @@ __host__ __device__ inline size_t lb_smem_bytes(int cap, int ncs_max, int block,
     b += (size_t)(ncs_max + 1) * sizeof(int) * 3;          // cs[], gbase[], ccoord[]
     b += 2 * (FC_MAX_HOMEROWS + 1) * sizeof(int);          // hstart[], tstart[]
     b += 8 * sizeof(int);
+    b += (size_t)(ncs_max + 1) * sizeof(int);              // cfull[]: atoms of every staged cell before compaction
     b = (b + 15) & ~(size_t)15;
     b += (size_t)block * LB_ROW_BYTES;
     return b;
+}
+
+// ---- compacted staging (CellArgs::compact) ----------------------------------------------------------------------------------
+// Position of the atom in global slot `slot` of staged cell t in the brick's frame (the arithmetic of stage_atoms), and whether
+// it lies within rc + skin of the brick's home box: only such atoms can be a partner of a home atom.
+struct BrickFrame {
+    double bcx, bcy, bcz;       // scaled centre of the home box
+    double hx, hy, hz;          // half extents of the home box (length units)
+};
+__device__ __forceinline__ BrickFrame brick_frame(const CellArgs &a, const BrickGeom &bg)
+{
+    const GridDesc &g = a.g;
+    const int uz0 = (g.zwrap ? bg.hz0 : g.zglob0 + bg.hz0);
+    BrickFrame f;
+    f.bcx = ((double)bg.hx0 + 0.5 * bg.nhx) / g.M; f.bcy = ((double)bg.hy0 + 0.5 * bg.nhy) / g.M; f.bcz = ((double)uz0 + 0.5 * bg.nhz) / g.M;
+    f.hx = 0.5 * bg.nhx * a.cell_edge; f.hy = 0.5 * bg.nhy * a.cell_edge; f.hz = 0.5 * bg.nhz * a.cell_edge;
+    return f;
+}
+__device__ __forceinline__ bool staged_keep(const CellArgs &a, const BrickFrame &f, const double *ctab, int cc, int slot, double &px, double &py, double &pz)
+{
+    const double cx = ctab[cc & 255], cy = ctab[32 + ((cc >> 8) & 255)], cz = ctab[64 + (cc >> 16)];
+    double dx = a.sx[slot] - cx, dy = a.sy[slot] - cy, dz = a.sz[slot] - cz;
+    dx -= rint_magic(dx); dy -= rint_magic(dy); dz -= rint_magic(dz);
+    px = a.L * (dx + (cx - f.bcx)); py = a.L * (dy + (cy - f.bcy)); pz = a.L * (dz + (cz - f.bcz));
+    const double ex = fmax(fabs(px) - f.hx, 0.0), ey = fmax(fabs(py) - f.hy, 0.0), ez = fmax(fabs(pz) - f.hz, 0.0);
+    return fma(ez, ez, fma(ey, ey, ex * ex)) <= a.keep2;
+}
+// atoms of staged cell t that are kept (one warp; every lane returns the count)
+__device__ __forceinline__ int count_kept(const CellArgs &a, const BrickFrame &f, const double *ctab, int cc, int slot0, int n, int lane)
+{
+    int cnt = 0;
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        double px, py, pz;
+        const bool keep = k0 + lane < n && staged_keep(a, f, ctab, cc, slot0 + k0 + lane, px, py, pz);
+        cnt += __popc(__ballot_sync(0xffffffffu, keep));
+    }
+    return cnt;
+}
+// largest number of kept atoms over all bricks (one block per brick): the staged-atom capacity of the compacted list kernels
+__global__ void __launch_bounds__(256) k_brick_keep_max(CellArgs a, int *out)
+{
+    __shared__ int cs[FC_MAX_NCS_SMALL], gbase[FC_MAX_NCS_SMALL], ccoord[FC_MAX_NCS_SMALL];
+    __shared__ double ctab[FC_DIMTAB];
+    __shared__ int total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const BrickGeom bg = brick_geom(a.g, (int)blockIdx.x);
+    if (bg.ncs > FC_MAX_NCS_SMALL) { if (tid == 0) atomicMax(out, 1 << 30); return; }      // (not a one-cell-class brick: no compaction)
+    if (tid == 0) total = 0;
+    stage_cell_table(a, bg, cs, gbase, ccoord, ctab, tid, (int)blockDim.x);
+    __syncthreads();
+    const BrickFrame f = brick_frame(a, bg);
+    int mine = 0;
+    for (int t = warp; t < bg.ncs; t += (int)blockDim.x >> 5) mine += count_kept(a, f, ctab, ccoord[t], gbase[t], cs[t], lane);
+    if (lane == 0) atomicAdd(&total, mine);
+    __syncthreads();
+    if (tid == 0) atomicMax(out, total);
 }
 
 // N3 (Newton's third law inside the brick): a pair of two HOME atoms of the brick is listed once, by the atom with the smaller
@@ -64,7 +121,8 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
     int *hstart = ccoord + (a.ncs_max + 1);
     int *tstart = hstart + (FC_MAX_HOMEROWS + 1);
     int *scal = tstart + (FC_MAX_HOMEROWS + 1);
-    unsigned char *rows = smem_raw + ((reinterpret_cast<unsigned char *>(scal + 8) - smem_raw + 15) & ~(size_t)15);
+    int *cfull = scal + 8;
+    unsigned char *rows = smem_raw + ((reinterpret_cast<unsigned char *>(cfull + (a.ncs_max + 1)) - smem_raw + 15) & ~(size_t)15);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int R = g.R;
@@ -80,6 +138,16 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         for (int q = tid; q < npairrec; q += blockDim.x) hp[q] = make_uint4(fu, fu, fu, 0u);
     }
     __syncthreads();
+    const BrickFrame frame = brick_frame(a, bg);
+    if (a.compact) {
+        // compaction, pass A: cs[t] = atoms of staged cell t within rc + skin of the home box (cfull[t] keeps the cell's population)
+        for (int t = warp; t < ncs; t += (int)blockDim.x >> 5) {
+            const int n = cs[t];
+            const int kept = count_kept(a, frame, ctab, ccoord[t], gbase[t], n, lane);
+            if (lane == 0) { cfull[t] = n; cs[t] = kept; }
+        }
+        __syncthreads();
+    }
     if (warp == 0) {
         int run = 0;
         for (int base = 0; base < ncs; base += 32) {
@@ -121,7 +189,7 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
 
     __half *hph = reinterpret_cast<__half *>(hp);
     int2 *recipe = a.recipe + (size_t)bid * a.rcap;
-    stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, tid, (int)blockDim.x, [&](int idx, int slot, int ccode, double px, double py, double pz) {
+    auto store_atom = [&](int idx, int slot, int ccode, double px, double py, double pz) {
         __half *rec = hph + (idx >> 1) * 8 + (idx & 1);
         rec[0] = __float2half_rn((float)px);
         rec[2] = __float2half_rn((float)py);
@@ -137,7 +205,24 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
             }
         }
         if (idx + 1 < a.rcap) recipe[idx + 1] = make_int2(slot, code);
-    });
+    };
+    if (a.compact) {
+        // compaction, pass B: the kept atoms of every staged cell in their (cell, id) order, numbered from the cell's new prefix
+        for (int t = warp; t < ncs; t += (int)blockDim.x >> 5) {
+            const int n = cfull[t], cc = ccoord[t];
+            int run = cs[t];
+            for (int k0 = 0; k0 < n; k0 += 32) {
+                double px = 0, py = 0, pz = 0;
+                const int slot = gbase[t] + k0 + lane;
+                const bool keep = k0 + lane < n && staged_keep(a, frame, ctab, cc, slot, px, py, pz);
+                const unsigned m = __ballot_sync(0xffffffffu, keep);
+                const int idx = run + __popc(m & ((1u << lane) - 1u));
+                if (keep && idx < nstaged) store_atom(idx, slot, cc, px, py, pz);
+                run += __popc(m);
+            }
+        }
+    } else
+        stage_atoms(a, bg, cs, gbase, ccoord, ctab, 0, nstaged, tid, (int)blockDim.x, store_atom);
     if (a.seg) {
         // segment table for the TMA staging of k_force_list_p: every staged (y, z) row is one contiguous slot range, two at the
         // periodic seam in x; bulk copies need 16-byte alignment, so a segment starts at the even slot at or below its first

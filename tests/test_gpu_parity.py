@@ -284,6 +284,38 @@ def test_two_level_list(em, oracle, skin2, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("compact", [1, 0])
+def test_dense_cells_compacted_staging(em, oracle, compact, monkeypatch):
+    """Dense cells (rc = 5 sigma: ~150 atoms per cell, ~440 pairs per atom): the 27 cells around a one-cell brick do not fit twice in
+    shared memory, so the persistent list kernel stages a COMPACTED brick -- k_list_build keeps the atoms within rc + skin of the
+    home box and writes the recipe for those only (EMDEE_COMPACT=0: the block-per-brick kernel as before).  Single point through
+    the list kernels, then stepping: forces, E, W, pair digest and the evaluated pair count against the oracle."""
+    monkeypatch.setenv("EMDEE_COMPACT", str(compact))
+    pos, L = em.workloads.fcc_lattice(10)               # L = 16.8: three cells of edge 5.6 per dimension
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 5.0, 4.0, atoms)
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_masses(np.ones(N))
+    s.set_skin(0.5)
+    s.bin(1)
+    cfg = s.step_config()
+    assert cfg["brick"] == (1, 1, 1) and cfg["pair_list"]
+    assert cfg["persistent"] == bool(compact) and cfg["compacted"] == bool(compact), cfg
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 5.0, 4.0, atoms, ndiv=1, fast=True)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]), "single point")
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    s.compute(em.CUTOFF, em.FORCES)
+    for nsteps, every in ((1, 5), (3, 5), (6, -1)):
+        s.vv_step(0.005, nsteps, rebin_every=every)
+        s.synchronize()
+        ref = oracle.cutoff_cells(s.positions(), L, 5.0, 4.0, atoms, ndiv=1, bitmask=1, fast=True)
+        assert s.list_pair_count() == ref["npairs"], (nsteps, every)
+        assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"]), (nsteps, every)
+    s.close()
+
+
 def test_config1_both_modes(em, oracle):
     """Config 1 checked in ALLPAIRS_REFERENCE mode as well."""
     pos, L = em.workloads.fcc_lattice(10)
