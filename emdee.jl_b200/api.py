@@ -359,7 +359,7 @@ class NonbondedSystem:
         o = np.zeros(8, dtype=np.int32)
         call("emdee_get_step_config", self._h, _ptr(o))
         return dict(brick=(int(o[0]), int(o[1]), int(o[2])), brick_capacity=int(o[3]), pair_list=bool(o[4]),
-                    persistent=bool(o[5] & 1), tma=bool(o[5] & 2), compacted=bool(o[5] & 4), shallow_stacks=bool(o[5] & 8),
+                    persistent=bool(o[5] & 1), tma=bool(o[5] & 2), compacted=bool(o[5] & 4), shallow_stacks=bool(o[5] & 8), split_lists=bool(o[5] & 16),
                     fused_vv=bool(o[6]), list_chunks=int(o[7]))
 
     def step_counters(self):

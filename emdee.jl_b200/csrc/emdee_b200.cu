@@ -184,6 +184,8 @@ struct emdee_system {
     // one-cell brick do not fit twice) k_list_build keeps only the atoms within rc + skin of the home box, see CellArgs::compact
     int fl_cap = 0, fl_qcap = FL_QCAP;
     bool fl_compact = false, want_compact = true;
+    // two lanes of the persistent kernel per home atom (split lists): bricks with at most half as many warp tasks as consumer warps
+    bool fl_split = false, want_split = true;
     bool fl_fuse = true;                                  // walk and drain share a basic block
     int reserve_sms = 0, nccl_sms = 4;                    // SMs left free for NCCL during the interior launch of a slab step (EMDEE_NCCL_SMS).
                                                           // With bricks claimed dynamically every SM is busy until the launch ends, so NCCL's kernel would
@@ -503,6 +505,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_TMA")) s->want_tma = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_SKIN2")) s->skin2 = std::max(0.0, atof(e));
     if (const char *e = getenv("EMDEE_COMPACT")) s->want_compact = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_SPLIT")) s->want_split = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
     s->nown = N;
@@ -1087,7 +1090,7 @@ static int choose_bricks(emdee_system *s)
         *out = ListFit{false, cap_full, FL_QCAP, false};
         if (!s->want_persistent) return EMDEE_OK;
         for (int q : {FL_QCAP, FLP_QCAP_SMALL})
-            if ((q == FL_QCAP || allow_compact) && flp_smem_bytes(cap_full, ncs, nt, 2, 0, q) <= c->smem_optin) {
+            if ((q == FL_QCAP || (allow_compact && c->nranks == 1)) && flp_smem_bytes(cap_full, ncs, nt, 2, 0, q) <= c->smem_optin) {
                 *out = ListFit{true, cap_full, q, false};
                 return EMDEE_OK;
             }
@@ -1106,7 +1109,10 @@ static int choose_bricks(emdee_system *s)
         s->fc_rowmax = rowmax;
         // 32-atom groups per brick from the densest cell, with head-room so that density fluctuations between
         // re-binnings do not resize the pair list
-        const int gmax = (g.bx * g.by * g.bz * (std::max(maxpop, 1) + 8) + 31) / 32 + 1;
+        // split lists (two lanes per home atom) where a brick has too few warp tasks to occupy the consumer warps of two buffers
+        s->fl_split = lf.ok && s->want_split && !s->want_n3 && !s->want_tma && c->nranks == 1 &&
+                      std::ceil(1.03 * per_cell * g.bx * g.by * g.bz / 32.0) <= FLP_NCONS / 2;
+        const int gmax = ((g.bx * g.by * g.bz * (std::max(maxpop, 1) + 8) << (s->fl_split ? 1 : 0)) + 31) / 32 + 1;
         if (gmax > s->fc_gmax || gmax * 2 < s->fc_gmax) s->fc_gmax = gmax;
         s->list_valid = false;
         s->fc_ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
@@ -1750,16 +1756,22 @@ template <bool MULTI, bool COUNT, bool EW>
 static int launch_list_p(emdee_system *s, const CellArgs &a, int nblocks, bool store_f)
 {
     auto kern = s->fl_fuse ? k_force_list_p<MULTI, COUNT, 2, EW, true> : k_force_list_p<MULTI, COUNT, 2, EW, false>;
+    // dense cells (shallow stacks and / or split lists): the variants that read both from the launch arguments
+    const bool dense = s->fl_split || s->fl_qcap != FL_QCAP;
+    if (dense) kern = k_force_list_p<MULTI, COUNT, 2, EW, true, false, false, false, false, 0, true>;
     const bool n3 = !COUNT && !EW && s->vv_mode != 0 && s->list_n3;
     bool tma = s->fl_tma && a.seg != nullptr && !n3;      // the stepping variants and the single-point F/E/W variant have a TMA form
     if (!COUNT && !EW && s->vv_mode != 0) {
         if (n3) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, true>;
         else if (tma) kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true, false, true> : k_force_list_p<MULTI, false, 2, false, true, true, false, false, true>;
+        else if (dense) kern = k_force_list_p<MULTI, false, 2, false, true, true, false, false, false, 0, true>;
         else if (s->lm == 1 && !s->p2p_launch) kern = k_force_list_p<MULTI, false, 2, false, true, true, false, false, false, 1>;
         else if (s->lm == 2 && !s->p2p_launch) kern = k_force_list_p<MULTI, false, 2, false, true, true, false, false, false, 2>;
         else kern = s->p2p_launch ? k_force_list_p<MULTI, false, 2, false, true, true, true> : k_force_list_p<MULTI, false, 2, false, true, true, false>;
         s->counters[(n3 || tma || s->p2p_launch) ? 1 : 1 + s->lm]++;
-    } else if (COUNT && !EW && s->lm == 2)       // the audit counts through the inner list when the stepping kernel would replay it
+    } else if (dense)
+        tma = false;
+    else if (COUNT && !EW && s->lm == 2)       // the audit counts through the inner list when the stepping kernel would replay it
         { kern = k_force_list_p<MULTI, true, 2, false, true, false, false, false, false, 2>; tma = false; }
     else if (tma && !COUNT && EW && s->fl_fuse)
         kern = k_force_list_p<MULTI, false, 2, true, true, false, false, false, true>;
@@ -1876,7 +1888,7 @@ extern "C" int emdee_fp16_threshold(const double half_extent[3], double rcut, fl
 // bits, and the accumulators fit next to the two staging buffers
 static bool n3_usable(const emdee_system *s)
 {
-    return s->want_n3 && s->fl_persistent && !s->fl_compact && s->fl_qcap == FL_QCAP && s->fc_gmax * 32 < 2047 &&
+    return s->want_n3 && s->fl_persistent && !s->fl_compact && !s->fl_split && s->fl_qcap == FL_QCAP && s->fc_gmax * 32 < 2047 &&
            flp_smem_bytes(s->fc_cap, s->fc_ncs, std::max(s->ntypes, 1), 2, s->fc_gmax) <= s->ctx->smem_optin;
 }
 
@@ -1933,6 +1945,7 @@ static int run_cells(emdee_system *s, int bitmask, bool audit, int32_t *pairs, i
     a.cap = (mode != 0 && s->fl_persistent) ? s->fl_cap : s->fc_cap;
     a.qcap = s->fl_qcap;
     a.compact = (mode != 0 && s->fl_persistent && s->fl_compact) ? 1 : 0;
+    a.split = (mode != 0 && s->fl_persistent && s->fl_split) ? 1 : 0;
     {
         const double rl = s->cutoff + s->skin;
         a.keep2 = rl * rl * (1.0 + 1e-6);
@@ -2596,7 +2609,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 s->p2p_publish = (!last && !next_rebin) ? s->epoch : 0;     // a re-binning exchanges the ghosts itself
             }
             s->lm = 0;
-            if (inner_ok && !s->list_n3 && !s->fl_tma) {
+            if (inner_ok && !s->list_n3 && !s->fl_tma && !s->fl_split) {
                 const bool have = s->inner_gen != 0 && s->inner_gen == s->list_gen && s->steps_since_prune >= 1;
                 const double moved = (double)s->steps_since_prune * std::sqrt((double)step2max) * (1.0 + 1e-6);
                 s->lm = have && moved <= 0.5 * s->skin2 ? 2 : 1;
@@ -2710,8 +2723,8 @@ extern "C" int emdee_get_step_config(emdee_system *s, int32_t out[8])
     out[2] = s->grid_ok ? s->g.bz : 0;
     out[3] = s->grid_ok ? s->fc_cap : 0;      // (full staging; a compacted persistent configuration stages fl_cap atoms)
     out[4] = listed ? 1 : 0;
-    // bit 1: staging by bulk asynchronous copies (EMDEE_TMA=1); bit 2: compacted staging (dense cells); bit 3: shallow stacks
-    out[5] = listed && s->fl_persistent ? (1 | (s->fl_tma ? 2 : 0) | (s->fl_compact ? 4 : 0) | (s->fl_qcap != FL_QCAP ? 8 : 0)) : 0;
+    // bit 1: staging by bulk asynchronous copies (EMDEE_TMA=1); bit 2: compacted staging (dense cells); bit 3: shallow stacks; bit 4: split lists
+    out[5] = listed && s->fl_persistent ? (1 | (s->fl_tma ? 2 : 0) | (s->fl_compact ? 4 : 0) | (s->fl_qcap != FL_QCAP ? 8 : 0) | (s->fl_split ? 16 : 0)) : 0;
     if (listed && s->fl_persistent) out[3] = s->fl_cap;
     out[6] = listed && s->fl_persistent && s->fuse_vv && s->n14 == 0 && (c->nranks == 1 || s->peer_ok) ? 1 : 0;
     out[7] = s->lcap8;

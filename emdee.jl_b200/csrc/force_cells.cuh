@@ -87,6 +87,7 @@ struct CellArgs {
     // (about 76 % of the 27 cells around a one-cell brick) and numbers them in staging order; the recipe it writes lists those
     // atoms only, so k_force_list_p stages the compacted brick without knowing about it
     int compact;
+    int split;                        // 1: two lanes of the stepping kernel per home atom (few home atoms per brick: dense cells)
     double keep2;                     // (rc + skin)^2 with a margin for rounding
     unsigned *vv_maxstep;             // fused integrator: max over atoms of |r(n+1) - r(n)|^2 (float bits; the host resets it at a prune step)
     // staging recipe, written by k_list_build and valid until the next re-binning (the persistent kernel stages from it

@@ -231,12 +231,17 @@ __device__ __forceinline__ BrickBuf brick_buf(unsigned char *base, int cap, int 
 // number of rows for every lane, so it is written as coalesced 16-byte chunks.  LM = 2 replays that log on the following steps:
 // no FP16 test, no stack, one gather and the pair arithmetic per row.  The host switches back to LM = 1 before an atom can have
 // moved skin2 / 2 since the prune step (emdee_vv_step), so the evaluated pair set stays the oracle's on every step.
-template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false, bool TMA = false, int LM = 0>
+// DENSE (dense cells, see choose_bricks): the per-lane stack depth and the split of an atom's list over two lanes are run-time
+// arguments (a.qcap, a.split); as compile-time constants in the other instantiations they cost the hot loops no registers.
+template <bool MULTI, bool COUNT, int NBUF, bool EW, bool FUSE, bool VV = false, bool P2P = false, bool N3 = false, bool TMA = false, int LM = 0,
+          bool DENSE = false>
 __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
 {
     constexpr int ILP = FLP_ILP;
+    static_assert(!DENSE || (!P2P && !N3 && !TMA && LM == 0), "the dense-cell variants exist for the plain single-GPU kernels");
+    const int SPL = DENSE ? a.split : 0;
     static_assert(LM == 0 || (ILP == 4 && FUSE && !N3 && !EW && (LM == 2 || !COUNT)), "the two-level list is a variant of the fused stepping kernel");
-    const int QCAP = a.qcap;          // per-lane stack entries (FL_QCAP; FLP_QCAP_SMALL where shared memory is short: dense cells)
+    const int QCAP = DENSE ? a.qcap : FL_QCAP;      // per-lane stack entries (FLP_QCAP_SMALL where shared memory is short)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const GridDesc &g = a.g;
     const int cap1 = a.cap + 1;
@@ -305,9 +310,9 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 double mass[W], f3[W][3], v3[W][3], r3[W][3], rb3[W][3];
 #pragma unroll
                 for (int u = 0; u < W; u++) {
-                    const int h = h00 + u * PN + tid;
-                    ok[u] = h < vnh && (h >> 5) < a.gmax;
-                    slot[u] = ok[u] ? (int)a.homeidx[((size_t)vbid * a.gmax + (h >> 5)) * 32 + (h & 31)] : 1;
+                    const int h = h00 + u * PN + tid, hv = h << SPL;      // (split lists: home atom h is the virtual atoms 2h, 2h + 1)
+                    ok[u] = h < vnh && (hv >> 5) < a.gmax;
+                    slot[u] = ok[u] ? (int)a.homeidx[((size_t)vbid * a.gmax + (hv >> 5)) * 32 + (hv & 31)] : 1;
                 }
 #pragma unroll
                 for (int u = 0; u < W; u++) slot[u] = vrecipe[slot[u]].x;
@@ -548,7 +553,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 }
             }
             {   // the consumers claim this brick's tasks dynamically: bring every group's entry counts and first chunks into L2
-                const int ng = min((nh + 31) >> 5, a.gmax);
+                const int ng = min(((nh << SPL) + 31) >> 5, a.gmax);
                 for (int t = tid; t < ng * 8; t += PN) {      // 2 chunks x 512 B = 8 lines of 128 B per group
                     const size_t gs = (size_t)bid * a.gmax + (t >> 3);
                     const int part = t & 7;
@@ -699,7 +704,7 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
         const uint16_t *phome = B.phome;
         double *acc = B.acc;
         const int2 *recipe = a.recipe + (size_t)bid * a.rcap;
-        const int nh = B.scal[0];
+        const int nh = B.scal[0] << SPL;      // (virtual) home atoms: with split lists every home atom is two lanes
         const int ngroups = (nh + 31) >> 5;
         if (ngroups > a.gmax) atomicCAS(a.err, 0, 5);
         const int ntask = min(ngroups, a.gmax);
@@ -936,7 +941,13 @@ __global__ void FLP_BOUNDS k_force_list_p(CellArgs a, int nbricks, int store_f)
                 if (EW) { e = f3[3]; w = f3[4]; }
             }
             if (COUNT) npair += np;
-            if (active) {
+            bool writer = active;
+            if (SPL) {      // the two halves of an atom's list were evaluated by neighbouring lanes: the even one stores the sum
+                fx += __shfl_xor_sync(0xffffffffu, fx, 1); fy += __shfl_xor_sync(0xffffffffu, fy, 1); fz += __shfl_xor_sync(0xffffffffu, fz, 1);
+                if (EW) { e += __shfl_xor_sync(0xffffffffu, e, 1); w += __shfl_xor_sync(0xffffffffu, w, 1); }
+                writer = active && !(lane & 1);
+            }
+            if (writer) {
                 if (N3) {      // own sums join the reactions other lanes have added; the producers write the totals out
                     double *ai = acc + 3 * h;
                     atomicAdd(ai, fx); atomicAdd(ai + 1, fy); atomicAdd(ai + 2, fz);

@@ -256,11 +256,17 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
     {   // header and home list (home atom h -> staged index + 1)
         const int nh = hstart[nhy * nhz];
         if (tid == 0) { a.brickhdr[2 * bid] = nstaged + 1; a.brickhdr[2 * bid + 1] = nh; }
-        for (int h = tid; h < nh && (h >> 5) < a.gmax; h += blockDim.x) {
+        // (a.split = 1: every home atom is two consecutive "virtual" home atoms 2h, 2h + 1 -- two lanes of the stepping kernel --
+        // that share the atom's list chunk by chunk)
+        for (int h = tid; h < nh && (((h << a.split) + a.split) >> 5) < a.gmax; h += blockDim.x) {
             int hr = 0;
             while (hstart[hr + 1] <= h) hr++;
             const int hrow = (hr / nhy + R) * syn + (hr % nhy + R);
-            a.homeidx[((size_t)bid * a.gmax + (h >> 5)) * 32 + (h & 31)] = (uint16_t)(cs[hrow * sxn + R] + (h - hstart[hr]) + 1);
+            const uint16_t st = (uint16_t)(cs[hrow * sxn + R] + (h - hstart[hr]) + 1);
+            for (int par = 0; par <= a.split; par++) {
+                const int hv = (h << a.split) + par;
+                a.homeidx[((size_t)bid * a.gmax + (hv >> 5)) * 32 + (hv & 31)] = st;
+            }
         }
     }
     __syncthreads();
@@ -303,9 +309,11 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         }
         const int h = hstart[hr] + (me - cs[hrow * sxn + R]);
         EMDEE_CHECK(hr < nhy * nhz && me < nstaged && a0 >= cs[hrow * sxn + R] && cxb < sxn, a.err);
-        if ((h >> 5) >= a.gmax) { atomicCAS(a.err, 0, 5); break; }
-        const size_t gs = (size_t)bid * a.gmax + (h >> 5);
-        uint4 *lp = a.list8 + gs * a.lcap8 * 32 + (h & 31);
+        const int hv0 = h << a.split, hv1 = hv0 + a.split;       // the lane's virtual home atom(s)
+        if ((hv1 >> 5) >= a.gmax) { atomicCAS(a.err, 0, 5); break; }
+        const size_t gs = (size_t)bid * a.gmax + (hv0 >> 5), gs1 = (size_t)bid * a.gmax + (hv1 >> 5);
+        uint4 *lp = a.list8 + gs * a.lcap8 * 32 + (hv0 & 31);
+        uint4 *lp1 = a.list8 + gs1 * a.lcap8 * 32 + (hv1 & 31);  // split: odd chunks of the atom's list go to the second half
         int nchunks = 0;                    // chunks already in global memory
         // the lane's row is addressed by its 32-bit shared-memory address: a push is one st.shared.u16 and one add.
         // The compiler does not see these stores as memory accesses, which lets it batch the candidate loads of an
@@ -336,7 +344,8 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
                         }
                         v = make_uint4(e[0], e[1], e[2], e[3]);
                     }
-                    if (nchunks + c < a.lcap8) lp[(size_t)(nchunks + c) * 32] = v;
+                    const int cg = nchunks + c, ch = cg >> a.split;       // chunk of the atom's list, chunk of its half
+                    if (ch < a.lcap8) ((cg & a.split) ? lp1 : lp)[(size_t)ch * 32] = v;
                     else atomicCAS(a.err, 0, 5);
                 }
             }
@@ -411,7 +420,11 @@ __global__ void __launch_bounds__(LB_MAX_BLOCK, LB_MIN_BLOCKS) k_list_build(Cell
         {
             const int n = nchunks * 8 + ((int)(wsh - row_sh) >> 1);
             flush(false);
-            if (active) a.list_n[gs * 32 + (h & 31)] = (uint16_t)min(n, a.lcap8 * 8);
+            if (active && !a.split) a.list_n[gs * 32 + (h & 31)] = (uint16_t)min(n, a.lcap8 * 8);
+            if (active && a.split) {      // whole chunks per half (dropped and padding entries are zeros = the dummy atom)
+                a.list_n[gs * 32 + (hv0 & 31)] = (uint16_t)min(((nchunks + 1) >> 1) * 8, a.lcap8 * 8);
+                a.list_n[gs1 * 32 + (hv1 & 31)] = (uint16_t)min((nchunks >> 1) * 8, a.lcap8 * 8);
+            }
         }
     }
 }

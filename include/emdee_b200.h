@@ -181,7 +181,7 @@ int emdee_profile_kind(emdee_system *sys, int kind, double *ms, int64_t *launche
 /* Host-only: how the stepping path is configured after the last emdee_bin (what bench.py names as the dominant
  * kernel): out = {brick cells x, y, z, staged-atom capacity of a brick, list-capable (1: k_list_build + list walk,
  * 0: window scan on every step), persistent (bit 0: k_force_list_p instead of k_force_list, one block per brick; bit 1: bulk-copy
- * staging; bit 2: compacted staging -- only the atoms within rc + skin of the home box; bit 3: shallow per-lane stacks),
+ * staging; bit 2: compacted staging -- only the atoms within rc + skin of the home box; bit 3: shallow per-lane stacks; bit 4: split lists, two lanes per home atom),
  * velocity-Verlet fused into the stepping kernel (1/0), list chunks of 8 entries per atom}. */
 int emdee_get_step_config(emdee_system *sys, int32_t out[8]);
 
