@@ -16,8 +16,10 @@ metric  : LJ pair-interactions/s = (unique pairs i<j with r2 <= rc2, counted by 
 workload: c3 = LJ fluid N=4,000,000 (fcc 100^3), rc=2.5 sigma, rs=2.0, rho*=0.8442 -- the configuration
           BASELINE.json's target is quoted on; it fits one B200, and is strong-scaled over 1/2/4/8 GPUs.
 e2e     : the same metric through the C ABI with HOST buffers: positions in pinned host memory ->
-          emdee_set_positions (H2D) -> emdee_bin -> emdee_compute_nonbonded(F|E|V) -> forces, energies,
-          virials back to pinned host memory (D2H), every iteration inside the timed region.
+          emdee_set_positions (H2D) -> emdee_bin -> emdee_compute_nonbonded_into(F|E|V: the reference's call shape,
+          forces / energies / virials written to pinned host memory; chunks of z planes are copied out behind the
+          evaluation), every iteration inside the timed region.  Slab ranks move the id window of the atoms they own
+          (emdee_set_positions_range, emdee_compute_nonbonded, emdee_get_*_range).
 roofline: dominant kernel k_force_list_p (the pair-list stepping kernel, one launch per step); achieved =
           71 flop x pairs per launch / mean launch duration (CUDA events around every launch on the library's
           stream, emdee_profile_begin/end/kind); peak = DFMA throughput measured on this GPU in the same run

@@ -173,6 +173,13 @@ function berendsen!(s::NonbondedSystem, kT::Real, tau::Real, elapsed::Real; ndof
     return now, lambda
 end
 # how the stepping path is configured after bin!: (brick cells x,y,z, brick capacity, pair list?, persistent?, fused VV?, list chunks)
+# re-binnings and stepping launches by list mode (full walk, prune, replay) since the system was created
+function step_counters(s::NonbondedSystem)
+    o = zeros(Int64, 4)
+    check(ccall((:emdee_get_step_counters, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int64}), s.handle, o))
+    return o
+end
+
 function step_config(s::NonbondedSystem)
     o = zeros(Int32, 8)
     check(ccall((:emdee_get_step_config, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}), s.handle, o))
