@@ -183,7 +183,8 @@ struct emdee_system {
     // staged-atom capacity, stack depth and staging mode of the list kernels: with compaction (dense cells: the 27 cells around a
     // one-cell brick do not fit twice) k_list_build keeps only the atoms within rc + skin of the home box, see CellArgs::compact
     int fl_cap = 0, fl_qcap = FL_QCAP;
-    bool fl_compact = false, want_compact = true;
+    bool fl_compact = false;
+    int want_compact = 1;      // EMDEE_COMPACT: 0 never, 1 when nothing else fits (dense cells), 2 whenever the persistent kernel runs on one GPU
     // two lanes of the persistent kernel per home atom (split lists): bricks with at most half as many warp tasks as consumer warps
     bool fl_split = false, want_split = true;
     bool fl_fuse = true;                                  // walk and drain share a basic block
@@ -504,7 +505,7 @@ extern "C" int emdee_system_create(emdee_ctx *c, int64_t N, double L, emdee_syst
     if (const char *e = getenv("EMDEE_N3")) s->want_n3 = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_TMA")) s->want_tma = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_SKIN2")) s->skin2 = std::max(0.0, atof(e));
-    if (const char *e = getenv("EMDEE_COMPACT")) s->want_compact = atoi(e) != 0;
+    if (const char *e = getenv("EMDEE_COMPACT")) s->want_compact = atoi(e);
     if (const char *e = getenv("EMDEE_SPLIT")) s->want_split = atoi(e) != 0;
     if (const char *e = getenv("EMDEE_NCCL_SMS")) s->nccl_sms = std::max(0, atoi(e));
     s->cap = N + (c->nranks > 1 ? N / 4 + 1024 : 0);   // head-room for ghost copies in a slab decomposition
@@ -1092,14 +1093,19 @@ static int choose_bricks(emdee_system *s)
         for (int q : {FL_QCAP, FLP_QCAP_SMALL})
             if ((q == FL_QCAP || (allow_compact && c->nranks == 1)) && flp_smem_bytes(cap_full, ncs, nt, 2, 0, q) <= c->smem_optin) {
                 *out = ListFit{true, cap_full, q, false};
-                return EMDEE_OK;
+                break;
             }
-        if (!allow_compact || !s->want_compact || c->nranks != 1 || s->want_tma || s->want_n3 || ncs > FC_MAX_NCS_SMALL) return EMDEE_OK;
+        if (out->ok && s->want_compact < 2) return EMDEE_OK;
+        if (!(allow_compact || s->want_compact >= 2) || !s->want_compact || c->nranks != 1 || s->want_tma || s->want_n3 || ncs > FC_MAX_NCS_SMALL)
+            return EMDEE_OK;
         int ccap = 0;
         EMDEE_TRY(brick_capacity_compact(s, &ccap));
         for (int q : {FL_QCAP, FLP_QCAP_SMALL})
-            if (ccap < 65534 && flp_smem_bytes(ccap, ncs, nt, 2, 0, q) <= c->smem_optin) { *out = ListFit{true, ccap, q, true}; return EMDEE_OK; }
-        return EMDEE_OK;
+            if (ccap < 65534 && (q == FL_QCAP || allow_compact) && flp_smem_bytes(ccap, ncs, nt, 2, 0, q) <= c->smem_optin) {
+                *out = ListFit{true, ccap, q, true};
+                return EMDEE_OK;
+            }
+        return EMDEE_OK;      // (what the uncompacted attempt found, if anything)
     };
     auto finish = [&](int cap, int block, int lblock, int rowmax, ListFit lf) -> int {
         s->fc_cap = cap;
@@ -1148,7 +1154,7 @@ static int choose_bricks(emdee_system *s)
         const int ncs = (g.bx + 2 * R) * (g.by + 2 * R) * (g.bz + 2 * R);
         const size_t need = listed ? fl_smem_bytes(cap, ncs, s->fl_block, std::max(s->ntypes, 1)) : fc_smem_bytes(cap, ncs, s->fc_block, typed);
         ListFit lf = {false, cap, FL_QCAP, false};
-        if (listed) EMDEE_TRY(list_fit(cap, ncs, s->fl_compact || s->fl_qcap != FL_QCAP, &lf));
+        if (listed) EMDEE_TRY(list_fit(cap, ncs, (s->fl_compact && s->want_compact < 2) || s->fl_qcap != FL_QCAP, &lf));
         if (cap <= 65534 && need <= s->fc_smem_budget && fc_smem_bytes(cap, ncs, s->fc_block, typed) <= c->smem_optin &&
             (!listed || (lf.ok == s->fl_persistent && lf.compact == s->fl_compact && lf.qcap == s->fl_qcap)))
             return finish(cap, s->fc_block, s->fl_block, rowmax, lf);
@@ -1736,7 +1742,8 @@ template <bool EXCL>
 static int launch_build_t(emdee_system *s, const CellArgs &a, int nblocks)
 {
     if (nblocks <= 0) return EMDEE_OK;
-    auto kern = s->build_n3 ? k_list_build<EXCL, true> : k_list_build<EXCL, false>;
+    auto kern = s->build_n3 ? k_list_build_plain<EXCL, true> : k_list_build_plain<EXCL, false>;
+    if (a.split || a.compact) kern = k_list_build<EXCL, false, true>;      // (dense cells; never together with the half list)
     const size_t smem = lb_smem_bytes(a.cap, s->fc_ncs, LB_MAX_BLOCK, EXCL);
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<nblocks, LB_MAX_BLOCK, smem, s->ctx->stream>>>(a);
