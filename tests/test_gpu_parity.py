@@ -316,6 +316,31 @@ def test_dense_cells_compacted_staging(em, oracle, compact, monkeypatch):
     s.close()
 
 
+def test_config5_parameters(em, oracle):
+    """BASELINE config 5's model (rc = 3.0, rs = 2.5, rho* = 0.8442) at a size the oracle finishes in seconds (fcc 24^3 = 55,296 atoms):
+    single point (E, W, forces, pair digest) and the stepping path with adaptive re-binning (evaluated pair count and forces at the
+    final positions).  The full-size runs (N = 32,000,000 on 1 / 2 / 4 / 8 GPUs) carry the same checks in their bench lines."""
+    pos, L = em.workloads.fcc_lattice(24)
+    N = pos.shape[0]
+    atoms = em.workloads.lj_fluid_atoms(N)
+    s = make_system(em, pos, L, 3.0, 2.5, atoms)
+    s.set_velocities(em.workloads.maxwell_velocities(N, 1.44))
+    s.set_masses(np.ones(N))
+    s.set_skin(0.45)
+    s.bin(1)
+    s.compute(em.CUTOFF, 7)
+    ref = oracle.cutoff_cells(pos, L, 3.0, 2.5, atoms, ndiv=1, fast=True)
+    check_efw((s.forces(), s.energies(), s.virials()), (ref["forces"], ref["energies"], ref["virials"]), "config 5 single point")
+    assert np.array_equal(s.pair_set_digest(), ref["digest"])
+    s.compute(em.CUTOFF, em.FORCES)
+    s.vv_step(0.005, 15, rebin_every=-1)
+    s.synchronize()
+    ref = oracle.cutoff_cells(s.positions(), L, 3.0, 2.5, atoms, ndiv=1, bitmask=1, fast=True)
+    assert s.list_pair_count() == ref["npairs"]
+    assert np.abs(s.forces() - ref["forces"]).max() <= F_TOL * frms(ref["forces"])
+    s.close()
+
+
 def test_config1_both_modes(em, oracle):
     """Config 1 checked in ALLPAIRS_REFERENCE mode as well."""
     pos, L = em.workloads.fcc_lattice(10)
