@@ -29,6 +29,13 @@ def test_header_symbols_exported(em):
     assert set(syms) == bound
 
 
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md names every entry point the header declares (section 6: the reference symbol each one replaces)."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [name for name in declared_symbols() if "`%s`" % name not in text]
+    assert not missing, missing
+
+
 def test_no_cpu_fallback(em):
     import torch
 
