@@ -173,6 +173,13 @@ function berendsen!(s::NonbondedSystem, kT::Real, tau::Real, elapsed::Real; ndof
     return now, lambda
 end
 # how the stepping path is configured after bin!: (brick cells x,y,z, brick capacity, pair list?, persistent?, fused VV?, list chunks)
+synchronize(s::NonbondedSystem) = check(ccall((:emdee_synchronize, libemdee), Cint, (Ptr{Cvoid},), s.handle))
+# ids sorted by (cell, id) and the first slot of every cell (0-based), the order `Cells` is built from
+function cell_order(s::NonbondedSystem, M::Integer)
+    perm = zeros(Int32, s.N); start = zeros(Int32, M^3 + 1)
+    check(ccall((:emdee_get_cell_order, libemdee), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), s.handle, perm, start))
+    return perm, start
+end
 # re-binnings and stepping launches by list mode (full walk, prune, replay) since the system was created
 function step_counters(s::NonbondedSystem)
     o = zeros(Int64, 4)
