@@ -57,6 +57,11 @@ int main(void)
     int64_t npairs = 0;
     CHECK(emdee_get_totals(sys, &E, &W, &npairs));
     printf("cutoff: E %.12g  W %.12g  pairs %lld\n", E, W, (long long)npairs);
+    /* the reference's call shape on the resident system: the three output arrays are host memory, filled in one call */
+    CHECK(emdee_compute_nonbonded_into(sys, EMDEE_CUTOFF, EMDEE_FORCES | EMDEE_ENERGIES | EMDEE_VIRIALS, f, e, w));
+    E = 0;
+    for (int64_t i = 0; i < N; i++) E += e[i];
+    printf("cutoff, host arrays: sum of per-atom energies %.12g\n", E);
     CHECK(emdee_system_destroy(sys));
     CHECK(emdee_destroy(ctx));
     free(pos); free(atoms); free(f); free(e); free(w);
