@@ -2616,7 +2616,7 @@ extern "C" int emdee_vv_step(emdee_system *s, double dt, int64_t nsteps, int reb
                 s->p2p_publish = (!last && !next_rebin) ? s->epoch : 0;     // a re-binning exchanges the ghosts itself
             }
             s->lm = 0;
-            if (inner_ok && !s->list_n3 && !s->fl_tma && !s->fl_split) {
+            if (inner_ok && !s->list_n3 && !s->fl_tma && !s->fl_split && s->fl_qcap == FL_QCAP) {      // (the dense-cell kernels have no prune / replay form)
                 const bool have = s->inner_gen != 0 && s->inner_gen == s->list_gen && s->steps_since_prune >= 1;
                 const double moved = (double)s->steps_since_prune * std::sqrt((double)step2max) * (1.0 + 1e-6);
                 s->lm = have && moved <= 0.5 * s->skin2 ? 2 : 1;
